@@ -1,0 +1,197 @@
+/*
+ * unipose_b200.h — C-ABI of the B200-native (sm_100a) UniPose hot path.
+ *
+ * The reference (bmartacho/UniPose) is pure PyTorch and has no FFI of its own; every entry
+ * point below replaces the ATen/cuDNN operator that a reference `nn.Module.forward()` call
+ * dispatches to.  The citation beside each function names the reference call site
+ * (file:line under /root/reference) whose arithmetic the function implements.
+ *
+ * Conventions
+ *   - plain pointers + sizes; no torch types.  All pointers are DEVICE pointers unless named h_*.
+ *   - every function returns 0 on success or a negative UpStatus; `up_last_error()` returns a
+ *     thread-local human readable message.  Nothing throws across the ABI.
+ *   - all launches are asynchronous on the `stream` argument (a cudaStream_t passed as void*);
+ *     the library never synchronises and never allocates persistent device memory.
+ *   - activations are NHWC, 16-bit (bf16 or fp16).  In UP_SPLIT mode a tensor is TWO bf16
+ *     planes (hi, lo = bf16(x - hi)) `plane_stride` elements apart; GEMMs then run the three
+ *     bf16 products hi*hi + lo*hi + hi*lo with fp32 accumulation (fp32-grade results on the
+ *     bf16 tensor cores).  The user-facing tensors (input image, heat-maps, ConvLSTM states)
+ *     are fp32 NCHW exactly as in the reference.
+ */
+#ifndef UNIPOSE_B200_H_
+#define UNIPOSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UP_VERSION 100
+
+typedef enum UpStatus {
+  UP_OK = 0,
+  UP_ERR_INVALID = -1,   /* bad shape / alignment / flag combination */
+  UP_ERR_CUDA = -2,      /* CUDA runtime or driver call failed */
+  UP_ERR_UNSUPPORTED = -3
+} UpStatus;
+
+typedef enum UpDtype {
+  UP_BF16 = 0,  /* bf16 storage, one tensor-core pass */
+  UP_FP16 = 1,  /* fp16 storage, one tensor-core pass */
+  UP_SPLIT = 2  /* bf16 hi+lo planes, three tensor-core passes: fp32-grade ("parity") mode */
+} UpDtype;
+
+enum {
+  UP_FLAG_RELU = 1,          /* y = max(y, 0) after scale/shift(/residual) */
+  UP_FLAG_RESIDUAL = 2,      /* y += residual (same NHWC geometry as y) before ReLU */
+  UP_FLAG_OUT_NCHW_F32 = 4,  /* write fp32 NCHW [n, cout_valid, ho, wo] instead of 16-bit NHWC */
+  UP_FLAG_STATS = 8          /* also accumulate per-channel sum / sum-of-squares of the stored output
+                                (train-mode BatchNorm statistics) into stats[2*cout] with atomics */
+};
+
+const char* up_last_error(void);
+int up_version(void);
+/* Number of SMs / compute capability of the current device (for tests and the bench). */
+int up_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 tensor cores (TMA-staged, im2col-free), fused
+ * per-channel scale/shift (+residual) (+ReLU) epilogue.
+ *
+ * Replaces every nn.Conv2d (+ eval-mode BatchNorm2d + ReLU + residual add) of the hot path:
+ *   Bottleneck.forward            model/modules/backbone/resnet.py:22-42
+ *   ResNet.forward stem           model/modules/backbone/resnet.py:114-116 (as a 4x4 conv on the
+ *                                 2x2 space-to-depth image, see up_pack_input_s2d)
+ *   _AtrousModule.forward         model/modules/wasp.py:16-20
+ *   wasp.forward conv1/conv2      model/modules/wasp.py:72-88
+ *   Decoder.forward               model/modules/decoder.py:39-41,52
+ *   video "middle CNN" conv1..5   model/uniposeLSTM.py:120-124
+ *
+ * Geometry: y[n,ho,wo,co] = sum_{kh,kw,ci} w[co,kh,kw,ci] * x[n, ho*stride + kh*dil - pad_h,
+ *                                                            wo*stride + kw*dil - pad_w, ci]
+ * (cross-correlation, zero padding; the bottom/right padding is implied by ho/wo).
+ * stride is 1 or 2 (2 needs even h, w).  Channel counts are the PADDED ones: cin % 16 == 0
+ * (and % 64 == 0 when cin > 64 ... see up_conv2d_check), cout % 32 == 0.
+ *
+ * Weights are pre-packed by up_pack_conv_weight: 16-bit [plane][kh*kw][cout][cin].
+ * scale/shift are fp32 [cout] (eval BatchNorm folded, or scale=1 / shift=bias).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct UpConvDesc {
+  int32_t n, h, w;       /* input batch / height / width */
+  int32_t ho, wo;        /* output height / width */
+  int32_t cin, cout;     /* padded channel counts seen by the GEMM */
+  int32_t kh, kw;
+  int32_t stride, dil;
+  int32_t pad_h, pad_w;  /* top / left zero padding */
+  int32_t x_cstride, x_coff;   /* channels per pixel of the x buffer, first channel of the view */
+  int32_t x_groups;            /* K-split concat: cin = x_groups * (cin / x_groups); group g of the
+                                  channels lives x_group_nstride images further along n */
+  int32_t x_group_nstride;
+  int32_t y_cstride, y_coff;
+  int32_t r_cstride, r_coff;   /* residual view (UP_FLAG_RESIDUAL) */
+  int32_t dtype;               /* UpDtype */
+  int32_t flags;               /* UP_FLAG_* */
+  int32_t cout_valid;          /* real channel count for UP_FLAG_OUT_NCHW_F32 */
+  int32_t reserved;
+  int64_t x_plane_stride;      /* UP_SPLIT: elements between hi and lo planes */
+  int64_t y_plane_stride;
+  int64_t r_plane_stride;
+  int64_t w_plane_stride;
+} UpConvDesc;
+
+int up_conv2d_fwd(const UpConvDesc* desc, const void* x, const void* w_packed, const float* scale,
+                  const float* shift, const void* residual, void* y, float* stats, void* stream);
+
+/* Pack OIHW fp32 weights [cout_real][cin_real][kh][kw] -> 16-bit [plane][kh*kw][cout][cin]
+ * (zero padded).  dtype UP_SPLIT writes two bf16 planes `w_plane_stride` elements apart. */
+int up_pack_conv_weight(const float* w_oihw, void* w_packed, int cout_real, int cin_real, int kh, int kw,
+                        int cout, int cin, int dtype, int64_t w_plane_stride, void* stream);
+
+/* Fold eval-mode BatchNorm2d into per-channel scale/shift (torch semantics, eps inside sqrt):
+ *   scale = gamma / sqrt(var + eps), shift = beta - mean * scale;  channels >= c_real get 0/0.
+ * nn.BatchNorm2d call sites: resnet.py:26,30,34 wasp.py:18,86 decoder.py:40 */
+int up_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+               float* scale, float* shift, int c_real, int c, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Bandwidth kernels (NHWC 16-bit unless noted)
+ * ------------------------------------------------------------------------------------------ */
+/* fp32 NCHW image [n,3,h,w] -> 2x2 space-to-depth NHWC [n,h/2,w/2,16] (12 real channels, order
+ * (ph,pw,c)), so that the 7x7/s2 stem (resnet.py:61,114) becomes a 4x4/s1 tensor-core conv. */
+int up_pack_input_s2d(const float* x_nchw, void* y, int n, int h, int w, int dtype, int64_t y_plane_stride,
+                      void* stream);
+/* Generic fp32 NCHW [n,c_real,h,w] -> NHWC 16-bit view (channels >= c_real zero-filled up to c). */
+int up_nchw_f32_to_nhwc(const float* x, void* y, int n, int c_real, int h, int w, int c, int y_cstride,
+                        int y_coff, int dtype, int64_t y_plane_stride, void* stream);
+/* NHWC 16-bit view -> fp32 NCHW [n,c_real,h,w]. */
+int up_nhwc_to_nchw_f32(const void* x, float* y, int n, int c_real, int h, int w, int x_cstride, int x_coff,
+                        int dtype, int64_t x_plane_stride, void* stream);
+
+/* nn.MaxPool2d(kernel_size=3, stride=2, padding=1): resnet.py:64,117  decoder.py:33,47 */
+int up_maxpool3x3s2(const void* x, void* y, int n, int h, int w, int c, int x_cstride, int x_coff,
+                    int y_cstride, int y_coff, int dtype, int64_t x_plane_stride, int64_t y_plane_stride,
+                    void* stream);
+/* F.interpolate(mode='bilinear', align_corners=True): wasp.py:83 decoder.py:49 unipose.py:32 */
+int up_upsample_bilinear_ac(const void* x, void* y, int n, int h, int w, int ho, int wo, int c, int x_cstride,
+                            int x_coff, int y_cstride, int y_coff, int dtype, int64_t x_plane_stride,
+                            int64_t y_plane_stride, void* stream);
+/* nn.AdaptiveAvgPool2d((1,1)): wasp.py:51.  x NHWC view -> 16-bit [n,1,1,c] view. */
+int up_global_avgpool(const void* x, void* y, int n, int h, int w, int c, int x_cstride, int x_coff,
+                      int y_cstride, int y_coff, int dtype, int64_t x_plane_stride, int64_t y_plane_stride,
+                      void* stream);
+/* Broadcast a [n,1,1,c] tensor over ho x wo (bilinear from 1x1 with align_corners, wasp.py:83). */
+int up_broadcast_hw(const void* x, void* y, int n, int ho, int wo, int c, int x_cstride, int x_coff,
+                    int y_cstride, int y_coff, int dtype, int64_t x_plane_stride, int64_t y_plane_stride,
+                    void* stream);
+/* fp32 NCHW F.interpolate(bilinear, align_corners=True) for the stride != 8 output path
+ * (model/unipose.py:31-32). */
+int up_upsample_bilinear_ac_nchw_f32(const float* x, float* y, int n, int c, int h, int w, int ho, int wo,
+                                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Video variant (model/uniposeLSTM.py)
+ * ------------------------------------------------------------------------------------------ */
+/* nn.AvgPool2d(kernel_size=9, stride=8, padding=1), count_include_pad: uniposeLSTM.py:91,114.
+ * fp32 [n,c,h,w] -> fp32 [n,c,ho,wo]. */
+int up_avgpool9s8p1_f32(const float* x, float* y, int n, int c, int h, int w, int ho, int wo, void* stream);
+/* LSTM_0.forward (uniposeLSTM.py:16-24): x fp32 NCHW [b,cin,h,w];  weights OIHW [c,cin,3,3] + bias
+ * for g,i,o;  outputs cell, hide fp32 NCHW [b,c,h,w]. */
+int up_convlstm_cell0_fwd(const float* x, const float* wg, const float* bg, const float* wi, const float* bi,
+                          const float* wo, const float* bo, float* cell, float* hide, int b, int cin, int c,
+                          int h, int w, void* stream);
+/* LSTM.forward (uniposeLSTM.py:40-64): gates g,o,i,f each conv_x(x)+conv_h(h_prev) with bias.
+ * wx/bx: [4][c][cin][3][3] / [4][c] in gate order g,i,o,f;  wh/bh: [4][c][c][3][3] / [4][c]. */
+int up_convlstm_cell_fwd(const float* x, const float* h_prev, const float* c_prev, const float* wx,
+                         const float* bx, const float* wh, const float* bh, float* cell, float* hide, int b,
+                         int cin, int c, int h, int w, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Evaluation (utils/evaluate.py)
+ * ------------------------------------------------------------------------------------------ */
+/* get_max_preds (utils/evaluate.py:32-54): per (n, joint) first-occurrence argmax over h*w.
+ * heat fp32 [n,k,h,w] -> idx int32 [n,k] (flat index), preds fp32 [n,k,2] (x, y; zeroed where
+ * max <= 0), maxvals fp32 [n,k]. */
+int up_argmax2d(const float* heat, int32_t* idx, float* preds, float* maxvals, int n, int k, int h, int w,
+                void* stream);
+/* calc_dists (utils/evaluate.py:5-19): dists fp32 [k,n]; -1 where target x<=1 or y<=1. */
+int up_calc_dists(const float* preds, const float* target, float* dists, int n, int k, float norm_x,
+                  float norm_y, void* stream);
+/* dist_acc (utils/evaluate.py:22-29) for every joint at once: acc fp32 [k] (-1 if no valid sample). */
+int up_dist_acc(const float* dists, float* acc, int n, int k, float threshold, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Training glue (unipose.py:113-124)
+ * ------------------------------------------------------------------------------------------ */
+/* nn.MSELoss() (mean): loss[0] = mean((pred-target)^2); grad = 2*(pred-target)/count * gscale. */
+int up_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* grad, int64_t count,
+                   float gscale, void* stream);
+/* torch.optim.Adam step (no weight decay, no amsgrad) over a flat fp32 buffer. */
+int up_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, float lr,
+                 float beta1, float beta2, float eps, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIPOSE_B200_H_ */

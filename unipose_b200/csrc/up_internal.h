@@ -1,0 +1,65 @@
+// Internal (non-ABI) helpers shared by the translation units of libunipose_b200.so.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/unipose_b200.h"
+
+namespace up {
+
+// Records a thread-local message and returns `code` (so callers can `return fail(...)`).
+int fail(int code, const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+#define UP_CHECK_ARG(cond, ...)                                \
+  do {                                                         \
+    if (!(cond)) return ::up::fail(UP_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define UP_CHECK_LAUNCH(what)                                   \
+  do {                                                          \
+    int _rc = ::up::check_cuda(cudaGetLastError(), what);       \
+    if (_rc != 0) return _rc;                                   \
+  } while (0)
+
+// ---- 16-bit storage <-> fp32 (device) -------------------------------------------------------
+// kFmt: 0 = fp16, 1 = bf16 (matches the tcgen05 instruction-descriptor encoding).
+template <int kFmt>
+__device__ __forceinline__ float cvt16_to_f32(uint16_t v) {
+  if constexpr (kFmt == 1) {
+    return __uint_as_float(static_cast<uint32_t>(v) << 16);
+  } else {
+    return __half2float(__ushort_as_half(v));
+  }
+}
+template <int kFmt>
+__device__ __forceinline__ uint16_t cvt_f32_to16(float f) {
+  if constexpr (kFmt == 1) {
+    return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+  } else {
+    return __half_as_ushort(__float2half_rn(f));
+  }
+}
+__device__ __forceinline__ float cvt16_to_f32_rt(uint16_t v, int fmt) {
+  return fmt == 1 ? cvt16_to_f32<1>(v) : cvt16_to_f32<0>(v);
+}
+__device__ __forceinline__ uint16_t cvt_f32_to16_rt(float f, int fmt) {
+  return fmt == 1 ? cvt_f32_to16<1>(f) : cvt_f32_to16<0>(f);
+}
+// Pack two floats into one 32-bit word of two 16-bit values (a in the low half).
+__device__ __forceinline__ uint32_t pack2_rt(float a, float b, int fmt) {
+  return static_cast<uint32_t>(cvt_f32_to16_rt(a, fmt)) | (static_cast<uint32_t>(cvt_f32_to16_rt(b, fmt)) << 16);
+}
+// bf16 hi/lo split of an fp32 value: x ~= hi + lo with ~16 mantissa bits.
+__device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) {
+  hi = cvt_f32_to16<1>(x);
+  lo = cvt_f32_to16<1>(x - cvt16_to_f32<1>(hi));
+}
+
+inline int fmt_of_dtype(int dtype) { return dtype == UP_FP16 ? 0 : 1; }
+
+}  // namespace up

@@ -1,0 +1,263 @@
+"""Tensor-level wrappers over the C-ABI: torch owns device memory and the stream, nothing else.
+
+`Act` is an NHWC 16-bit activation buffer ([planes, N, H, W, C]; planes == 2 in the fp32-grade
+"split" mode).  Every function launches on torch's current CUDA stream and returns immediately.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (UP_BF16, UP_FLAG_OUT_NCHW_F32, UP_FLAG_RELU, UP_FLAG_RESIDUAL, UP_FP16, UP_SPLIT, UpConvDesc)
+
+PRECISIONS = {"bf16": UP_BF16, "fp16": UP_FP16, "fp32": UP_SPLIT}
+
+
+def mode_of(precision: str) -> int:
+    try:
+        return PRECISIONS[precision]
+    except KeyError:
+        raise ValueError("precision must be one of %s (got %r)" % (sorted(PRECISIONS), precision))
+
+
+def _torch_dtype(mode: int) -> torch.dtype:
+    return torch.float16 if mode == UP_FP16 else torch.bfloat16
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("unipose_b200: %s must live on a CUDA device (there is no CPU path)" % what)
+
+
+class Act:
+    """NHWC activation buffer; `.t` has shape [planes, n, h, w, c]."""
+
+    def __init__(self, n: int, h: int, w: int, c: int, mode: int, device, zero: bool = False):
+        assert c % 8 == 0
+        self.n, self.h, self.w, self.c, self.mode = n, h, w, c, mode
+        planes = 2 if mode == UP_SPLIT else 1
+        alloc = torch.zeros if zero else torch.empty
+        self.t = alloc((planes, n, h, w, c), dtype=_torch_dtype(mode), device=device)
+
+    @property
+    def plane_stride(self) -> int:
+        return self.n * self.h * self.w * self.c
+
+    def ptr(self, n_off: int = 0) -> ctypes.c_void_p:
+        return ctypes.c_void_p(self.t.data_ptr() + 2 * n_off * self.h * self.w * self.c)
+
+    def to_float(self) -> torch.Tensor:
+        """[n, h, w, c] fp32 (hi + lo in split mode) - for tests."""
+        f = self.t.float()
+        return f.sum(0) if self.mode == UP_SPLIT else f[0]
+
+
+@dataclass
+class View:
+    """Channel slice [coff, coff + c) of images [n_off, n_off + n) of an Act."""
+    act: Act
+    coff: int = 0
+    c: int = -1
+    n_off: int = 0
+    n: int = -1
+
+    def __post_init__(self):
+        if self.c < 0:
+            self.c = self.act.c - self.coff
+        if self.n < 0:
+            self.n = self.act.n - self.n_off
+
+    @property
+    def h(self):
+        return self.act.h
+
+    @property
+    def w(self):
+        return self.act.w
+
+    def ptr(self):
+        return self.act.ptr(self.n_off)
+
+
+def as_view(a) -> View:
+    return a if isinstance(a, View) else View(a)
+
+
+@dataclass
+class PackedConv:
+    """Pre-packed conv weights [planes, kh*kw, cout, cin] + fp32 per-channel scale / shift."""
+    w: torch.Tensor
+    scale: torch.Tensor
+    shift: torch.Tensor
+    kh: int
+    kw: int
+    cout: int
+    cin: int
+    cout_real: int
+    cin_real: int
+    mode: int
+
+    @property
+    def plane_stride(self) -> int:
+        return self.kh * self.kw * self.cout * self.cin
+
+
+def pack_conv_weight(w_oihw: torch.Tensor, mode: int, cout: Optional[int] = None, cin: Optional[int] = None):
+    """OIHW fp32 -> packed 16-bit [planes, taps, cout, cin] (zero padded) via up_pack_conv_weight."""
+    require_cuda(w_oihw, "weight")
+    w_oihw = w_oihw.detach().contiguous().float()
+    co_r, ci_r, kh, kw = w_oihw.shape
+    cout = cout or round_up(co_r, 32)
+    cin = cin or round_up(ci_r, 16)
+    planes = 2 if mode == UP_SPLIT else 1
+    out = torch.empty((planes, kh * kw, cout, cin), dtype=_torch_dtype(mode), device=w_oihw.device)
+    _lib.call("up_pack_conv_weight", _ptr(w_oihw), _ptr(out), co_r, ci_r, kh, kw, cout, cin, mode,
+              kh * kw * cout * cin, _stream())
+    return out, (kh, kw, cout, cin, co_r, ci_r)
+
+
+def bn_fold(gamma, beta, mean, var, eps: float, c: int):
+    c_real = gamma.numel()
+    scale = torch.empty(c, dtype=torch.float32, device=gamma.device)
+    shift = torch.empty(c, dtype=torch.float32, device=gamma.device)
+    _lib.call("up_bn_fold", _ptr(gamma.detach().float().contiguous()), _ptr(beta.detach().float().contiguous()),
+              _ptr(mean.float().contiguous()), _ptr(var.float().contiguous()), float(eps), _ptr(scale), _ptr(shift),
+              c_real, c, _stream())
+    return scale, shift
+
+
+def make_packed_conv(w_oihw, mode, scale=None, shift=None, bias=None, cout=None, cin=None) -> PackedConv:
+    """Pack weights and build the epilogue constants: (scale, shift) given, or scale=1 / shift=bias(0)."""
+    w, (kh, kw, co, ci, co_r, ci_r) = pack_conv_weight(w_oihw, mode, cout, cin)
+    dev = w.device
+    if scale is None:
+        scale = torch.zeros(co, dtype=torch.float32, device=dev)
+        scale[:co_r] = 1.0
+        shift = torch.zeros(co, dtype=torch.float32, device=dev)
+        if bias is not None:
+            shift[:co_r] = bias.detach().float()
+    return PackedConv(w, scale.contiguous(), shift.contiguous(), kh, kw, co, ci, co_r, ci_r, mode)
+
+
+def conv2d(x, pc: PackedConv, y, *, stride: int = 1, dil: int = 1, pad=None, relu: bool = False,
+           residual=None, ho: Optional[int] = None, wo: Optional[int] = None, x_groups: int = 1,
+           x_group_nstride: int = 0, cout_valid: Optional[int] = None) -> None:
+    """y = epilogue(conv(x, w)).  `y` is an Act/View (NHWC 16-bit) or an fp32 NCHW tensor [n, cout_valid, ho, wo]."""
+    xv = as_view(x)
+    if pad is None:
+        pad = (dil * (pc.kh - 1) // 2, dil * (pc.kw - 1) // 2)
+    if isinstance(pad, int):
+        pad = (pad, pad)
+    d = UpConvDesc()
+    d.n, d.h, d.w = xv.n, xv.h, xv.w
+    if ho is None:
+        ho = (xv.h + 2 * pad[0] - dil * (pc.kh - 1) - 1) // stride + 1
+        wo = (xv.w + 2 * pad[1] - dil * (pc.kw - 1) - 1) // stride + 1
+    d.ho, d.wo = ho, wo
+    d.cin, d.cout = pc.cin, pc.cout
+    d.kh, d.kw, d.stride, d.dil = pc.kh, pc.kw, stride, dil
+    d.pad_h, d.pad_w = pad
+    d.x_cstride, d.x_coff = xv.act.c, xv.coff
+    d.x_groups, d.x_group_nstride = x_groups, x_group_nstride
+    d.dtype = pc.mode
+    d.x_plane_stride = xv.act.plane_stride
+    d.w_plane_stride = pc.plane_stride
+    flags = UP_FLAG_RELU if relu else 0
+    rptr = ctypes.c_void_p(0)
+    if residual is not None:
+        rv = as_view(residual)
+        flags |= UP_FLAG_RESIDUAL
+        d.r_cstride, d.r_coff, d.r_plane_stride = rv.act.c, rv.coff, rv.act.plane_stride
+        rptr = rv.ptr()
+    if isinstance(y, torch.Tensor):
+        flags |= UP_FLAG_OUT_NCHW_F32
+        d.cout_valid = cout_valid if cout_valid is not None else pc.cout_real
+        assert y.dtype == torch.float32 and y.is_contiguous() and tuple(y.shape) == (xv.n, d.cout_valid, ho, wo), \
+            (tuple(y.shape), (xv.n, d.cout_valid, ho, wo))
+        yptr = _ptr(y)
+    else:
+        yv = as_view(y)
+        assert (yv.n, yv.h, yv.w) == (xv.n, ho, wo) and yv.c == pc.cout, ((yv.n, yv.h, yv.w, yv.c), (xv.n, ho, wo, pc.cout))
+        d.y_cstride, d.y_coff, d.y_plane_stride = yv.act.c, yv.coff, yv.act.plane_stride
+        yptr = yv.ptr()
+    d.flags = flags
+    _lib.call("up_conv2d_fwd", ctypes.byref(d), xv.ptr(), _ptr(pc.w), _ptr(pc.scale), _ptr(pc.shift), rptr, yptr,
+              ctypes.c_void_p(0), _stream())
+
+
+# ---------------------------------------------------------------------------------------------
+# bandwidth kernels
+# ---------------------------------------------------------------------------------------------
+def pack_input_s2d(x_nchw: torch.Tensor, y: Act) -> None:
+    n, c, h, w = x_nchw.shape
+    assert c == 3 and (y.n, y.h, y.w, y.c) == (n, h // 2, w // 2, 16)
+    _lib.call("up_pack_input_s2d", _ptr(x_nchw), y.ptr(), n, h, w, y.mode, y.plane_stride, _stream())
+
+
+def nchw_to_act(x: torch.Tensor, y, c_real: Optional[int] = None) -> None:
+    yv = as_view(y)
+    n, c, h, w = x.shape
+    assert (yv.n, yv.h, yv.w) == (n, h, w) and x.dtype == torch.float32 and x.is_contiguous()
+    _lib.call("up_nchw_f32_to_nhwc", _ptr(x), yv.ptr(), n, c, h, w, yv.c, yv.act.c, yv.coff, yv.act.mode,
+              yv.act.plane_stride, _stream())
+
+
+def act_to_nchw(x, c_real: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    xv = as_view(x)
+    if out is None:
+        out = torch.empty((xv.n, c_real, xv.h, xv.w), dtype=torch.float32, device=xv.act.t.device)
+    _lib.call("up_nhwc_to_nchw_f32", xv.ptr(), _ptr(out), xv.n, c_real, xv.h, xv.w, xv.act.c, xv.coff, xv.act.mode,
+              xv.act.plane_stride, _stream())
+    return out
+
+
+def maxpool3x3s2(x, y) -> None:
+    xv, yv = as_view(x), as_view(y)
+    assert xv.c == yv.c and xv.n == yv.n
+    _lib.call("up_maxpool3x3s2", xv.ptr(), yv.ptr(), xv.n, xv.h, xv.w, xv.c, xv.act.c, xv.coff, yv.act.c, yv.coff,
+              xv.act.mode, xv.act.plane_stride, yv.act.plane_stride, _stream())
+
+
+def upsample_bilinear_ac(x, y) -> None:
+    xv, yv = as_view(x), as_view(y)
+    assert xv.c == yv.c and xv.n == yv.n
+    _lib.call("up_upsample_bilinear_ac", xv.ptr(), yv.ptr(), xv.n, xv.h, xv.w, yv.h, yv.w, xv.c, xv.act.c, xv.coff,
+              yv.act.c, yv.coff, xv.act.mode, xv.act.plane_stride, yv.act.plane_stride, _stream())
+
+
+def global_avgpool(x, y) -> None:
+    xv, yv = as_view(x), as_view(y)
+    assert xv.c == yv.c and xv.n == yv.n and yv.h == 1 and yv.w == 1
+    _lib.call("up_global_avgpool", xv.ptr(), yv.ptr(), xv.n, xv.h, xv.w, xv.c, xv.act.c, xv.coff, yv.act.c, yv.coff,
+              xv.act.mode, xv.act.plane_stride, yv.act.plane_stride, _stream())
+
+
+def broadcast_hw(x, y) -> None:
+    xv, yv = as_view(x), as_view(y)
+    assert xv.c == yv.c and xv.n == yv.n and xv.h == 1 and xv.w == 1
+    _lib.call("up_broadcast_hw", xv.ptr(), yv.ptr(), xv.n, yv.h, yv.w, xv.c, xv.act.c, xv.coff, yv.act.c, yv.coff,
+              xv.act.mode, xv.act.plane_stride, yv.act.plane_stride, _stream())
+
+
+def upsample_bilinear_ac_nchw(x: torch.Tensor, size) -> torch.Tensor:
+    n, c, h, w = x.shape
+    out = torch.empty((n, c, size[0], size[1]), dtype=torch.float32, device=x.device)
+    _lib.call("up_upsample_bilinear_ac_nchw_f32", _ptr(x.contiguous()), _ptr(out), n, c, h, w, size[0], size[1],
+              _stream())
+    return out
