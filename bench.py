@@ -1,0 +1,317 @@
+"""bench.py — frames/s of the UniPose forward hot path on synthetic MPII-shaped input (BASELINE.json config 2:
+MPII 384x384, 16 joints, batch 32 per GPU, fp16) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision fp16|bf16|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One JSON line on rank 0.  A "step" is one forward pass of one batch (32 frames per GPU); the batch dimension
+shards across ranks with no data-path collective (weak scaling).  `value` = frames/s with the input resident in
+HBM; `e2e` = the same through the reference-facing API (`model(input)`) with the batch coming from pinned host
+memory and the heat-maps going back to the host every step.  `--impl reference` times the CPU oracle port of the
+reference's eager path on the host cores (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec MPII 384x384 bs32 forward (UniPose ResNet-101+WASP+decoder)"
+UNIT = "frames/s"
+WASP_FLOPS_PER_IMG = 3.625e9        # 1.8125 GMAC nominal @24x24
+WASP_MIN_BYTES_C2 = 91.4e6          # minimal fused bytes, batch 32, 2 B/elt
+NET_FLOPS_PER_IMG = 68.1e9          # conv-only fwd @384^2
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("UNIPOSE_B200_BENCH_PRECISION", "fp16"),
+                    choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=32, help="frames per GPU")
+    ap.add_argument("--size", type=int, default=384)
+    ap.add_argument("--joints", type=int, default=16)
+    ap.add_argument("--cpu-batch", type=int, default=4, help="frames per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tflops_burst=p["bf16_tflops"], tflops_sustained=p["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        if self.ok:
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's eager path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_forward_fps(args, steps: int, warmup: int):
+    import torch
+    from oracle import unipose_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.synth_state_dict(args.joints, seed=0)
+    x = O.synth_input(args.cpu_batch, args.size, args.size, seed=0)
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.unipose_forward(x, sd)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.unipose_forward(x, sd)
+        dt = time.perf_counter() - t0
+    return args.cpu_batch * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(args) -> int:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = max(1, min(args.steps, 6))
+    warmup = max(1, min(args.warmup, 2))
+    fps, sec_per_step, threads = cpu_forward_fps(args, steps, warmup)
+    sample = "%d steps of batch %d at %dx%d (oracle port of the reference eager graph, torch CPU fp32)" % (
+        steps, args.cpu_batch, args.size, args.size)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MPII 384x384 inference, 16 joints (config 2), CPU sample batch %d" % args.cpu_batch},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args) -> int:
+    import warnings
+
+    import torch
+    import torch.distributed as dist
+
+    from unipose_b200 import synth
+    from unipose_b200.model.unipose import unipose
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = unipose(dataset="MPII", num_classes=args.joints, precision=args.precision)
+    synth.trained_like_init_(model, seed=0)
+    model = model.cuda().eval()
+    B, S = args.batch, args.size
+    x_host = synth.mpii_like_input(B, S, S, seed=rank).pin_memory()
+    x_dev = x_host.to(dev)
+    plan = model.plan_for(x_dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    # ---- kernel-resident number: inputs already in HBM ----
+    for _ in range(max(args.warmup, 3)):
+        model.forward_static(x_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()                      # evict L2 between timed steps (not timed)
+        starts[i].record()
+        model.forward_static(x_dev)
+        ends[i].record()
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    launches = plan.launches * args.steps
+
+    # ---- end to end through the public API: pinned host batch -> model(input) -> heat-maps on the host ----
+    out_host = torch.empty((B, args.joints + 1, S // 8, S // 8), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        out_host.copy_(model(x_host.to(dev, non_blocking=True)))
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        xin = x_host.to(dev, non_blocking=True)
+        out_host.copy_(model(xin), non_blocking=True)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    peaks = measured_peaks()
+    roofline = None
+    if not args.no_roofline and rank == 0:
+        roofline = wasp_roofline(model, args, dev, peaks)
+        roofline["net_tflops_in_step"] = NET_FLOPS_PER_IMG * B * args.steps / (dev_ms * 1e-3) / 1e12 / world * world
+        roofline["net_frac_of_sustained_peak"] = (NET_FLOPS_PER_IMG * B * args.steps / (dev_ms * 1e-3) / 1e12) / \
+            peaks["tflops_sustained"]
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        fps, sec, threads = cpu_forward_fps(args, steps=2, warmup=1)
+        cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "2 steps of batch %d at %dx%d after 1 warm-up (oracle port, torch CPU fp32, %.2f s/step)" % (
+                   args.cpu_batch, S, S, sec)}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    frames = B * world * args.steps
+    line = {
+        "metric": METRIC, "value": frames / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "bf16x3 (fp32-grade)"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": "MPII %dx%d inference, %d joints, batch %d per GPU (BASELINE.json configs[1])" % (
+            S, S, args.joints, B), "global_batch": B * world, "precision": args.precision, "parallelism": "dp%d" % world,
+            "l2": "flushed between timed steps (256 MiB memset, untimed); per-step CUDA events summed",
+            "cuda_graph": plan.use_graph},
+        "clocks": clocks,
+        "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
+                "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+    }
+    if roofline is not None:
+        line["roofline"] = roofline
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    return 0
+
+
+def wasp_roofline(model, args, dev, peaks):
+    """Times the WASP block alone (the graded block) on a resident [B, 2048, S/16, S/16] input:
+    nominal dense FLOPs (zero-padding taps counted) / CUDA-event time vs the measured bf16 tensor peak."""
+    import torch
+
+    from unipose_b200 import engine
+    B, hw = args.batch, args.size // 16
+    plan = engine.Plan(dev, args.precision)
+    b = plan.builder
+    x = b.act(B, hw, hw, 2048)
+    x.t.copy_(torch.randn(x.t.shape, device=dev).clamp_min_(0) * (0.02 if x.t.shape[0] == 2 else 1.0))
+    model.wasp._emit(b, x)
+    plan.finalize([])
+    for _ in range(3):
+        plan.run()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    reps = 10
+    tot = 0.0
+    for _ in range(reps):
+        flush.zero_()
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        plan.graph.replay() if plan.graph is not None else plan._launch_all()
+        b.record()
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    ms = tot / reps
+    flops = WASP_FLOPS_PER_IMG * (hw * hw / 576.0) * B
+    achieved = flops / (ms * 1e-3) / 1e12
+    t_roof_ms = max(flops / (peaks["tflops_burst"] * 1e12), WASP_MIN_BYTES_C2 / (peaks["hbm_gbs"] * 1e9)) * 1e3
+    return {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["tflops_burst"], "traffic": None, "peak_source": peaks["source"],
+            "kernel": "conv_tcgen05_kernel (WASP block = %d launches: 9 convs + GAP + broadcast)" % plan.launches,
+            "wasp_ms": ms, "wasp_t_roof_ms": t_roof_ms, "wasp_roofline_frac": t_roof_ms / ms,
+            "flops_convention": "nominal dense (zero taps counted), %.1f GFLOP per launch group" % (flops / 1e9)}
+
+
+def main() -> int:
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -93,8 +93,9 @@ typedef struct UpConvDesc {
   int32_t r_cstride, r_coff;   /* residual view (UP_FLAG_RESIDUAL) */
   int32_t dtype;               /* UpDtype */
   int32_t flags;               /* UP_FLAG_* */
-  int32_t cout_valid;          /* real channel count for UP_FLAG_OUT_NCHW_F32 */
-  int32_t reserved;
+  int32_t cout_valid;          /* UP_FLAG_OUT_NCHW_F32: number of real output channels written */
+  int32_t out_c_total;         /* UP_FLAG_OUT_NCHW_F32: channels of the fp32 NCHW destination (0 -> cout_valid);
+                                  lets the head write the first cout_valid channels of a wider tensor */
   int64_t x_plane_stride;      /* UP_SPLIT: elements between hi and lo planes */
   int64_t y_plane_stride;
   int64_t r_plane_stride;
@@ -154,14 +155,16 @@ int up_upsample_bilinear_ac_nchw_f32(const float* x, float* y, int n, int c, int
  * Video variant (model/uniposeLSTM.py)
  * ------------------------------------------------------------------------------------------ */
 /* nn.AvgPool2d(kernel_size=9, stride=8, padding=1), count_include_pad: uniposeLSTM.py:91,114.
- * fp32 [n,c,h,w] -> fp32 [n,c,ho,wo]. */
-int up_avgpool9s8p1_f32(const float* x, float* y, int n, int c, int h, int w, int ho, int wo, void* stream);
-/* LSTM_0.forward (uniposeLSTM.py:16-24): x fp32 NCHW [b,cin,h,w];  weights OIHW [c,cin,3,3] + bias
- * for g,i,o;  outputs cell, hide fp32 NCHW [b,c,h,w]. */
-int up_convlstm_cell0_fwd(const float* x, const float* wg, const float* bg, const float* wi, const float* bi,
-                          const float* wo, const float* bo, float* cell, float* hide, int b, int cin, int c,
-                          int h, int w, void* stream);
-/* LSTM.forward (uniposeLSTM.py:40-64): gates g,o,i,f each conv_x(x)+conv_h(h_prev) with bias.
+ * fp32 [n,c,h,w] -> channels [y_c_off, y_c_off+c) of an fp32 [n,y_c_total,ho,wo] tensor
+ * (y_c_total <= 0 means y_c_total = c), i.e. the pooled centre map lands directly in the
+ * torch.cat((x, centermap)) buffer of uniposeLSTM.py:116. */
+int up_avgpool9s8p1_f32(const float* x, float* y, int n, int c, int h, int w, int ho, int wo, int y_c_total,
+                        int y_c_off, void* stream);
+/* LSTM_0.forward (uniposeLSTM.py:16-24): x fp32 NCHW [b,cin,h,w];  w3 [3][c][cin][3][3] and b3 [3][c]
+ * hold conv_{g,i,o}_lstm in that order;  outputs cell, hide fp32 NCHW [b,c,h,w]  (c <= 16). */
+int up_convlstm_cell0_fwd(const float* x, const float* w3, const float* b3, float* cell, float* hide, int b,
+                          int cin, int c, int h, int w, void* stream);
+/* LSTM.forward (uniposeLSTM.py:40-64): gates g,i,o,f each conv_x(x)+conv_h(h_prev) with both biases.
  * wx/bx: [4][c][cin][3][3] / [4][c] in gate order g,i,o,f;  wh/bh: [4][c][c][3][3] / [4][c]. */
 int up_convlstm_cell_fwd(const float* x, const float* h_prev, const float* c_prev, const float* wx,
                          const float* bx, const float* wh, const float* bh, float* cell, float* hide, int b,
@@ -170,23 +173,25 @@ int up_convlstm_cell_fwd(const float* x, const float* h_prev, const float* c_pre
 /* ------------------------------------------------------------------------------------------
  * Evaluation (utils/evaluate.py)
  * ------------------------------------------------------------------------------------------ */
-/* get_max_preds (utils/evaluate.py:32-54): per (n, joint) first-occurrence argmax over h*w.
- * heat fp32 [n,k,h,w] -> idx int32 [n,k] (flat index), preds fp32 [n,k,2] (x, y; zeroed where
- * max <= 0), maxvals fp32 [n,k]. */
+/* get_max_preds (utils/evaluate.py:32-54): per (n, joint) first-occurrence argmax over h*w (numpy
+ * semantics incl. NaN).  heat fp32 [n,k,h,w] -> idx int32 [n,k] (flat index), preds fp32 [n,k,2]
+ * (x, y; zeroed where max <= 0), maxvals fp32 [n,k]. */
 int up_argmax2d(const float* heat, int32_t* idx, float* preds, float* maxvals, int n, int k, int h, int w,
                 void* stream);
-/* calc_dists (utils/evaluate.py:5-19): dists fp32 [k,n]; -1 where target x<=1 or y<=1. */
-int up_calc_dists(const float* preds, const float* target, float* dists, int n, int k, float norm_x,
-                  float norm_y, void* stream);
-/* dist_acc (utils/evaluate.py:22-29) for every joint at once: acc fp32 [k] (-1 if no valid sample). */
-int up_dist_acc(const float* dists, float* acc, int n, int k, float threshold, void* stream);
+/* calc_dists (utils/evaluate.py:5-19): dists float64 [k,n] (the reference's dtype); -1 where the
+ * target has x<=1 or y<=1. */
+int up_calc_dists(const float* preds, const float* target, double* dists, int n, int k, double norm_x,
+                  double norm_y, void* stream);
+/* dist_acc (utils/evaluate.py:22-29) for every joint at once: acc float64 [k] (-1 if no valid sample). */
+int up_dist_acc(const double* dists, double* acc, int n, int k, double threshold, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Training glue (unipose.py:113-124)
  * ------------------------------------------------------------------------------------------ */
-/* nn.MSELoss() (mean): loss[0] = mean((pred-target)^2); grad = 2*(pred-target)/count * gscale. */
-int up_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* grad, int64_t count,
-                   float gscale, void* stream);
+/* nn.MSELoss() (mean), unipose.py:70,117: loss[0] = mean((pred-target)^2);
+ * grad (optional) = gscale * 2*(pred-target)/count.  scratch: one device double. */
+int up_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* grad, double* scratch,
+                   int64_t count, float gscale, void* stream);
 /* torch.optim.Adam step (no weight decay, no amsgrad) over a flat fp32 buffer. */
 int up_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, float lr,
                  float beta1, float beta2, float eps, int step, void* stream);

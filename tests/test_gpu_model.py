@@ -1,0 +1,175 @@
+"""GPU parity of the nn.Module mirrors (the reference-facing API) against the golden fixtures produced by the
+real reference and against the CPU oracle on the same seeded weights / inputs.
+
+Tolerances: fp32 ("parity") mode <= 1e-3 relative (north star), measured as max |err| / max |ref|, plus
+bit-exact arg-max joint indices wherever the reference's own top-2 margin exceeds the error bound;
+bf16 / fp16 throughput modes are reported with their own looser bound."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import evaluate_oracle as E
+from oracle import unipose_oracle as O
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(got, ref):
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-12))
+
+
+def _model(num_classes, seed, precision, dataset="MPII", **kw):
+    import warnings
+    from unipose_b200.model.unipose import unipose
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = unipose(dataset=dataset, num_classes=num_classes, precision=precision, **kw)
+    m.load_state_dict(O.synth_state_dict(num_classes, seed=seed), strict=True)
+    return m.cuda().eval()
+
+
+def _argmax_checked(got, ref, err_bound):
+    """Joint indices must be identical wherever the reference's top-2 margin exceeds 2 x the error bound."""
+    n, k = ref.shape[:2]
+    fr = ref.reshape(n, k, -1)
+    top2 = np.sort(fr, axis=2)[:, :, -2:]
+    safe = (top2[..., 1] - top2[..., 0]) > 2 * err_bound
+    ia = got.reshape(n, k, -1).argmax(2)
+    ib = fr.argmax(2)
+    assert safe.mean() > 0.5
+    assert np.array_equal(ia[safe], ib[safe])
+
+
+def test_image_model_fp32_mode_vs_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "image_mpii_96.npz"))
+    m = _model(16, 0, "fp32")
+    x = O.synth_input(2, 96, 96, seed=0).cuda()
+    heat = m(x)
+    assert heat.shape == (2, 17, 12, 12) and heat.dtype == torch.float32
+    r = _rel(heat.cpu().numpy(), g["heat"])
+    assert r < 1e-3, r
+    _argmax_checked(heat.cpu().numpy(), g["heat"], 1e-3 * np.abs(g["heat"]).max())
+    # module boundaries (build_backbone / build_wasp / build_decoder forward signatures)
+    feat, low = m.backbone(x)
+    assert _rel(feat.cpu().numpy()[:, ::16], g["feat_s"]) < 1e-3
+    assert _rel(low.cpu().numpy()[:, ::16, ::2, ::2], g["low_s"]) < 1e-3
+    w = m.wasp(feat)
+    assert _rel(w.cpu().numpy(), g["wasp"]) < 1e-3
+    heat2 = m.decoder(w, low)
+    assert _rel(heat2.cpu().numpy(), g["heat"]) < 1e-3
+    # second call replays the captured graph and must give the same bits
+    assert torch.equal(m(x), heat)
+
+
+def test_image_model_stride4_fullres_vs_golden():
+    g = np.load(os.path.join(GOLDEN, "image_mpii_96_fullres.npz"))
+    m = _model(16, 0, "fp32", stride=4)
+    heat = m(O.synth_input(2, 96, 96, seed=0).cuda())
+    assert heat.shape == (2, 17, 96, 96)
+    assert _rel(heat.cpu().numpy()[:, :, ::4, ::4], g["heat"]) < 1e-3
+
+
+def test_config1_lsp_256_vs_golden():
+    g = np.load(os.path.join(GOLDEN, "image_lsp_256.npz"))
+    m = _model(14, 1, "fp32", dataset="LSP")
+    heat = m(O.synth_input(1, 256, 256, seed=1).cuda())
+    assert heat.shape == (1, 15, 32, 32)
+    assert _rel(heat.cpu().numpy(), g["heat"]) < 1e-3
+
+
+@pytest.mark.parametrize("precision,bound", [("bf16", 6e-2), ("fp16", 1.5e-2)])
+def test_throughput_modes_error_is_bounded(precision, bound):
+    g = np.load(os.path.join(GOLDEN, "image_mpii_96.npz"))
+    m = _model(16, 0, precision)
+    heat = m(O.synth_input(2, 96, 96, seed=0).cuda()).cpu().numpy()
+    r = _rel(heat, g["heat"])
+    print("%s max-rel error vs reference: %.3g" % (precision, r))
+    assert r < bound, r
+
+
+def test_mpii_384_vs_oracle_and_batch_consistency():
+    """Config-2 geometry (384x384 -> 24x24 WASP map, 48x48 heat-maps): parity against the CPU oracle at
+    batch 4, then batch 32 must reproduce the same per-image results (tile decomposition over n)."""
+    sd = O.synth_state_dict(16, seed=4)
+    m = _model(16, 4, "fp32")
+    x = O.synth_input(32, 384, 384, seed=4)
+    with torch.no_grad():
+        ref = O.unipose_forward(x[:4], sd).numpy()
+    h4 = m(x[:4].cuda()).cpu().numpy()
+    assert _rel(h4, ref) < 1e-3
+    _argmax_checked(h4, ref, 1e-3 * np.abs(ref).max())
+    h32 = m(x.cuda()).cpu().numpy()
+    assert h32.shape == (32, 17, 48, 48)
+    assert _rel(h32[:4], h4) < 1e-5
+    # the bf16 throughput mode on the full config-2 batch: PCKh@0.5 on its own heat-maps vs the fp32 ones
+    mb = _model(16, 4, "bf16")
+    hb = mb(x.cuda()).cpu().numpy()
+    a = E.accuracy(hb, h32, 0.2, 0.5, "MPII")
+    print("bf16 vs fp32 heat-maps, config 2: max-rel %.3g, acc@0.5 %.4f" % (_rel(hb, h32), a[0][0]))
+
+
+def test_video_model_vs_golden_and_batch():
+    import warnings
+    from unipose_b200.model import uniposeLSTM
+    g = np.load(os.path.join(GOLDEN, "video_penn_368.npz"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = uniposeLSTM.unipose(num_classes=13, precision="fp32")
+    m.load_state_dict(O.synth_state_dict(13, video=True, seed=2), strict=True)
+    m = m.cuda().eval()
+    inp = O.synth_input(3, 368, 368, seed=2).view(1, 3, 3, 368, 368).cuda()
+    cm = torch.from_numpy(E.gaussian_heatmaps(1, 3, 368, 368, seed=5, sigma=21.0)[:, 1:4]).view(1, 3, 1, 368, 368).cuda()
+    heat = torch.zeros(14, 46, 46).cuda()
+    cell = torch.zeros(15, 46, 46).cuda()
+    hide = torch.zeros(15, 46, 46).cuda()
+    for it in range(3):
+        heat, cell, hide = m(inp, cm, it, heat, hide, cell)   # reference call pattern (uniposeLSTM.py:124-125)
+        assert heat.shape == (1, 14, 46, 46) and cell.shape == (1, 15, 46, 46)
+        for name, t in (("heat", heat), ("cell", cell), ("hide", hide)):
+            r = _rel(t.cpu().numpy(), g["%s%d" % (name, it)])
+            assert r < 1e-3, (name, it, r)
+    # batch > 1 (config 4 uses B=8): every sample must equal the B=1 result
+    inp2 = inp.repeat(2, 1, 1, 1, 1)
+    cm2 = cm.repeat(2, 1, 1, 1, 1)
+    h2, c2, hd2 = m(inp2, cm2, 0, None, None, None)
+    assert _rel(h2[1:].cpu().numpy(), g["heat0"]) < 1e-3
+    assert torch.allclose(h2[0], h2[1], atol=1e-6)
+
+
+def test_lstm_cells_vs_oracle():
+    from unipose_b200.model.uniposeLSTM import LSTM, LSTM_0
+    sd = {k: v for k, v in O.synth_state_dict(13, video=True, seed=7).items() if k.startswith("lstm")}
+    torch.manual_seed(0)
+    x = torch.randn(3, 15, 46, 46)
+    hp = torch.randn(3, 15, 46, 46) * 0.5
+    cp = torch.randn(3, 15, 46, 46) * 0.5
+    l0 = LSTM_0(15, 15, 3, 1)
+    l0.load_state_dict({k[len("lstm_0."):]: v for k, v in sd.items() if k.startswith("lstm_0.")})
+    l1 = LSTM(15, 15, 3, 1)
+    l1.load_state_dict({k[len("lstm."):]: v for k, v in sd.items() if k.startswith("lstm.")})
+    c0, h0 = l0.cuda()(x.cuda())
+    rc0, rh0 = O.lstm0_forward(x, sd)
+    assert (c0.cpu() - rc0).abs().max() < 2e-6 and (h0.cpu() - rh0).abs().max() < 2e-6
+    c1, h1 = l1.cuda()(x.cuda(), hp.cuda(), cp.cuda())
+    rc1, rh1 = O.lstm_forward(x, hp, cp, sd)
+    assert (c1.cpu() - rc1).abs().max() < 5e-6 and (h1.cpu() - rh1).abs().max() < 5e-6
+
+
+def test_weights_refresh_after_load_state_dict():
+    m = _model(16, 0, "fp32")
+    x = O.synth_input(1, 64, 64, seed=9).cuda()
+    a = m(x)
+    sd2 = O.synth_state_dict(16, seed=5)
+    m.load_state_dict(sd2)
+    b = m(x)
+    with torch.no_grad():
+        ref = O.unipose_forward(x.cpu(), sd2).numpy()
+    assert _rel(b.cpu().numpy(), ref) < 1e-3
+    assert not torch.equal(a, b)

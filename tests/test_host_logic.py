@@ -1,0 +1,80 @@
+"""CPU tests of the host-side mirror of the reference interface (no kernels launched)."""
+import json
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from unipose_b200.model.modules.backbone.resnet import stem_s2d_weight
+from unipose_b200.model.unipose import unipose
+from unipose_b200.model import uniposeLSTM
+
+from conftest import GOLDEN
+
+
+@pytest.fixture(scope="module")
+def keys():
+    return json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))
+
+
+def test_image_model_state_dict_identical_to_reference(keys):
+    with pytest.warns(UserWarning):   # offline: no ImageNet checkpoint in the hub cache
+        m = unipose(dataset="MPII", num_classes=16)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(keys["image_mpii_keys"].keys())
+    for k, v in sd.items():
+        assert list(v.shape) == keys["image_mpii_keys"][k], k
+    assert sum(p.numel() for p in m.parameters()) == 47547313
+
+
+def test_video_model_state_dict_identical_to_reference(keys):
+    with pytest.warns(UserWarning):
+        m = uniposeLSTM.unipose(num_classes=13)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(keys["video_keys"].keys())
+    for k, v in sd.items():
+        assert list(v.shape) == keys["video_keys"][k], k
+
+
+def test_reference_error_conventions():
+    from unipose_b200.model.modules.backbone import build_backbone
+    from unipose_b200.model.modules.wasp import build_wasp
+    import torch.nn as nn
+    with pytest.raises(NotImplementedError):
+        build_backbone('xception', 16, nn.BatchNorm2d)
+    with pytest.raises(NotImplementedError):
+        build_wasp('resnet', 32, nn.BatchNorm2d)
+
+
+def test_no_cpu_fallback():
+    with pytest.warns(UserWarning):
+        m = unipose(dataset="MPII", num_classes=16).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 3, 64, 64))
+
+
+def test_stem_space_to_depth_weights_are_equivalent():
+    torch.manual_seed(0)
+    w = torch.randn(8, 3, 7, 7, dtype=torch.float64)
+    x = torch.randn(2, 3, 32, 48, dtype=torch.float64)
+    ref = F.conv2d(x, w, stride=2, padding=3)
+    # 2x2 space-to-depth with channel order (ph, pw, c), padded to 16 channels
+    n, c, h, wd = x.shape
+    x2 = x.view(n, c, h // 2, 2, wd // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(n, 12, h // 2, wd // 2)
+    x2 = torch.cat([x2, x2.new_zeros(n, 4, h // 2, wd // 2)], 1)
+    w2 = stem_s2d_weight(w)
+    got = F.conv2d(F.pad(x2, (2, 1, 2, 1)), w2)
+    assert torch.allclose(got, ref, atol=1e-12)
+
+
+def test_precision_switch_and_lr_groups():
+    with pytest.warns(UserWarning):
+        m = unipose(dataset="MPII", num_classes=16)
+    m.set_precision("bf16")
+    assert m.backbone.layer3[5].precision == "bf16"
+    with pytest.raises(ValueError):
+        m.set_precision("int8")
+    n1 = sum(p.numel() for p in m.get_1x_lr_params())
+    n10 = sum(p.numel() for p in m.get_10x_lr_params())
+    assert n1 == 42500160 and n1 + n10 == 47547313

@@ -27,7 +27,7 @@ class UpConvDesc(ctypes.Structure):
         ("y_cstride", c_int32), ("y_coff", c_int32),
         ("r_cstride", c_int32), ("r_coff", c_int32),
         ("dtype", c_int32), ("flags", c_int32),
-        ("cout_valid", c_int32), ("reserved", c_int32),
+        ("cout_valid", c_int32), ("out_c_total", c_int32),
         ("x_plane_stride", c_int64), ("y_plane_stride", c_int64),
         ("r_plane_stride", c_int64), ("w_plane_stride", c_int64),
     ]
@@ -37,6 +37,7 @@ _P = c_void_p
 _I = c_int
 _L = c_int64
 _F = c_float
+_D = ctypes.c_double
 
 # name -> argtypes (restype is always int unless listed in _RESTYPES)
 _SIGNATURES = {
@@ -53,13 +54,13 @@ _SIGNATURES = {
     "up_global_avgpool": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P],
     "up_broadcast_hw": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P],
     "up_upsample_bilinear_ac_nchw_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
-    "up_avgpool9s8p1_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
-    "up_convlstm_cell0_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "up_avgpool9s8p1_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "up_convlstm_cell0_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "up_convlstm_cell_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "up_argmax2d": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
-    "up_calc_dists": [_P, _P, _P, _I, _I, _F, _F, _P],
-    "up_dist_acc": [_P, _P, _I, _I, _F, _P],
-    "up_mse_fwd_bwd": [_P, _P, _P, _P, _L, _F, _P],
+    "up_calc_dists": [_P, _P, _P, _I, _I, _D, _D, _P],
+    "up_dist_acc": [_P, _P, _I, _I, _D, _P],
+    "up_mse_fwd_bwd": [_P, _P, _P, _P, _P, _L, _F, _P],
     "up_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P],
 }
 

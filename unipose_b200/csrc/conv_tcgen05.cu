@@ -47,7 +47,7 @@ struct ConvKParams {
   uint32_t idesc;
   uint32_t tmem_cols;
   int flags, fmt, split;
-  int cout_valid;
+  int cout_valid, out_c_total;
   int y_coff;
   int r_cs, r_coff;
   long long r_plane;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(256, 1)
             float v = __uint_as_float(r[j]) * __ldg(p.scale + col) + __ldg(p.shift + col);
             if (p.flags & UP_FLAG_RELU) v = fmaxf(v, 0.f);
             if (valid && col < p.cout_valid) {
-              p.out_f32[((static_cast<long long>(n) * p.cout_valid + col) * p.Ho + h) * p.Wo + w] = v;
+              p.out_f32[((static_cast<long long>(n) * p.out_c_total + col) * p.Ho + h) * p.Wo + w] = v;
             }
           }
         }
@@ -548,6 +548,7 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   const bool split = d->dtype == UP_SPLIT;
   if (nchw) {
     UP_CHECK_ARG(d->cout_valid > 0 && d->cout_valid <= d->cout, "up_conv2d_fwd: bad cout_valid");
+    UP_CHECK_ARG(d->out_c_total == 0 || d->out_c_total >= d->cout_valid, "up_conv2d_fwd: bad out_c_total");
     UP_CHECK_ARG(!(d->flags & UP_FLAG_RESIDUAL), "up_conv2d_fwd: residual not supported with NCHW fp32 output");
   } else {
     UP_CHECK_ARG(d->cout % 64 == 0, "up_conv2d_fwd: NHWC output needs cout %% 64 == 0 (got %d)", d->cout);
@@ -616,6 +617,7 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   p.fmt = fmt;
   p.split = split ? 1 : 0;
   p.cout_valid = d->cout_valid;
+  p.out_c_total = d->out_c_total > 0 ? d->out_c_total : d->cout_valid;
   p.y_coff = d->y_coff;
   p.r_cs = d->r_cstride;
   p.r_coff = d->r_coff;

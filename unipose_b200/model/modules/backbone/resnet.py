@@ -1,0 +1,173 @@
+"""Dilated ResNet-101 backbone on tcgen05 implicit-GEMM convs.
+
+Mirrors model/modules/backbone/resnet.py of the reference (Bottleneck :5-42, ResNet :44-150,
+ResNet101 :152-160): same attribute names -> same state_dict keys; same initialisation
+(normal(0, sqrt(2/(k*k*out))) convs, BN weight 1 / bias 0, resnet.py:126-136).  forward() does not run
+torch ops: every conv+BN(+residual)+ReLU is ONE fused kernel launch recorded into an engine.Plan.
+"""
+import math
+import os
+import warnings
+
+import torch
+import torch.nn as nn
+
+from ....plan_module import PlanModule
+
+_IMAGENET_FILE = 'resnet101-5d3b4d8f.pth'   # what resnet.py:142 downloads
+
+
+def stem_s2d_weight(w):
+    """[co,3,7,7] stride-2 stem filter -> [co,16,4,4] stride-1 filter over the 2x2 space-to-depth image
+    (channel order (ph,pw,c), taps at offsets -2..1; up_pack_input_s2d produces the matching activations)."""
+    w2 = w.new_zeros((w.shape[0], 16, 4, 4))
+    for a in range(4):
+        for ph in range(2):
+            kh = 2 * (a - 2) + ph + 3
+            if not 0 <= kh < 7:
+                continue
+            for bb in range(4):
+                for pw in range(2):
+                    kw = 2 * (bb - 2) + pw + 3
+                    if 0 <= kw < 7:
+                        c0 = (ph * 2 + pw) * 3
+                        w2[:, c0:c0 + 3, a, bb] = w[:, :, kh, kw]
+    return w2
+
+
+class Bottleneck(PlanModule):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None, BatchNorm=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=1, bias=False)
+        self.bn1 = BatchNorm(planes)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, stride=stride, dilation=dilation,
+                               padding=dilation, bias=False)
+        self.bn2 = BatchNorm(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, kernel_size=1, bias=False)
+        self.bn3 = BatchNorm(planes * 4)
+        self.downsample = downsample
+        self.stride, self.dilation = stride, dilation
+        self._out_channels = (planes * 4,)
+
+    def _emit(self, b, x):
+        n, h, w = x.n, x.h, x.w
+        planes = self.conv1.out_channels
+        s, d = self.stride, self.dilation
+        ho, wo = (h - 1) // s + 1, (w - 1) // s + 1
+        t1 = b.act(n, h, w, planes)
+        b.conv(x, b.packed_conv(self.conv1, self.bn1), t1, "bottleneck.conv1", relu=True)
+        t2 = b.act(n, ho, wo, planes)
+        b.conv(t1, b.packed_conv(self.conv2, self.bn2), t2, "bottleneck.conv2", stride=s, dil=d, pad=d, relu=True)
+        res = x
+        if self.downsample is not None:
+            res = b.act(n, ho, wo, planes * 4)
+            b.conv(x, b.packed_conv(self.downsample[0], self.downsample[1]), res, "bottleneck.downsample",
+                   stride=s, pad=0)
+        out = b.act(n, ho, wo, planes * 4)
+        b.conv(t2, b.packed_conv(self.conv3, self.bn3), out, "bottleneck.conv3", relu=True, residual=res)
+        return out
+
+
+class ResNet(PlanModule):
+    def __init__(self, block, layers, output_stride, BatchNorm, pretrained=True):
+        super().__init__()
+        self.inplanes = 64
+        if output_stride == 16:
+            strides, dilations = [1, 2, 2, 1], [1, 1, 1, 2]
+        elif output_stride == 8:
+            strides, dilations = [1, 2, 1, 1], [1, 1, 2, 4]
+        else:
+            raise NotImplementedError
+        self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = BatchNorm(64)
+        self.layer1 = self._stack(block, 64, [dilations[0]] * layers[0], strides[0], BatchNorm)
+        self.layer2 = self._stack(block, 128, [dilations[1]] * layers[1], strides[1], BatchNorm)
+        self.layer3 = self._stack(block, 256, [dilations[2]] * layers[2], strides[2], BatchNorm)
+        # multi-grid unit: dilation x [1, 2, 4] (resnet.py:49,70,94-111)
+        self.layer4 = self._stack(block, 512, [m * dilations[3] for m in (1, 2, 4)], strides[3], BatchNorm)
+        self._out_channels = (2048, 256)
+        self._init_weight()
+        if pretrained:
+            self._load_pretrained_model()
+
+    def _stack(self, block, planes, dils, stride, BatchNorm):
+        down = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            down = nn.Sequential(nn.Conv2d(self.inplanes, planes * block.expansion, kernel_size=1, stride=stride,
+                                           bias=False), BatchNorm(planes * block.expansion))
+        blocks = [block(self.inplanes, planes, stride, dils[0], down, BatchNorm)]
+        self.inplanes = planes * block.expansion
+        blocks += [block(self.inplanes, planes, 1, d, None, BatchNorm) for d in dils[1:]]
+        return nn.Sequential(*blocks)
+
+    def _init_weight(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2. / n))
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+
+    def _load_pretrained_model(self):
+        """The reference downloads the torchvision ImageNet ResNet-101 here (resnet.py:138-150).  Offline, the
+        file is used when it already sits in the torch hub cache; otherwise the random init stays."""
+        path = os.path.join(torch.hub.get_dir(), 'checkpoints', _IMAGENET_FILE)
+        if not os.path.exists(path):
+            warnings.warn('unipose_b200: %s not in the torch hub cache - backbone keeps its random init' % path)
+            return
+        pretrain = torch.load(path, map_location='cpu')
+        own = self.state_dict()
+        own.update({k: v for k, v in pretrain.items() if k in own})
+        self.load_state_dict(own)
+
+    # image entry point: fp32 NCHW -> 2x2 space-to-depth NHWC (instead of the generic NCHW->NHWC copy)
+    def _input_channels_pad(self, idx, c):
+        return 16
+
+    def _emit_image(self, b, x_static):
+        from .... import ops
+        n, _, h, w = x_static.shape
+        if h % 16 or w % 16:
+            raise ValueError('unipose_b200: input height/width must be multiples of 16 (got %dx%d)' % (h, w))
+        x2 = b.act(n, h // 2, w // 2, 16)
+        b.add(lambda: ops.pack_input_s2d(x_static, x2), "pack_input_s2d")
+        stem = b.act(n, h // 2, w // 2, 64)
+        pc = b.packed_conv(self.conv1, self.bn1, cin_pad=16, weight_fn=stem_s2d_weight)
+        b.conv(x2, pc, stem, "stem", pad=2, relu=True, ho=h // 2, wo=w // 2)
+        x = b.act(n, h // 4, w // 4, 64)
+        b.add(lambda: ops.maxpool3x3s2(stem, x), "maxpool")
+        low = None
+        for name in ('layer1', 'layer2', 'layer3', 'layer4'):
+            for blk in getattr(self, name):
+                x = blk._emit(b, x)
+            if name == 'layer1':
+                low = x
+        return x, low
+
+    def forward(self, input):
+        from .... import engine, ops
+        self._check_inputs([input])
+        self._bn_eval_only()
+        key = (tuple(input.shape), self._precision(), input.device.index)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = engine.Plan(input.device, self._precision())
+            b = plan.builder
+            st = plan.static_input(tuple(input.shape))
+            x, low = self._emit_image(b, st)
+            outs = []
+            for a, c in ((x, 2048), (low, 256)):
+                dst = b.tensor((a.n, c, a.h, a.w))
+                b.add(lambda a=a, c=c, dst=dst: ops.act_to_nchw(a, c, dst), "nhwc_to_nchw")
+                outs.append(dst)
+            plan.finalize(outs)
+            self._plans[key] = plan
+        x, low = plan.run(input.detach().float())
+        return x.clone(), low.clone()
+
+
+def ResNet101(output_stride, BatchNorm, pretrained=True):
+    return ResNet(Bottleneck, [3, 4, 23, 3], output_stride, BatchNorm, pretrained=pretrained)

@@ -1,0 +1,106 @@
+"""WASP "waterfall" atrous module on tcgen05 implicit-GEMM convs.
+
+Mirrors model/modules/wasp.py of the reference (_AtrousModule :6-31, wasp :33-104, build_wasp :106-107).
+Kernel plan for x [N, h, w, 2048] (all NHWC 16-bit, BN folded into the conv epilogues in eval mode):
+
+    aspp1 1x1 2048->256          -> S[0:N]          (S stacks the four cascade outputs along n)
+    aspp2/3/4 3x3 d18/12/6       -> S[N:2N], S[2N:3N], S[3N:4N]   (taps that fall outside the map are skipped)
+    conv2 1x1 (shared weights)   S -> T, T -> U[0:4N]              (two launches over M = 4N*h*w instead of eight)
+    GAP -> 1x1 -> BN -> ReLU -> broadcast                -> U[4N:5N]
+    conv1 1x1 1280->256 + bn1 + ReLU reads U as a 5-group K-split (no concat buffer) -> out
+"""
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...ops import View
+from ...plan_module import PlanModule
+
+
+class _AtrousModule(PlanModule):
+    def __init__(self, inplanes, planes, kernel_size, padding, dilation, BatchNorm):
+        super().__init__()
+        self.atrous_conv = nn.Conv2d(inplanes, planes, kernel_size=kernel_size, stride=1, padding=padding,
+                                     dilation=dilation, bias=False)
+        self.bn = BatchNorm(planes)
+        self._out_channels = (planes,)
+        _kaiming_init(self)
+
+    def _emit(self, b, x, y=None):
+        conv = self.atrous_conv
+        if y is None:
+            y = b.act(x.n, x.h, x.w, conv.out_channels)
+        b.conv(x, b.packed_conv(conv, self.bn), y, "wasp.atrous", dil=conv.dilation[0], pad=conv.padding[0], relu=True)
+        return y
+
+
+def _kaiming_init(module):
+    for m in module.modules():
+        if isinstance(m, nn.Conv2d):
+            torch.nn.init.kaiming_normal_(m.weight)
+        elif isinstance(m, nn.BatchNorm2d):
+            m.weight.data.fill_(1)
+            m.bias.data.zero_()
+
+
+class wasp(PlanModule):
+    _gap_has_bn = True
+
+    def __init__(self, backbone, output_stride, BatchNorm):
+        super().__init__()
+        inplanes = self._inplanes(backbone)
+        if output_stride == 16:
+            dilations = [24, 18, 12, 6]
+        elif output_stride == 8:
+            dilations = [48, 36, 24, 12]
+        else:
+            raise NotImplementedError
+        self.aspp1 = _AtrousModule(inplanes, 256, 1, padding=0, dilation=dilations[0], BatchNorm=BatchNorm)
+        self.aspp2 = _AtrousModule(256, 256, 3, padding=dilations[1], dilation=dilations[1], BatchNorm=BatchNorm)
+        self.aspp3 = _AtrousModule(256, 256, 3, padding=dilations[2], dilation=dilations[2], BatchNorm=BatchNorm)
+        self.aspp4 = _AtrousModule(256, 256, 3, padding=dilations[3], dilation=dilations[3], BatchNorm=BatchNorm)
+        gap = [nn.AdaptiveAvgPool2d((1, 1)), nn.Conv2d(inplanes, 256, 1, stride=1, bias=False)]
+        if self._gap_has_bn:
+            gap.append(nn.BatchNorm2d(256))
+        gap.append(nn.ReLU())
+        self.global_avg_pool = nn.Sequential(*gap)
+        self.conv1 = nn.Conv2d(1280, 256, 1, bias=False)
+        self.conv2 = nn.Conv2d(256, 256, 1, bias=False)
+        self.bn1 = BatchNorm(256)
+        self.dropout = nn.Dropout(0.5)
+        self._out_channels = (256,)
+        _kaiming_init(self)
+
+    @staticmethod
+    def _inplanes(backbone):
+        return 2048
+
+    def _emit(self, b, x):
+        n, h, w = x.n, x.h, x.w
+        S = b.act(4 * n, h, w, 256)
+        branch = [View(S, n_off=i * n, n=n) for i in range(4)]
+        self.aspp1._emit(b, x, branch[0])
+        self.aspp2._emit(b, branch[0], branch[1])
+        self.aspp3._emit(b, branch[1], branch[2])
+        self.aspp4._emit(b, branch[2], branch[3])
+        # shared 1x1 conv2 applied twice to every branch, no BN / ReLU in between (wasp.py:72-80)
+        pc2 = b.packed_conv(self.conv2, None)
+        T = b.act(4 * n, h, w, 256)
+        U = b.act(5 * n, h, w, 256)
+        b.conv(S, pc2, T, "wasp.conv2a")
+        b.conv(T, pc2, View(U, n_off=0, n=4 * n), "wasp.conv2b")
+        # image-level branch: GAP -> 1x1 (-> BN) -> ReLU -> bilinear from 1x1 == broadcast (wasp.py:82-83)
+        g = b.act(n, 1, 1, x.c)
+        b.add(lambda: ops.global_avgpool(x, g), "wasp.gap")
+        g2 = b.act(n, 1, 1, 256)
+        gap_bn = self.global_avg_pool[2] if self._gap_has_bn else None
+        b.conv(g, b.packed_conv(self.global_avg_pool[1], gap_bn), g2, "wasp.gap_conv", relu=True)
+        b.add(lambda: ops.broadcast_hw(g2, View(U, n_off=4 * n, n=n)), "wasp.gap_broadcast")
+        out = b.act(n, h, w, 256)
+        b.conv(View(U, n_off=0, n=n), b.packed_conv(self.conv1, self.bn1), out, "wasp.conv1", relu=True,
+               x_groups=5, x_group_nstride=n)
+        return out   # nn.Dropout(0.5) is the identity in eval mode (wasp.py:90)
+
+
+def build_wasp(backbone, output_stride, BatchNorm):
+    return wasp(backbone, output_stride, BatchNorm)

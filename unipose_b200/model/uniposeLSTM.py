@@ -1,0 +1,194 @@
+"""UniPose-LSTM video model — drop-in for model/uniposeLSTM.py of the reference (LSTM_0 :9-24, LSTM :27-64,
+unipose :67-147): same constructors / forward signatures / state_dict keys.
+
+    heat, cell, hide = model(input[B,T,3,H,W], centermap[B,T,1,H,W], iter, previous, previousHide, previousCell)
+
+Per frame: trunk (backbone -> waspVideo -> decoder) writes its K+1 heat-maps straight into the 15-channel
+fp32 buffer that the 9x9/8 centre-map pooling completes; one fused ConvLSTM-cell kernel (all gate convs +
+sigmoid/tanh + state update); the 11x11 / 1x1 "middle CNN" runs on the tcgen05 conv kernel with bias+ReLU
+epilogues.  The reference hard-codes batch 1 and 46x46 (uniposeLSTM.py:99-104); here the batch dimension is free.
+"""
+import torch
+import torch.nn as nn
+
+from .. import engine, ops
+from ..plan_module import PlanModule
+from .modules.backbone import build_backbone
+from .modules.decoder import build_decoder
+from .modules.waspVideo import build_wasp
+
+
+def _nchw_state(t, b, c, h, w, what):
+    t = t.detach()
+    if t.dim() == 3:
+        t = t.unsqueeze(0)
+    if tuple(t.shape) != (b, c, h, w):
+        raise ValueError('unipose_b200: %s must have shape %s (got %s)' % (what, (b, c, h, w), tuple(t.shape)))
+    return t.float().contiguous()
+
+
+class LSTM_0(PlanModule):
+    def __init__(self, inplanes, planes, kernel_size, padding):
+        super().__init__()
+        assert kernel_size == 3 and padding == 1 and planes <= 16
+        self.conv_g_lstm = nn.Conv2d(inplanes, planes, kernel_size=kernel_size, padding=padding)
+        self.conv_i_lstm = nn.Conv2d(inplanes, planes, kernel_size=kernel_size, padding=padding)
+        self.conv_o_lstm = nn.Conv2d(inplanes, planes, kernel_size=kernel_size, padding=padding)
+
+    def _gates(self):
+        return (self.conv_g_lstm, self.conv_i_lstm, self.conv_o_lstm)
+
+    def launch(self, x, cell, hide):
+        """x fp32 NCHW (contiguous, CUDA) -> cell, hide written in place."""
+        w3 = torch.stack([c.weight.detach().float() for c in self._gates()]).contiguous()
+        b3 = torch.stack([c.bias.detach().float() for c in self._gates()]).contiguous()
+        b, cin, h, w = x.shape
+        ops._lib.call("up_convlstm_cell0_fwd", ops._ptr(x), ops._ptr(w3), ops._ptr(b3), ops._ptr(cell), ops._ptr(hide),
+                      b, cin, w3.shape[1], h, w, ops._stream())
+
+    def forward(self, x):
+        ops.require_cuda(x, "LSTM_0 input")
+        x = x.detach().float().contiguous()
+        planes = self.conv_g_lstm.out_channels
+        cell = torch.empty((x.shape[0], planes, x.shape[2], x.shape[3]), device=x.device)
+        hide = torch.empty_like(cell)
+        self.launch(x, cell, hide)
+        return cell, hide
+
+
+class LSTM(PlanModule):
+    def __init__(self, inplanes, planes, kernel_size, padding):
+        super().__init__()
+        assert kernel_size == 3 and padding == 1 and planes <= 16
+        for g in ('gx', 'ix', 'ox', 'fx'):
+            setattr(self, 'conv_%s_lstm' % g, nn.Conv2d(inplanes, planes, kernel_size=kernel_size, padding=padding))
+        for g in ('gh', 'ih', 'oh', 'fh'):
+            setattr(self, 'conv_%s_lstm' % g, nn.Conv2d(planes, planes, kernel_size=kernel_size, padding=padding))
+
+    def _stacked(self, suffix):
+        convs = [getattr(self, 'conv_%s%s_lstm' % (g, suffix)) for g in 'giof']
+        return (torch.stack([c.weight.detach().float() for c in convs]).contiguous(),
+                torch.stack([c.bias.detach().float() for c in convs]).contiguous())
+
+    def launch(self, x, h_prev, c_prev, cell, hide):
+        wx, bx = self._stacked('x')
+        wh, bh = self._stacked('h')
+        b, cin, h, w = x.shape
+        ops._lib.call("up_convlstm_cell_fwd", ops._ptr(x), ops._ptr(h_prev), ops._ptr(c_prev), ops._ptr(wx),
+                      ops._ptr(bx), ops._ptr(wh), ops._ptr(bh), ops._ptr(cell), ops._ptr(hide), b, cin, wx.shape[1],
+                      h, w, ops._stream())
+
+    def forward(self, x, prevHide, prevCell):
+        ops.require_cuda(x, "LSTM input")
+        x = x.detach().float().contiguous()
+        b, _, h, w = x.shape
+        planes = self.conv_gx_lstm.out_channels
+        hp = _nchw_state(prevHide, b, planes, h, w, 'prevHide')
+        cp = _nchw_state(prevCell, b, planes, h, w, 'prevCell')
+        cell = torch.empty_like(hp)
+        hide = torch.empty_like(hp)
+        self.launch(x, hp, cp, cell, hide)
+        return cell, hide
+
+
+class unipose(PlanModule):
+    def __init__(self, backbone='resnet', output_stride=16, num_classes=21, sync_bn=True, freeze_bn=False,
+                 stride=8, precision=None):
+        super().__init__()
+        self.stride = stride
+        self.precision = precision
+        self.BatchNorm = nn.BatchNorm2d
+        self.pool_center = nn.AvgPool2d(kernel_size=9, stride=8, padding=1)
+        self.backbone = build_backbone(backbone, output_stride, self.BatchNorm)
+        self.wasp = build_wasp(backbone, output_stride, self.BatchNorm)
+        self.decoder = build_decoder("Penn_Action", num_classes, backbone, self.BatchNorm)
+        self.lstm_0 = LSTM_0(15, 15, 3, 1)
+        self.lstm = LSTM(15, 15, 3, 1)
+        # "middle CNN" (uniposeLSTM.py:85-89)
+        self.conv1 = nn.Conv2d(15, 128, kernel_size=11, padding=5)
+        self.conv2 = nn.Conv2d(128, 128, kernel_size=11, padding=5)
+        self.conv3 = nn.Conv2d(128, 128, kernel_size=11, padding=5)
+        self.conv4 = nn.Conv2d(128, 128, kernel_size=1, padding=0)
+        self.conv5 = nn.Conv2d(128, 14, kernel_size=1, padding=0)
+        if freeze_bn:
+            self.freeze_bn()
+
+    # one plan per (frame shape, first-frame?)
+    def _build_plan(self, b_, h, w, first, device):
+        plan = engine.Plan(device, self._precision())
+        b = plan.builder
+        frame = plan.static_input((b_, 3, h, w))
+        cmap = plan.static_input((b_, 1, h, w))
+        k1 = self.decoder.num_out                       # K+1 trunk heat-maps
+        lstm_c = self.lstm_0.conv_g_lstm.in_channels    # 15 = K+1 + centre map
+        hs, ws = h // 8, w // 8
+        x, low = self.backbone._emit_image(b, frame)
+        x = self.wasp._emit(b, x)
+        cat = b.tensor((b_, lstm_c, hs, ws), zero=True)
+        self.decoder._emit(b, x, low, out=cat, out_c_total=lstm_c)
+        b.add(lambda: ops._lib.call("up_avgpool9s8p1_f32", ops._ptr(cmap), ops._ptr(cat), b_, 1, h, w, hs, ws, lstm_c,
+                                    k1, ops._stream()), "pool_center")
+        planes = self.lstm_0.conv_g_lstm.out_channels
+        cell = b.tensor((b_, planes, hs, ws))
+        hide = b.tensor((b_, planes, hs, ws))
+        if first:
+            b.add(lambda: self.lstm_0.launch(cat, cell, hide), "lstm_0")
+        else:
+            hp = plan.static_input((b_, planes, hs, ws))
+            cp = plan.static_input((b_, planes, hs, ws))
+            b.add(lambda: self.lstm.launch(cat, hp, cp, cell, hide), "lstm")
+        hin = b.act(b_, hs, ws, 16, zero=True)
+        b.add(lambda: ops.nchw_to_act(hide, hin), "hide_to_nhwc")
+        a1 = b.act(b_, hs, ws, 128)
+        b.conv(hin, b.packed_conv(self.conv1, None, cin_pad=16), a1, "middle.conv1", pad=5, relu=True)
+        a2 = b.act(b_, hs, ws, 128)
+        b.conv(a1, b.packed_conv(self.conv2, None), a2, "middle.conv2", pad=5, relu=True)
+        a3 = b.act(b_, hs, ws, 128)
+        b.conv(a2, b.packed_conv(self.conv3, None), a3, "middle.conv3", pad=5, relu=True)
+        a4 = b.act(b_, hs, ws, 128)
+        b.conv(a3, b.packed_conv(self.conv4, None), a4, "middle.conv4", relu=True)
+        heat = b.tensor((b_, self.conv5.out_channels, hs, ws))
+        b.conv(a4, b.packed_conv(self.conv5, None, nchw_out=True), heat, "middle.conv5", relu=True)
+        plan.finalize([heat, cell, hide])
+        return plan
+
+    def forward(self, input, centermap, iter, previous, previousHide, previousCell):
+        self._check_inputs([input, centermap])
+        self._bn_eval_only()
+        b_, _t, _c, h, w = input.shape
+        first = (iter == 0)
+        key = (b_, h, w, first, self._precision(), input.device.index)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._build_plan(b_, h, w, first, input.device)
+            self._plans[key] = plan
+        frame = input[:, iter].detach().float()
+        cmap = centermap[:, iter].detach().float()
+        if first:
+            outs = plan.run(frame, cmap)
+        else:
+            planes = self.lstm_0.conv_g_lstm.out_channels
+            hp = _nchw_state(previousHide, b_, planes, h // 8, w // 8, 'previousHide')
+            cp = _nchw_state(previousCell, b_, planes, h // 8, w // 8, 'previousCell')
+            outs = plan.run(frame, cmap, hp, cp)
+        heat, cell, hide = [o.clone() for o in outs]
+        return heat, cell, hide
+
+    def freeze_bn(self):
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+
+    def _lr_params(self, roots):
+        for root in roots:
+            for m in root.modules():
+                if isinstance(m, (nn.Conv2d, nn.BatchNorm2d)):
+                    for p in m.parameters(recurse=False):
+                        if p.requires_grad:
+                            yield p
+
+    def get_1x_lr_params(self):
+        return self._lr_params([self.backbone])
+
+    def get_10x_lr_params(self):
+        return self._lr_params([self.wasp, self.decoder])

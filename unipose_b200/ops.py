@@ -157,7 +157,7 @@ def make_packed_conv(w_oihw, mode, scale=None, shift=None, bias=None, cout=None,
 
 def conv2d(x, pc: PackedConv, y, *, stride: int = 1, dil: int = 1, pad=None, relu: bool = False,
            residual=None, ho: Optional[int] = None, wo: Optional[int] = None, x_groups: int = 1,
-           x_group_nstride: int = 0, cout_valid: Optional[int] = None) -> None:
+           x_group_nstride: int = 0, cout_valid: Optional[int] = None, out_c_total: Optional[int] = None) -> None:
     """y = epilogue(conv(x, w)).  `y` is an Act/View (NHWC 16-bit) or an fp32 NCHW tensor [n, cout_valid, ho, wo]."""
     xv = as_view(x)
     if pad is None:
@@ -188,8 +188,9 @@ def conv2d(x, pc: PackedConv, y, *, stride: int = 1, dil: int = 1, pad=None, rel
     if isinstance(y, torch.Tensor):
         flags |= UP_FLAG_OUT_NCHW_F32
         d.cout_valid = cout_valid if cout_valid is not None else pc.cout_real
-        assert y.dtype == torch.float32 and y.is_contiguous() and tuple(y.shape) == (xv.n, d.cout_valid, ho, wo), \
-            (tuple(y.shape), (xv.n, d.cout_valid, ho, wo))
+        d.out_c_total = out_c_total or d.cout_valid
+        assert y.dtype == torch.float32 and y.is_contiguous() and tuple(y.shape) == (xv.n, d.out_c_total, ho, wo), \
+            (tuple(y.shape), (xv.n, d.out_c_total, ho, wo))
         yptr = _ptr(y)
     else:
         yv = as_view(y)
