@@ -192,6 +192,61 @@ int up_dist_acc(const double* dists, double* acc, int n, int k, double threshold
  * grad (optional) = gscale * 2*(pred-target)/count.  scratch: one device double. */
 int up_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* grad, double* scratch,
                    int64_t count, float gscale, void* stream);
+/* ---- backward of the convolutions (what loss.backward() runs for every nn.Conv2d, unipose.py:123) ----
+ * dgrad is up_conv2d_fwd itself on the incoming gradient with the filter transposed + flipped
+ * (pack w[ci][co][kh'][kw'] = w[co][ci][KH-1-kh'][KW-1-kw'], pad' = dil*(k-1) - pad; for stride 2 first
+ * up_zero_insert2x the gradient).  wgrad is its own tcgen05 kernel (both operands MN-major):
+ *   dw[co][ci][kh][kw] (+)= sum_{n,ho,wo} dz[n,ho,wo,co] * x[n, ho*stride + kh*dil - pad_h, wo*stride + kw*dil - pad_w, ci]
+ * `desc` is the FORWARD descriptor of the layer (x geometry / view, cin, cout, filter, stride, dil, pad, dtype,
+ * x_groups); dz must be a dense NHWC [n,ho,wo,cout] tensor whose hi/lo plane stride is desc->y_plane_stride.
+ * scratch: fp32 workspace of at least up_conv2d_wgrad_scratch_bytes(desc). */
+int64_t up_conv2d_wgrad_scratch_bytes(const UpConvDesc* desc);
+int up_conv2d_wgrad(const UpConvDesc* desc, const void* x, const void* dz, float* dw_oihw, int cout_real,
+                    int cin_real, float* scratch, int64_t scratch_bytes, int accumulate, void* stream);
+
+/* NHWC 16-bit channel-slice view used by the training kernels below. */
+typedef struct UpView {
+  void* ptr;            /* base of the buffer (plane 0, channel 0 of pixel 0) */
+  int32_t cstride;      /* channels per pixel of the buffer */
+  int32_t coff;         /* first channel of the view */
+  int64_t plane_stride; /* UP_SPLIT: elements between hi and lo planes */
+} UpView;
+
+/* Train-mode nn.BatchNorm2d forward (resnet.py:26-34, wasp.py:18,86, decoder.py:40 in .train()):
+ *   up_bn_stats     per-channel sum / sum of squares of the conv output z over npix pixels -> sums[2*c] (double)
+ *   up_bn_finalize  batch mean / biased var -> scale, shift, save_mean, save_invstd; running stats updated with
+ *                   momentum and the unbiased variance (torch semantics); running_* may be NULL
+ *   up_scale_shift_act  y = [relu](z*scale + shift (+ residual)) (* mask)   (mask = pre-scaled dropout mask) */
+int up_bn_stats(const UpView* z, int64_t npix, int c, int dtype, double* sums, void* stream);
+int up_bn_finalize(const double* sums, int64_t count, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
+                   float* save_invstd, int c_real, int c, void* stream);
+int up_scale_shift_act(const UpView* z, const UpView* y, const UpView* residual, const UpView* mask,
+                       const float* scale, const float* shift, int64_t npix, int c, int relu, int dtype,
+                       void* stream);
+/* BatchNorm (+ReLU) backward: reduce sum(dy'), sum(dy'*xhat) with dy' = dy*(y>0) -> sums[2*c]; then
+ *   dz = gamma*invstd*(dy' - sum_dy/M - xhat*sum_dy_xhat/M), optional dres = dy', dgamma / dbeta (optional). */
+int up_bn_bwd_reduce(const UpView* dy, const UpView* y, const UpView* z, const float* save_mean,
+                     const float* save_invstd, int64_t npix, int c, int relu, int dtype, double* sums, void* stream);
+int up_bn_bwd_apply(const UpView* dy, const UpView* y, const UpView* z, const UpView* dz, const UpView* dres,
+                    const float* save_mean, const float* save_invstd, const float* gamma, const double* sums,
+                    int64_t npix, int c_real, int c, int relu, int dtype, float* dgamma, float* dbeta, void* stream);
+/* out (+)= a            (mode_op 0)
+ * out (+)= a * m        (mode_op 1, dropout mask)
+ * out (+)= a * (m > 0)  (mode_op 2, ReLU gate with the forward output m) */
+int up_ew_mul(const UpView* a, const UpView* m, const UpView* out, int64_t npix, int c, int mode_op, int accumulate,
+              int dtype, void* stream);
+/* adjoints of the bandwidth kernels */
+int up_maxpool3x3s2_bwd(const UpView* x, const UpView* dy, const UpView* dx, int n, int h, int w, int c,
+                        int accumulate, int dtype, void* stream);
+int up_upsample_bilinear_ac_bwd(const UpView* dy, const UpView* dx, int n, int h, int w, int ho, int wo, int c,
+                                int accumulate, int dtype, void* stream);
+/* dx[n,h,w,:] (+)= g[n,:] * mult  (adjoint of the global average pool with mult = 1/(h*w)) */
+int up_add_broadcast(const UpView* g, const UpView* dx, int n, int hw, int c, float mult, int accumulate, int dtype,
+                     void* stream);
+/* y[n,2i,2j,:] = x[n,i,j,:], zeros elsewhere */
+int up_zero_insert2x(const UpView* x, const UpView* y, int n, int h, int w, int c, int dtype, void* stream);
+
 /* torch.optim.Adam step (no weight decay, no amsgrad) over a flat fp32 buffer. */
 int up_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, float lr,
                  float beta1, float beta2, float eps, int step, void* stream);

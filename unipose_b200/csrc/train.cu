@@ -82,3 +82,628 @@ extern "C" int up_adam_step(float* param, const float* grad, float* exp_avg, flo
   UP_CHECK_LAUNCH("adam_kernel");
   return 0;
 }
+
+// =============================================================================================
+// Train-mode BatchNorm + backward bandwidth kernels (NHWC 16-bit activations / gradients)
+// =============================================================================================
+namespace up {
+
+template <int kMode>
+__device__ __forceinline__ void t_load8(const uint16_t* p, long long plane, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[2 * e + 0] = cvt16_to_f32<(kMode == 0 ? 0 : 1)>(static_cast<uint16_t>(w[e] & 0xFFFFu));
+    v[2 * e + 1] = cvt16_to_f32<(kMode == 0 ? 0 : 1)>(static_cast<uint16_t>(w[e] >> 16));
+  }
+  if constexpr (kMode == 2) {
+    const uint4 l = __ldg(reinterpret_cast<const uint4*>(p + plane));
+    const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[2 * e + 0] += cvt16_to_f32<1>(static_cast<uint16_t>(lw[e] & 0xFFFFu));
+      v[2 * e + 1] += cvt16_to_f32<1>(static_cast<uint16_t>(lw[e] >> 16));
+    }
+  }
+}
+
+template <int kMode>
+__device__ __forceinline__ void t_store8(uint16_t* p, long long plane, const float (&v)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if constexpr (kMode == 2) {
+      uint16_t h0, l0, h1, l1;
+      split_bf16(v[2 * e], h0, l0);
+      split_bf16(v[2 * e + 1], h1, l1);
+      h[e] = h0 | (uint32_t(h1) << 16);
+      l[e] = l0 | (uint32_t(l1) << 16);
+    } else {
+      h[e] = cvt_f32_to16<kMode>(v[2 * e]) | (uint32_t(cvt_f32_to16<kMode>(v[2 * e + 1])) << 16);
+    }
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+  if constexpr (kMode == 2) *reinterpret_cast<uint4*>(p + plane) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+struct TView {           // NHWC channel-slice view
+  const uint16_t* p;     // base of the buffer (plane 0)
+  int cs, coff;
+  long long plane;
+};
+struct TViewW {
+  uint16_t* p;
+  int cs, coff;
+  long long plane;
+};
+
+// Per-channel reduction skeleton: every thread owns one channel octet (c/8 is a power of two <= 256) and strides
+// over pixels; partial sums are combined in shared memory and added to the global double accumulators.
+// kWhat 0: sums of (x, x^2).  kWhat 1: sums of (dy', dy' * xhat) with dy' = dy * (y > 0 if relu).
+template <int kMode, int kWhat>
+__global__ void channel_reduce_kernel(TView a, TView b, TView c, const float* __restrict__ mean,
+                                      const float* __restrict__ invstd, double* __restrict__ sums, long long npix,
+                                      int ch, int relu) {
+  const int octs = ch / 8;
+  const int oct = threadIdx.x % octs;
+  const int pstride = blockDim.x / octs;
+  const int plane_lane = threadIdx.x / octs;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
+  float mu[8], is[8];
+  if (kWhat == 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      mu[e] = mean[oct * 8 + e];
+      is[e] = invstd[oct * 8 + e];
+    }
+  }
+  const long long per_block = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * per_block;
+  const long long p1 = min(p0 + per_block, npix);
+  for (long long px = p0 + plane_lane; px < p1; px += pstride) {
+    float va[8];
+    t_load8<kMode>(a.p + px * a.cs + a.coff + oct * 8, a.plane, va);
+    if (kWhat == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s0[e] += va[e];
+        s1[e] = fmaf(va[e], va[e], s1[e]);
+      }
+    } else {
+      float vz[8];
+      t_load8<kMode>(c.p + px * c.cs + c.coff + oct * 8, c.plane, vz);
+      if (relu) {
+        float vy[8];
+        t_load8<kMode>(b.p + px * b.cs + b.coff + oct * 8, b.plane, vy);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) va[e] = vy[e] > 0.f ? va[e] : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s0[e] += va[e];
+        s1[e] = fmaf(va[e], (vz[e] - mu[e]) * is[e], s1[e]);
+      }
+    }
+  }
+  extern __shared__ float red[];  // [blockDim.x][16]
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    red[threadIdx.x * 16 + e] = s0[e];
+    red[threadIdx.x * 16 + 8 + e] = s1[e];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < octs * 16; idx += blockDim.x) {
+    const int o = idx / 16, e = idx % 16;
+    double s = 0.0;
+    for (int q = 0; q < pstride; ++q) s += red[(q * octs + o) * 16 + e];
+    const int chn = o * 8 + (e & 7);
+    atomicAdd(sums + (e < 8 ? 0 : ch) + chn, s);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
+                                   float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ save_mean, float* __restrict__ save_invstd, int c_real, int c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  if (i >= c_real) {
+    scale[i] = 0.f;
+    shift[i] = 0.f;
+    save_mean[i] = 0.f;
+    save_invstd[i] = 0.f;
+    return;
+  }
+  const double mean = sums[i] / count;
+  double var = sums[c + i] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float sc = gamma[i] * invstd;
+  scale[i] = sc;
+  shift[i] = beta[i] - static_cast<float>(mean) * sc;
+  save_mean[i] = static_cast<float>(mean);
+  save_invstd[i] = invstd;
+  if (rmean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    rmean[i] = (1.f - momentum) * rmean[i] + momentum * static_cast<float>(mean);
+    rvar[i] = (1.f - momentum) * rvar[i] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+// y = [relu]( z * scale[c] + shift[c] (+ res) ) (* mask)
+template <int kMode>
+__global__ void scale_shift_act_kernel(TView z, TViewW y, TView res, TView mask, const float* __restrict__ scale,
+                                       const float* __restrict__ shift, long long npix, int ch, int relu, int has_res,
+                                       int has_mask) {
+  const int c8 = ch / 8;
+  const long long total = npix * c8;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % c8);
+  const long long px = i / c8;
+  float v[8];
+  t_load8<kMode>(z.p + px * z.cs + z.coff + g * 8, z.plane, v);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], scale[g * 8 + e], shift[g * 8 + e]);
+  if (has_res) {
+    float r[8];
+    t_load8<kMode>(res.p + px * res.cs + res.coff + g * 8, res.plane, r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += r[e];
+  }
+  if (relu) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+  }
+  if (has_mask) {
+    float m[8];
+    t_load8<kMode>(mask.p + px * mask.cs + mask.coff + g * 8, mask.plane, m);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= m[e];
+  }
+  t_store8<kMode>(y.p + px * y.cs + y.coff + g * 8, y.plane, v);
+}
+
+// dz = gamma*invstd * ( dy' - sum_dy/M - xhat * sum_dy_xhat/M ),  dy' = dy * (y > 0 if relu);  optional dres = dy'
+template <int kMode>
+__global__ void bn_bwd_apply_kernel(TView dy, TView y, TView z, TViewW dz, TViewW dres, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const double* __restrict__ sums, double count, long long npix, int ch, int c_real,
+                                    int relu, int has_dres) {
+  const int c8 = ch / 8;
+  const long long total = npix * c8;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % c8);
+  const long long px = i / c8;
+  float vd[8], vz[8], o[8];
+  t_load8<kMode>(dy.p + px * dy.cs + dy.coff + g * 8, dy.plane, vd);
+  t_load8<kMode>(z.p + px * z.cs + z.coff + g * 8, z.plane, vz);
+  if (relu) {
+    float vy[8];
+    t_load8<kMode>(y.p + px * y.cs + y.coff + g * 8, y.plane, vy);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) vd[e] = vy[e] > 0.f ? vd[e] : 0.f;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = g * 8 + e;
+    if (c < c_real) {
+      const float xhat = (vz[e] - mean[c]) * invstd[c];
+      const float m0 = static_cast<float>(sums[c] / count);
+      const float m1 = static_cast<float>(sums[ch + c] / count);
+      o[e] = gamma[c] * invstd[c] * (vd[e] - m0 - xhat * m1);
+    } else {
+      o[e] = 0.f;
+    }
+  }
+  t_store8<kMode>(dz.p + px * dz.cs + dz.coff + g * 8, dz.plane, o);
+  if (has_dres) t_store8<kMode>(dres.p + px * dres.cs + dres.coff + g * 8, dres.plane, vd);
+}
+
+__global__ void bn_bwd_params_kernel(const double* __restrict__ sums, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, int c_real, int c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c_real) return;
+  dbeta[i] = static_cast<float>(sums[i]);
+  dgamma[i] = static_cast<float>(sums[c + i]);
+}
+
+// out = (accumulate ? out : 0) + a * b_mask   /  generic masked ReLU-gate / plain add:  op 0: out = a (*mask)
+template <int kMode>
+__global__ void ew_mul_kernel(TView a, TView m, TViewW out, long long npix, int ch, int has_mask, int accumulate,
+                              int relu_gate) {
+  // relu_gate: `m` is the forward OUTPUT y; pass a where y > 0.  has_mask: multiply by m.
+  const int c8 = ch / 8;
+  const long long total = npix * c8;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % c8);
+  const long long px = i / c8;
+  float v[8];
+  t_load8<kMode>(a.p + px * a.cs + a.coff + g * 8, a.plane, v);
+  if (has_mask || relu_gate) {
+    float mm[8];
+    t_load8<kMode>(m.p + px * m.cs + m.coff + g * 8, m.plane, mm);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = relu_gate ? (mm[e] > 0.f ? v[e] : 0.f) : v[e] * mm[e];
+  }
+  uint16_t* op = out.p + px * out.cs + out.coff + g * 8;
+  if (accumulate) {
+    float o[8];
+    t_load8<kMode>(op, out.plane, o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += o[e];
+  }
+  t_store8<kMode>(op, out.plane, v);
+}
+
+// max-pool 3/2/1 backward (gather form): an input pixel receives dy of every window whose FIRST maximum
+// (row-major scan, like ATen) it is.
+template <int kMode>
+__global__ void maxpool3x3s2_bwd_kernel(TView x, TView dy, TViewW dx, int n, int h, int w, int ho, int wo, int ch,
+                                        int accumulate) {
+  const int c8 = ch / 8;
+  const long long total = static_cast<long long>(n) * h * w * c8;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % c8);
+  const long long ipix = i / c8;
+  const int ix = static_cast<int>(ipix % w);
+  long long t = ipix / w;
+  const int iy = static_cast<int>(t % h);
+  const int b = static_cast<int>(t / h);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  float self[8];
+  t_load8<kMode>(x.p + ipix * x.cs + x.coff + g * 8, x.plane, self);
+  for (int oy = (iy + 1) / 2 - ((iy + 1) % 2 == 0 ? 1 : 0); oy <= (iy + 1) / 2; ++oy) {
+    if (oy < 0 || oy >= ho) continue;
+    for (int ox = (ix + 1) / 2 - ((ix + 1) % 2 == 0 ? 1 : 0); ox <= (ix + 1) / 2; ++ox) {
+      if (ox < 0 || ox >= wo) continue;
+      // is (iy, ix) the first maximum of window (oy, ox)?
+      bool first[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) first[e] = true;
+      for (int dyy = 0; dyy < 3; ++dyy) {
+        const int yy = 2 * oy - 1 + dyy;
+        if (yy < 0 || yy >= h) continue;
+        for (int dxx = 0; dxx < 3; ++dxx) {
+          const int xx = 2 * ox - 1 + dxx;
+          if (xx < 0 || xx >= w) continue;
+          if (yy == iy && xx == ix) continue;
+          float v[8];
+          t_load8<kMode>(x.p + ((static_cast<long long>(b) * h + yy) * w + xx) * x.cs + x.coff + g * 8, x.plane, v);
+          const bool before = (yy < iy) || (yy == iy && xx < ix);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (before ? (v[e] >= self[e]) : (v[e] > self[e])) first[e] = false;
+          }
+        }
+      }
+      float d[8];
+      t_load8<kMode>(dy.p + ((static_cast<long long>(b) * ho + oy) * wo + ox) * dy.cs + dy.coff + g * 8, dy.plane, d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += first[e] ? d[e] : 0.f;
+    }
+  }
+  uint16_t* op = dx.p + ipix * dx.cs + dx.coff + g * 8;
+  if (accumulate) {
+    float o[8];
+    t_load8<kMode>(op, dx.plane, o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += o[e];
+  }
+  t_store8<kMode>(op, dx.plane, acc);
+}
+
+// adjoint of the align_corners bilinear up-sampling (gather form, separable weights)
+template <int kMode>
+__global__ void upsample_bilinear_ac_bwd_kernel(TView dy, TViewW dx, int n, int h, int w, int ho, int wo, int ch,
+                                                float sh, float sw, int accumulate) {
+  const int c8 = ch / 8;
+  const long long total = static_cast<long long>(n) * h * w * c8;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % c8);
+  const long long ipix = i / c8;
+  const int ix = static_cast<int>(ipix % w);
+  long long t = ipix / w;
+  const int iy = static_cast<int>(t % h);
+  const int b = static_cast<int>(t / h);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  const int oy_lo = sh > 0.f ? max(0, static_cast<int>(floorf((iy - 1) / sh)) - 1) : 0;
+  const int oy_hi = sh > 0.f ? min(ho - 1, static_cast<int>(ceilf((iy + 1) / sh)) + 1) : ho - 1;
+  const int ox_lo = sw > 0.f ? max(0, static_cast<int>(floorf((ix - 1) / sw)) - 1) : 0;
+  const int ox_hi = sw > 0.f ? min(wo - 1, static_cast<int>(ceilf((ix + 1) / sw)) + 1) : wo - 1;
+  for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+    const float fy = sh * oy;
+    const int y0 = static_cast<int>(fy);
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+    const float ly1 = fy - y0, ly0 = 1.f - ly1;
+    const float wy = (y0 == iy ? ly0 : 0.f) + (y1 == iy ? ly1 : 0.f);
+    if (wy == 0.f) continue;
+    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+      const float fx = sw * ox;
+      const int x0 = static_cast<int>(fx);
+      const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+      const float lx1 = fx - x0, lx0 = 1.f - lx1;
+      const float wx = (x0 == ix ? lx0 : 0.f) + (x1 == ix ? lx1 : 0.f);
+      if (wx == 0.f) continue;
+      float d[8];
+      t_load8<kMode>(dy.p + ((static_cast<long long>(b) * ho + oy) * wo + ox) * dy.cs + dy.coff + g * 8, dy.plane, d);
+      const float ww = wy * wx;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(ww, d[e], acc[e]);
+    }
+  }
+  uint16_t* op = dx.p + ipix * dx.cs + dx.coff + g * 8;
+  if (accumulate) {
+    float o[8];
+    t_load8<kMode>(op, dx.plane, o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += o[e];
+  }
+  t_store8<kMode>(op, dx.plane, acc);
+}
+
+// dx[n,h,w,:] (+)= g[n,:] * mult   (adjoint of the global average pool: mult = 1/(h*w))
+template <int kMode>
+__global__ void add_broadcast_kernel(TView gsrc, TViewW dx, int n, int hw, int ch, float mult, int accumulate) {
+  const int c8 = ch / 8;
+  const long long total = static_cast<long long>(n) * hw * c8;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % c8);
+  const long long px = i / c8;
+  const int b = static_cast<int>(px / hw);
+  float v[8];
+  t_load8<kMode>(gsrc.p + static_cast<long long>(b) * gsrc.cs + gsrc.coff + g * 8, gsrc.plane, v);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] *= mult;
+  uint16_t* op = dx.p + px * dx.cs + dx.coff + g * 8;
+  if (accumulate) {
+    float o[8];
+    t_load8<kMode>(op, dx.plane, o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += o[e];
+  }
+  t_store8<kMode>(op, dx.plane, v);
+}
+
+// zero insertion: y[n, 2i, 2j, :] = x[n, i, j, :], everything else 0 (turns a stride-2 dgrad into a stride-1 conv)
+template <int kMode>
+__global__ void zero_insert2x_kernel(TView x, TViewW y, int n, int h, int w, int ch) {
+  const int c8 = ch / 8;
+  const long long total = static_cast<long long>(n) * (2 * h) * (2 * w) * c8;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % c8);
+  const long long opix = i / c8;
+  const int ox = static_cast<int>(opix % (2 * w));
+  long long t = opix / (2 * w);
+  const int oy = static_cast<int>(t % (2 * h));
+  const int b = static_cast<int>(t / (2 * h));
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  if ((ox & 1) == 0 && (oy & 1) == 0) {
+    t_load8<kMode>(x.p + ((static_cast<long long>(b) * h + oy / 2) * w + ox / 2) * x.cs + x.coff + g * 8, x.plane, v);
+  }
+  t_store8<kMode>(y.p + opix * y.cs + y.coff + g * 8, y.plane, v);
+}
+
+}  // namespace up
+
+#define UP_T_DISPATCH(dtype, ...)                                      \
+  do {                                                                 \
+    if ((dtype) == UP_FP16) {                                          \
+      constexpr int kMode = 0;                                         \
+      __VA_ARGS__;                                                     \
+    } else if ((dtype) == UP_BF16) {                                   \
+      constexpr int kMode = 1;                                         \
+      __VA_ARGS__;                                                     \
+    } else if ((dtype) == UP_SPLIT) {                                  \
+      constexpr int kMode = 2;                                         \
+      __VA_ARGS__;                                                     \
+    } else {                                                           \
+      return ::up::fail(UP_ERR_INVALID, "bad dtype %d", (int)(dtype)); \
+    }                                                                  \
+  } while (0)
+
+static inline up::TView tv(const UpView* v) {
+  up::TView t{};
+  if (v) {
+    t.p = static_cast<const uint16_t*>(v->ptr);
+    t.cs = v->cstride;
+    t.coff = v->coff;
+    t.plane = v->plane_stride;
+  }
+  return t;
+}
+static inline up::TViewW tvw(const UpView* v) {
+  up::TViewW t{};
+  if (v) {
+    t.p = static_cast<uint16_t*>(v->ptr);
+    t.cs = v->cstride;
+    t.coff = v->coff;
+    t.plane = v->plane_stride;
+  }
+  return t;
+}
+static int check_view(const char* who, const UpView* v, int c) {
+  UP_CHECK_ARG(v && v->ptr, "%s: null view", who);
+  UP_CHECK_ARG(c % 8 == 0 && v->cstride % 8 == 0 && v->coff % 8 == 0 && v->coff + c <= v->cstride,
+               "%s: bad channel view (c %d cstride %d coff %d)", who, c, v->cstride, v->coff);
+  UP_CHECK_ARG((reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0, "%s: view not 16-byte aligned", who);
+  return 0;
+}
+static inline int blocks_for(long long total) { return static_cast<int>((total + 255) / 256); }
+
+extern "C" int up_bn_stats(const UpView* x, int64_t npix, int c, int dtype, double* sums, void* stream) {
+  int rc = check_view("up_bn_stats", x, c);
+  if (rc) return rc;
+  UP_CHECK_ARG(sums && npix > 0, "up_bn_stats: bad argument");
+  const int octs = c / 8;
+  UP_CHECK_ARG(octs <= 256 && (octs & (octs - 1)) == 0, "up_bn_stats: c/8 must be a power of two <= 256 (c = %d)", c);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = up::check_cuda(cudaMemsetAsync(sums, 0, 2 * c * sizeof(double), st), "cudaMemsetAsync(bn sums)");
+  if (rc) return rc;
+  long long grid = (npix + 255) / 256;
+  if (grid > 1184) grid = 1184;
+  UP_T_DISPATCH(dtype, (up::channel_reduce_kernel<kMode, 0><<<static_cast<int>(grid), 256, 256 * 16 * sizeof(float), st>>>(
+                           tv(x), up::TView{}, up::TView{}, nullptr, nullptr, sums, npix, c, 0)));
+  UP_CHECK_LAUNCH("channel_reduce_kernel<stats>");
+  return 0;
+}
+
+extern "C" int up_bn_finalize(const double* sums, int64_t count, const float* gamma, const float* beta,
+                              float* running_mean, float* running_var, float momentum, float eps, float* scale,
+                              float* shift, float* save_mean, float* save_invstd, int c_real, int c, void* stream) {
+  UP_CHECK_ARG(sums && gamma && beta && scale && shift && save_mean && save_invstd && count > 0 && c >= c_real,
+               "up_bn_finalize: bad argument");
+  up::bn_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums, static_cast<double>(count), gamma, beta, running_mean, running_var, momentum, eps, scale, shift, save_mean,
+      save_invstd, c_real, c);
+  UP_CHECK_LAUNCH("bn_finalize_kernel");
+  return 0;
+}
+
+extern "C" int up_scale_shift_act(const UpView* z, const UpView* y, const UpView* residual, const UpView* mask,
+                                  const float* scale, const float* shift, int64_t npix, int c, int relu, int dtype,
+                                  void* stream) {
+  int rc = check_view("up_scale_shift_act(z)", z, c);
+  if (rc) return rc;
+  rc = check_view("up_scale_shift_act(y)", y, c);
+  if (rc) return rc;
+  if (residual && (rc = check_view("up_scale_shift_act(residual)", residual, c))) return rc;
+  if (mask && (rc = check_view("up_scale_shift_act(mask)", mask, c))) return rc;
+  UP_CHECK_ARG(scale && shift && npix > 0, "up_scale_shift_act: bad argument");
+  UP_T_DISPATCH(dtype, (up::scale_shift_act_kernel<kMode><<<blocks_for(npix*(c / 8)), 256, 0, (cudaStream_t)stream>>>(
+                           tv(z), tvw(y), tv(residual), tv(mask), scale, shift, npix, c, relu, residual != nullptr,
+                           mask != nullptr)));
+  UP_CHECK_LAUNCH("scale_shift_act_kernel");
+  return 0;
+}
+
+extern "C" int up_bn_bwd_reduce(const UpView* dy, const UpView* y, const UpView* z, const float* save_mean,
+                                const float* save_invstd, int64_t npix, int c, int relu, int dtype, double* sums,
+                                void* stream) {
+  int rc = check_view("up_bn_bwd_reduce(dy)", dy, c);
+  if (rc) return rc;
+  rc = check_view("up_bn_bwd_reduce(z)", z, c);
+  if (rc) return rc;
+  if (relu && (rc = check_view("up_bn_bwd_reduce(y)", y, c))) return rc;
+  const int octs = c / 8;
+  UP_CHECK_ARG(octs <= 256 && (octs & (octs - 1)) == 0, "up_bn_bwd_reduce: c/8 must be a power of two <= 256");
+  UP_CHECK_ARG(save_mean && save_invstd && sums && npix > 0, "up_bn_bwd_reduce: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = up::check_cuda(cudaMemsetAsync(sums, 0, 2 * c * sizeof(double), st), "cudaMemsetAsync(bn bwd sums)");
+  if (rc) return rc;
+  long long grid = (npix + 255) / 256;
+  if (grid > 1184) grid = 1184;
+  UP_T_DISPATCH(dtype, (up::channel_reduce_kernel<kMode, 1><<<static_cast<int>(grid), 256, 256 * 16 * sizeof(float), st>>>(
+                           tv(dy), tv(y), tv(z), save_mean, save_invstd, sums, npix, c, relu)));
+  UP_CHECK_LAUNCH("channel_reduce_kernel<bn bwd>");
+  return 0;
+}
+
+extern "C" int up_bn_bwd_apply(const UpView* dy, const UpView* y, const UpView* z, const UpView* dz,
+                               const UpView* dres, const float* save_mean, const float* save_invstd,
+                               const float* gamma, const double* sums, int64_t npix, int c_real, int c, int relu,
+                               int dtype, float* dgamma, float* dbeta, void* stream) {
+  int rc = check_view("up_bn_bwd_apply(dy)", dy, c);
+  if (rc) return rc;
+  rc = check_view("up_bn_bwd_apply(z)", z, c);
+  if (rc) return rc;
+  rc = check_view("up_bn_bwd_apply(dz)", dz, c);
+  if (rc) return rc;
+  if (relu && (rc = check_view("up_bn_bwd_apply(y)", y, c))) return rc;
+  if (dres && (rc = check_view("up_bn_bwd_apply(dres)", dres, c))) return rc;
+  UP_CHECK_ARG(save_mean && save_invstd && gamma && sums && npix > 0 && c_real <= c, "up_bn_bwd_apply: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  UP_T_DISPATCH(dtype, (up::bn_bwd_apply_kernel<kMode><<<blocks_for(npix*(c / 8)), 256, 0, st>>>(
+                           tv(dy), tv(y), tv(z), tvw(dz), tvw(dres), save_mean, save_invstd, gamma, sums,
+                           static_cast<double>(npix), npix, c, c_real, relu, dres != nullptr)));
+  UP_CHECK_LAUNCH("bn_bwd_apply_kernel");
+  if (dgamma && dbeta) {
+    up::bn_bwd_params_kernel<<<(c_real + 127) / 128, 128, 0, st>>>(sums, dgamma, dbeta, c_real, c);
+    UP_CHECK_LAUNCH("bn_bwd_params_kernel");
+  }
+  return 0;
+}
+
+extern "C" int up_ew_mul(const UpView* a, const UpView* m, const UpView* out, int64_t npix, int c, int mode_op,
+                         int accumulate, int dtype, void* stream) {
+  // mode_op: 0 copy/add, 1 multiply by m, 2 ReLU gate (pass where m > 0)
+  int rc = check_view("up_ew_mul(a)", a, c);
+  if (rc) return rc;
+  rc = check_view("up_ew_mul(out)", out, c);
+  if (rc) return rc;
+  if (mode_op != 0 && (rc = check_view("up_ew_mul(m)", m, c))) return rc;
+  UP_T_DISPATCH(dtype, (up::ew_mul_kernel<kMode><<<blocks_for(npix*(c / 8)), 256, 0, (cudaStream_t)stream>>>(
+                           tv(a), tv(m), tvw(out), npix, c, mode_op == 1, accumulate, mode_op == 2)));
+  UP_CHECK_LAUNCH("ew_mul_kernel");
+  return 0;
+}
+
+extern "C" int up_maxpool3x3s2_bwd(const UpView* x, const UpView* dy, const UpView* dx, int n, int h, int w, int c,
+                                   int accumulate, int dtype, void* stream) {
+  int rc = check_view("up_maxpool3x3s2_bwd(x)", x, c);
+  if (rc) return rc;
+  rc = check_view("up_maxpool3x3s2_bwd(dy)", dy, c);
+  if (rc) return rc;
+  rc = check_view("up_maxpool3x3s2_bwd(dx)", dx, c);
+  if (rc) return rc;
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  UP_T_DISPATCH(dtype, (up::maxpool3x3s2_bwd_kernel<kMode><<<blocks_for((long long)n * h * w * (c / 8)), 256, 0,
+                                                             (cudaStream_t)stream>>>(tv(x), tv(dy), tvw(dx), n, h, w, ho,
+                                                                                     wo, c, accumulate)));
+  UP_CHECK_LAUNCH("maxpool3x3s2_bwd_kernel");
+  return 0;
+}
+
+extern "C" int up_upsample_bilinear_ac_bwd(const UpView* dy, const UpView* dx, int n, int h, int w, int ho, int wo,
+                                           int c, int accumulate, int dtype, void* stream) {
+  int rc = check_view("up_upsample_bilinear_ac_bwd(dy)", dy, c);
+  if (rc) return rc;
+  rc = check_view("up_upsample_bilinear_ac_bwd(dx)", dx, c);
+  if (rc) return rc;
+  const float sh = ho > 1 ? static_cast<float>(h - 1) / static_cast<float>(ho - 1) : 0.f;
+  const float sw = wo > 1 ? static_cast<float>(w - 1) / static_cast<float>(wo - 1) : 0.f;
+  UP_T_DISPATCH(dtype, (up::upsample_bilinear_ac_bwd_kernel<kMode><<<blocks_for((long long)n * h * w * (c / 8)), 256, 0,
+                                                                     (cudaStream_t)stream>>>(
+                           tv(dy), tvw(dx), n, h, w, ho, wo, c, sh, sw, accumulate)));
+  UP_CHECK_LAUNCH("upsample_bilinear_ac_bwd_kernel");
+  return 0;
+}
+
+extern "C" int up_add_broadcast(const UpView* g, const UpView* dx, int n, int hw, int c, float mult, int accumulate,
+                                int dtype, void* stream) {
+  int rc = check_view("up_add_broadcast(g)", g, c);
+  if (rc) return rc;
+  rc = check_view("up_add_broadcast(dx)", dx, c);
+  if (rc) return rc;
+  UP_T_DISPATCH(dtype, (up::add_broadcast_kernel<kMode><<<blocks_for((long long)n * hw * (c / 8)), 256, 0,
+                                                          (cudaStream_t)stream>>>(tv(g), tvw(dx), n, hw, c, mult,
+                                                                                  accumulate)));
+  UP_CHECK_LAUNCH("add_broadcast_kernel");
+  return 0;
+}
+
+extern "C" int up_zero_insert2x(const UpView* x, const UpView* y, int n, int h, int w, int c, int dtype, void* stream) {
+  int rc = check_view("up_zero_insert2x(x)", x, c);
+  if (rc) return rc;
+  rc = check_view("up_zero_insert2x(y)", y, c);
+  if (rc) return rc;
+  UP_T_DISPATCH(dtype, (up::zero_insert2x_kernel<kMode><<<blocks_for((long long)n * 4 * h * w * (c / 8)), 256, 0,
+                                                          (cudaStream_t)stream>>>(tv(x), tvw(y), n, h, w, c)));
+  UP_CHECK_LAUNCH("zero_insert2x_kernel");
+  return 0;
+}

@@ -133,12 +133,12 @@ class ResNet(PlanModule):
         if h % 16 or w % 16:
             raise ValueError('unipose_b200: input height/width must be multiples of 16 (got %dx%d)' % (h, w))
         x2 = b.act(n, h // 2, w // 2, 16)
-        b.add(lambda: ops.pack_input_s2d(x_static, x2), "pack_input_s2d")
+        b.add(lambda x_static=x_static, x2=x2: ops.pack_input_s2d(x_static, x2), "pack_input_s2d")
         stem = b.act(n, h // 2, w // 2, 64)
         pc = b.packed_conv(self.conv1, self.bn1, cin_pad=16, weight_fn=stem_s2d_weight)
         b.conv(x2, pc, stem, "stem", pad=2, relu=True, ho=h // 2, wo=w // 2)
         x = b.act(n, h // 4, w // 4, 64)
-        b.add(lambda: ops.maxpool3x3s2(stem, x), "maxpool")
+        b.add(lambda stem=stem, x=x: ops.maxpool3x3s2(stem, x), "maxpool")
         low = None
         for name in ('layer1', 'layer2', 'layer3', 'layer4'):
             for blk in getattr(self, name):

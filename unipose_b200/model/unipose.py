@@ -37,9 +37,9 @@ class unipose(PlanModule):
         heat = self.decoder._emit(b, x, low)
         if self.stride != 8:   # model/unipose.py:31-32
             full = b.tensor((shape[0], heat.shape[1], shape[2], shape[3]))
-            b.add(lambda: ops._lib.call("up_upsample_bilinear_ac_nchw_f32", ops._ptr(heat), ops._ptr(full), shape[0],
-                                        heat.shape[1], heat.shape[2], heat.shape[3], shape[2], shape[3],
-                                        ops._stream()), "upsample_to_input")
+            b.add(lambda heat=heat, full=full: ops._lib.call(
+                "up_upsample_bilinear_ac_nchw_f32", ops._ptr(heat), ops._ptr(full), shape[0], heat.shape[1],
+                heat.shape[2], heat.shape[3], shape[2], shape[3], ops._stream()), "upsample_to_input")
             heat = full
         plan.finalize([heat])
         return plan
