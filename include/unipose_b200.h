@@ -96,6 +96,11 @@ typedef struct UpConvDesc {
   int32_t cout_valid;          /* UP_FLAG_OUT_NCHW_F32: number of real output channels written */
   int32_t out_c_total;         /* UP_FLAG_OUT_NCHW_F32: channels of the fp32 NCHW destination (0 -> cout_valid);
                                   lets the head write the first cout_valid channels of a wider tensor */
+  int32_t x_cextent;           /* 0, or > x_cstride: OVERLAPPING channel windows - the K-chunk of a "pixel" spans
+                                  x_cextent consecutive elements (several neighbouring pixels) while pixels stay
+                                  x_cstride elements apart (stride 1, x_groups 1).  The 2x2 space-to-depth stem uses
+                                  x_cstride 16 / x_cextent 64: one K-chunk = 4 horizontal taps x 16 channels. */
+  int32_t x_wpitch;            /* 0, or the row pitch of x in pixels when rows are padded (>= w) */
   int64_t x_plane_stride;      /* UP_SPLIT: elements between hi and lo planes */
   int64_t y_plane_stride;
   int64_t r_plane_stride;
@@ -120,9 +125,11 @@ int up_bn_fold(const float* gamma, const float* beta, const float* mean, const f
  * Bandwidth kernels (NHWC 16-bit unless noted)
  * ------------------------------------------------------------------------------------------ */
 /* fp32 NCHW image [n,3,h,w] -> 2x2 space-to-depth NHWC [n,h/2,w/2,16] (12 real channels, order
- * (ph,pw,c)), so that the 7x7/s2 stem (resnet.py:61,114) becomes a 4x4/s1 tensor-core conv. */
+ * (ph,pw,c)), so that the 7x7/s2 stem (resnet.py:61,114) becomes a 4x4/s1 tensor-core conv.  Rows of y may
+ * be padded: pixel (yq, xq) is written at row pitch y_wpitch (0 -> w/2) and column xq + y_wpad_left; the
+ * padding pixels are left untouched (the caller zero-fills them once). */
 int up_pack_input_s2d(const float* x_nchw, void* y, int n, int h, int w, int dtype, int64_t y_plane_stride,
-                      void* stream);
+                      int y_wpitch, int y_wpad_left, void* stream);
 /* Generic fp32 NCHW [n,c_real,h,w] -> NHWC 16-bit view (channels >= c_real zero-filled up to c). */
 int up_nchw_f32_to_nhwc(const float* x, void* y, int n, int c_real, int h, int w, int c, int y_cstride,
                         int y_coff, int dtype, int64_t y_plane_stride, void* stream);

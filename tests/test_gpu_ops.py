@@ -62,12 +62,38 @@ def test_pack_input_s2d_matches_definition():
     from unipose_b200 import ops
     dev = torch.device("cuda:0")
     x = torch.randn(2, 3, 32, 48, device=dev)
-    a = ops.Act(2, 16, 24, 16, ops.UP_SPLIT, dev)
-    ops.pack_input_s2d(x, a)
+    a = ops.Act(2, 16, 24 + 3, 16, ops.UP_SPLIT, dev, zero=True)
+    ops.pack_input_s2d(x, a, wpad_left=2)
     ref = x.view(2, 3, 16, 2, 24, 2).permute(0, 2, 4, 3, 5, 1).reshape(2, 16, 24, 12)
     got = a.to_float()
-    assert (got[..., :12] - ref).abs().max() < 1e-4
+    assert (got[:, :, 2:26, :12] - ref).abs().max() < 1e-4
     assert float(got[..., 12:].abs().max()) == 0.0
+    assert float(got[:, :, :2].abs().max()) == 0.0 and float(got[:, :, 26:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16", 2 ** -7), ("fp32", 1e-4)])
+def test_stem_as_overlapping_window_conv(prec, tol):
+    """7x7/s2 stem (resnet.py:61) = 4-row conv over 64-element windows of the row-padded space-to-depth image."""
+    from unipose_b200 import ops
+    from unipose_b200.model.modules.backbone.resnet import stem_window_weight
+    dev = torch.device("cuda:0")
+    mode = ops.mode_of(prec)
+    torch.manual_seed(3)
+    n, h, w = 3, 64, 96
+    x = torch.randn(n, 3, h, w, device=dev)
+    wt = torch.randn(64, 3, 7, 7, device=dev) / (3 * 49) ** 0.5
+    x2 = ops.Act(n, h // 2, w // 2 + 3, 16, mode, dev, zero=True)
+    ops.pack_input_s2d(x, x2, wpad_left=2)
+    pc = ops.make_packed_conv(stem_window_weight(wt), mode, cout=64, cin=64)
+    y = ops.Act(n, h // 2, w // 2, 64, mode, dev)
+    ops.conv2d(x2, pc, y, pad=(2, 0), relu=False, ho=h // 2, wo=w // 2, x_window=(w // 2, 64))
+    if prec == "bf16":
+        xq, wq = x.bfloat16().double(), wt.bfloat16().double()
+    else:
+        xq, wq = x.double(), wt.double()
+    ref = F.conv2d(xq, wq, stride=2, padding=3)
+    got = y.to_float().permute(0, 3, 1, 2).double()
+    assert (got - ref).abs().max() <= tol * ref.abs().max() + tol * ref.abs().mean()
 
 
 def test_fp32_nchw_bilinear_and_avgpool():

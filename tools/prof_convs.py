@@ -16,7 +16,6 @@ from unipose_b200 import ops  # noqa: E402
 
 # name, n, h, w, cin, cout, k, stride, dil, residual, cin_pad_override
 CONVS = [
-    ("stem_4x4_ck16", 32, 192, 192, 16, 64, 4, 1, 1, False),
     ("l1_conv2_3x3_64", 32, 96, 96, 64, 64, 3, 1, 1, False),
     ("l1_conv3_1x1_64_256_res", 32, 96, 96, 64, 256, 1, 1, 1, True),
     ("l3_conv1_1x1_1024_256", 32, 24, 24, 1024, 256, 1, 1, 1, False),
@@ -44,7 +43,7 @@ def main():
         x.t.copy_(torch.randn(x.t.shape, device=dev))
         wt = torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5
         pc = ops.make_packed_conv(wt, mode, cout=cout, cin=cin)
-        pad = 2 if name.startswith("stem") else dil * (k - 1) // 2
+        pad = dil * (k - 1) // 2
         ho, wo = h // stride, w // stride
         y = ops.Act(n, ho, wo, cout, mode, dev)
         r = None

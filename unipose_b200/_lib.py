@@ -28,6 +28,7 @@ class UpConvDesc(ctypes.Structure):
         ("r_cstride", c_int32), ("r_coff", c_int32),
         ("dtype", c_int32), ("flags", c_int32),
         ("cout_valid", c_int32), ("out_c_total", c_int32),
+        ("x_cextent", c_int32), ("x_wpitch", c_int32),
         ("x_plane_stride", c_int64), ("y_plane_stride", c_int64),
         ("r_plane_stride", c_int64), ("w_plane_stride", c_int64),
     ]
@@ -46,7 +47,7 @@ _SIGNATURES = {
     "up_conv2d_fwd": [POINTER(UpConvDesc), _P, _P, _P, _P, _P, _P, _P, _P],
     "up_pack_conv_weight": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _L, _P],
     "up_bn_fold": [_P, _P, _P, _P, _F, _P, _P, _I, _I, _P],
-    "up_pack_input_s2d": [_P, _P, _I, _I, _I, _I, _L, _P],
+    "up_pack_input_s2d": [_P, _P, _I, _I, _I, _I, _L, _I, _I, _P],
     "up_nchw_f32_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _L, _P],
     "up_nhwc_to_nchw_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _L, _P],
     "up_maxpool3x3s2": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P],
@@ -62,10 +63,26 @@ _SIGNATURES = {
     "up_dist_acc": [_P, _P, _I, _I, _D, _P],
     "up_mse_fwd_bwd": [_P, _P, _P, _P, _P, _L, _F, _P],
     "up_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P],
+    "up_conv2d_wgrad": [POINTER(UpConvDesc), _P, _P, _P, _I, _I, _P, _L, _I, _P],
+    "up_bn_stats": [_P, _L, _I, _I, _P, _P],
+    "up_bn_finalize": [_P, _L, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _I, _I, _P],
+    "up_scale_shift_act": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
+    "up_bn_bwd_reduce": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _P, _P],
+    "up_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P, _P, _P],
+    "up_ew_mul": [_P, _P, _P, _L, _I, _I, _I, _I, _P],
+    "up_maxpool3x3s2_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "up_upsample_bilinear_ac_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "up_add_broadcast": [_P, _P, _I, _I, _I, _F, _I, _I, _P],
+    "up_zero_insert2x": [_P, _P, _I, _I, _I, _I, _I, _P],
 }
+_RESTYPES = {"up_conv2d_wgrad_scratch_bytes": (c_int64, [POINTER(UpConvDesc)])}
+
+
+class UpView(ctypes.Structure):
+    _fields_ = [("ptr", c_void_p), ("cstride", c_int32), ("coff", c_int32), ("plane_stride", c_int64)]
 
 # Every symbol include/unipose_b200.h declares (tests check the .so exports all of them).
-DECLARED_SYMBOLS = ["up_last_error"] + list(_SIGNATURES)
+DECLARED_SYMBOLS = ["up_last_error"] + list(_SIGNATURES) + list(_RESTYPES)
 
 _lib = None
 
@@ -99,6 +116,11 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
             continue  # reported by the symbol test; calling it raises below
         fn.argtypes = args
         fn.restype = c_int
+    for name, (res, args) in _RESTYPES.items():
+        fn = getattr(lib, name, None)
+        if fn is not None:
+            fn.argtypes = args
+            fn.restype = res
     _lib = lib
     return lib
 

@@ -7,17 +7,21 @@
 //             N = output channels (tile = block_n in {32,64,128,256}),
 //             K = taps x input channels (k-block = one tap x `ck` channels, ck in {16,64}).
 //
-// Persistent, warp-specialised CTA (256 threads, 1 CTA / SM):
-//   warp 0 lane 0 : TMA producer            (smem ring: full/empty mbarriers)
-//   warp 1 lane 0 : tcgen05.mma issuer      (TMEM double buffer: tmem_full/tmem_empty mbarriers)
-//   warp 2        : TMEM allocator / deallocator
-//   warps 4..7    : epilogue (TMEM -> regs -> smem staging -> TMA store), overlaps the next tile's MMAs
+// Persistent, warp-specialised CTA (384 threads, 1 CTA / SM):
+//   warp 0 (32 lanes) : TMA producer - every lane owns every 32nd k-block, so the scalar address arithmetic of
+//                       32 k-blocks runs in parallel (a single producer thread was the bottleneck of small-K layers)
+//   warp 1 lane 0     : tcgen05.mma issuer   (smem ring: full/empty mbarriers; TMEM double buffer: tfull/tempty)
+//   warp 2            : TMEM alloc/dealloc; lane 0 = epilogue DMA thread: TMA-prefetches the residual tile of each
+//                       64-channel group into a staging buffer and TMA-stores the finished group (avail/ready mbarriers)
+//   warps 4..11       : epilogue math: TMEM -> regs, scale/shift (+ residual from smem) (+ ReLU), pack, write the
+//                       staging buffer in place.  Two warps per TMEM lane quarter, each takes 32 of the 64 columns.
 //
-// Filter taps whose whole input box lies outside the image contribute exact zeros and are skipped by
-// producer and issuer alike (large-dilation WASP convs on small maps: wasp.py:47-49).
+// Filter taps whose whole input box lies outside the image contribute exact zeros and are skipped by producer and
+// issuer alike (large-dilation WASP convs on small maps: wasp.py:47-49); the in-bounds taps of a tile always form a
+// rectangle [kh_lo,kh_hi] x [kw_lo,kw_hi].
 //
-// UP_SPLIT ("fp32-grade") mode: activations and weights are bf16 hi+lo planes; every k-block is issued
-// three times (hi*hi, lo*hi, hi*lo) into the same fp32 accumulator.
+// UP_SPLIT ("fp32-grade") mode: activations and weights are bf16 hi+lo planes; every k-block is issued three times
+// (hi*hi, lo*hi, hi*lo) into the same fp32 accumulator.
 #include <cuda.h>
 
 #include "up_internal.h"
@@ -26,10 +30,12 @@
 namespace up {
 
 constexpr int kMaxStages = 8;
+constexpr int kMaxBufs = 4;
 constexpr int kTileM = 128;
-constexpr int kStagingBytes = 2 * 16384;  // two 128-row x 128-byte output staging buffers
-constexpr int kEpiThreads = 128;
+constexpr int kThreads = 384;
+constexpr int kEpiThreads = 256;
 constexpr int kEpiWarp0 = 4;
+constexpr int kPlaneBytes = 16384;  // one 128-row x 128-byte staging plane
 
 struct ConvKParams {
   int N, Hq, Wq;  // input extent in box coordinates (H/stride, W/stride)
@@ -42,20 +48,16 @@ struct ConvKParams {
   int n_tiles, block_n;
   int cout;
   int nterms;
-  int stages;
-  uint32_t a_bytes, b_bytes;
+  int stages, nbuf;
+  uint32_t a_bytes, b_bytes, buf_bytes;
   uint32_t idesc;
   uint32_t tmem_cols;
   int flags, fmt, split;
   int cout_valid, out_c_total;
-  int y_coff;
-  int r_cs, r_coff;
-  long long r_plane;
+  int y_coff, r_coff;
   const float* scale;
   const float* shift;
-  const uint16_t* res;
   float* out_f32;
-  float* stats;
 };
 
 struct TileCoord {
@@ -76,55 +78,65 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile)
   return t;
 }
 
-// Box origin (ch, cw) and parity plane (ph, pw) of filter tap (kh, kw) for the tile at (h0, w0);
-// returns false when the box cannot touch the image.
-__device__ __forceinline__ bool tap_box(const ConvKParams& p, int h0, int w0, int kh, int kw, int& ch, int& cw,
-                                        int& ph, int& pw) {
-  int oh = kh * p.dil - p.pad_h;
-  int ow = kw * p.dil - p.pad_w;
-  ph = 0;
-  pw = 0;
+// Offset of filter tap k along one axis in box coordinates (+ parity plane for stride 2).
+__device__ __forceinline__ void tap_offset(const ConvKParams& p, int k, int pad, int& off, int& par) {
+  int o = k * p.dil - pad;
+  par = 0;
   if (p.stride == 2) {
-    ph = oh & 1;
-    pw = ow & 1;
-    oh = (oh - ph) >> 1;
-    ow = (ow - pw) >> 1;
+    par = o & 1;
+    o = (o - par) >> 1;
   }
-  ch = h0 + oh;
-  cw = w0 + ow;
-  return (ch + p.bh > 0) && (ch < p.Hq) && (cw + p.bw > 0) && (cw < p.Wq);
+  off = o;
 }
 
-__device__ __forceinline__ float load16(const uint16_t* p, int fmt) { return cvt16_to_f32_rt(*p, fmt); }
+// Inclusive range of taps along one axis whose box [x0+off, x0+off+ext) touches [0, limit).
+__device__ __forceinline__ void tap_range(const ConvKParams& p, int taps, int pad, int x0, int ext, int limit, int& lo,
+                                          int& hi) {
+  lo = taps;
+  hi = -1;
+  for (int k = 0; k < taps; ++k) {
+    int off, par;
+    tap_offset(p, k, pad, off, par);
+    const int c = x0 + off;
+    if (c + ext > 0 && c < limit) {
+      lo = min(lo, k);
+      hi = max(hi, k);
+    }
+  }
+}
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kThreads, 1)
     conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                         const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY0,
-                        const __grid_constant__ CUtensorMap tmY1, const ConvKParams p) {
+                        const __grid_constant__ CUtensorMap tmY1, const __grid_constant__ CUtensorMap tmR0,
+                        const __grid_constant__ CUtensorMap tmR1, const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: required by the 128B swizzle atoms of TMA and the UMMA descriptors.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
   const uint32_t staging = smem_base + p.stages * stage_bytes;
-  const uint32_t bars = staging + kStagingBytes;
-  // barrier layout (8 bytes each): full[kMaxStages] empty[kMaxStages] tmem_full[2] tmem_empty[2] ; then tmem ptr
+  const uint32_t bars = staging + p.nbuf * p.buf_bytes;
+  // barriers (8 bytes each): full[8] empty[8] tfull[2] tempty[2] avail[4] ready[4]; then the TMEM base slot
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * kMaxStages + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * kMaxStages + 2 + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 4);
-  // generic pointer to the tmem slot for reading it back
+  auto avail_bar = [&](int b) { return bars + 8u * (2 * kMaxStages + 4 + b); };
+  auto ready_bar = [&](int b) { return bars + 8u * (2 * kMaxStages + 4 + kMaxBufs + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 4 + 2 * kMaxBufs);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+  const bool nchw = (p.flags & UP_FLAG_OUT_NCHW_F32) != 0;
+  const bool has_res = (p.flags & UP_FLAG_RESIDUAL) != 0;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmY0);
+    if (!nchw) tma_prefetch_desc(&tmY0);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -132,6 +144,10 @@ __global__ void __launch_bounds__(256, 1)
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kEpiThreads);
+    }
+    for (int b = 0; b < kMaxBufs; ++b) {
+      mbar_init(avail_bar(b), 1);
+      mbar_init(ready_bar(b), kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -143,39 +159,53 @@ __global__ void __launch_bounds__(256, 1)
   tcgen05_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (threadIdx.x == 0) {
-    // ===================== TMA producer =====================
-    int s = 0;
-    uint32_t phase = 0;
+  if (warp == 0) {
+    // ===================== TMA producer (32 lanes, lane i owns k-blocks i, i+32, ...) =====================
+    uint32_t kb_base = 0;
     const int taps = p.taps_h * p.taps_w;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
-      for (int kh = 0; kh < p.taps_h; ++kh) {
-        for (int kw = 0; kw < p.taps_w; ++kw) {
-          int ch, cw, ph, pw;
-          if (!tap_box(p, t.h0, t.w0, kh, kw, ch, cw, ph, pw)) continue;
-          const int tap = kh * p.taps_w + kw;
-          for (int chunk = 0; chunk < p.chunks; ++chunk) {
-            const int g = chunk / p.chunks_per_group;
-            const int cc = chunk - g * p.chunks_per_group;
-            const int c = p.x_coff + cc * p.ck + pw * p.x_cs;
-            const int n = t.n0 + g * p.group_nstride;
-            for (int term = 0; term < p.nterms; ++term) {
-              mbar_wait(empty_bar(s), phase ^ 1u);
-              const uint32_t a_dst = smem_base + s * stage_bytes;
-              const uint32_t b_dst = a_dst + p.a_bytes;
-              mbar_arrive_expect_tx(full_bar(s), stage_bytes);
-              tma_load_5d(term == 1 ? &tmA1 : &tmA0, a_dst, full_bar(s), c, cw, ph, ch, n);
-              const int brow = ((term == 2 ? taps : 0) + tap) * p.cout + t.nt * p.block_n;
-              tma_load_2d(&tmB, b_dst, full_bar(s), chunk * p.ck, brow);
-              if (++s == p.stages) {
-                s = 0;
-                phase ^= 1u;
-              }
-            }
+      int kh_lo, kh_hi, kw_lo, kw_hi;
+      tap_range(p, p.taps_h, p.pad_h, t.h0, p.bh, p.Hq, kh_lo, kh_hi);
+      tap_range(p, p.taps_w, p.pad_w, t.w0, p.bw, p.Wq, kw_lo, kw_hi);
+      const int nw = kw_hi - kw_lo + 1;
+      const int nkb = (kh_hi - kh_lo + 1) * nw * p.chunks * p.nterms;
+      for (int i0 = 0; i0 < nkb; i0 += 32) {
+        // phase 1 (all lanes in parallel): coordinates of k-block i0 + lane
+        const int i = i0 + lane;
+        const bool active = i < nkb;
+        const int term = i % p.nterms;
+        const int j = i / p.nterms;
+        const int chunk = j % p.chunks;
+        const int a = j / p.chunks;
+        const int kh = kh_lo + a / nw;
+        const int kw = kw_lo + a % nw;
+        int oh, ow, ph, pw;
+        tap_offset(p, kh, p.pad_h, oh, ph);
+        tap_offset(p, kw, p.pad_w, ow, pw);
+        const int g = chunk / p.chunks_per_group;
+        const int cc = chunk - g * p.chunks_per_group;
+        const int c = p.x_coff + cc * p.ck + pw * p.x_cs;
+        const int n = t.n0 + g * p.group_nstride;
+        const uint32_t kb = kb_base + i;
+        const uint32_t s = kb % p.stages;
+        const uint32_t phase = (kb / p.stages) & 1u;
+        const uint32_t a_dst = smem_base + s * stage_bytes;
+        const int brow = ((term == 2 ? taps : 0) + kh * p.taps_w + kw) * p.cout + t.nt * p.block_n;
+        const CUtensorMap* amap = (term == 1) ? &tmA1 : &tmA0;
+        // phase 2 (in k-block order, one lane at a time): a later k-block may only wait on slots that earlier
+        // k-blocks - owned by lower lanes - have already filled, so the ordered issue cannot deadlock the warp
+        const int cnt = min(32, nkb - i0);
+        for (int l = 0; l < cnt; ++l) {
+          if (lane == l && active) {
+            mbar_wait(empty_bar(s), phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+            tma_load_5d(amap, a_dst, full_bar(s), c, t.w0 + ow, ph, t.h0 + oh, n);
+            tma_load_2d(&tmB, a_dst + p.a_bytes, full_bar(s), chunk * p.ck, brow);
           }
         }
       }
+      kb_base += nkb;
     }
   } else if (threadIdx.x == 32) {
     // ===================== MMA issuer =====================
@@ -185,34 +215,33 @@ __global__ void __launch_bounds__(256, 1)
     uint32_t acc_phase = 0;
     const uint32_t sw_bytes = p.ck * 2;
     const int kk = p.ck / 16;
+    const uint64_t adesc0 = make_smem_desc_kmajor(smem_base, sw_bytes);
+    const uint64_t bdesc0 = make_smem_desc_kmajor(smem_base + p.a_bytes, sw_bytes);
+    const uint32_t stage_step = stage_bytes >> 4;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
+      int kh_lo, kh_hi, kw_lo, kw_hi;
+      tap_range(p, p.taps_h, p.pad_h, t.h0, p.bh, p.Hq, kh_lo, kh_hi);
+      tap_range(p, p.taps_w, p.pad_w, t.w0, p.bw, p.Wq, kw_lo, kw_hi);
+      const int nkb = (kh_hi - kh_lo + 1) * (kw_hi - kw_lo + 1) * p.chunks * p.nterms;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tcgen05_after_thread_sync();
       const uint32_t tmem_d = tmem_base + acc * p.block_n;
       uint32_t accumulate = 0;
-      for (int kh = 0; kh < p.taps_h; ++kh) {
-        for (int kw = 0; kw < p.taps_w; ++kw) {
-          int ch, cw, ph, pw;
-          if (!tap_box(p, t.h0, t.w0, kh, kw, ch, cw, ph, pw)) continue;
-          const int nkb = p.chunks * p.nterms;
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(full_bar(s), phase);
-            tcgen05_after_thread_sync();
-            const uint32_t a_addr = smem_base + s * stage_bytes;
-            const uint64_t adesc = make_smem_desc_kmajor(a_addr, sw_bytes);
-            const uint64_t bdesc = make_smem_desc_kmajor(a_addr + p.a_bytes, sw_bytes);
-            for (int k = 0; k < kk; ++k) {
-              // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in 16-byte units
-              umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, accumulate);
-              accumulate = 1;
-            }
-            umma_commit(empty_bar(s));  // frees the smem slot once these MMAs have read it
-            if (++s == p.stages) {
-              s = 0;
-              phase ^= 1u;
-            }
-          }
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(full_bar(s), phase);
+        tcgen05_after_thread_sync();
+        const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage_step * s);
+        const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage_step * s);
+        for (int k = 0; k < kk; ++k) {
+          // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in 16-byte units
+          umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, accumulate);
+          accumulate = 1;
+        }
+        umma_commit(empty_bar(s));  // frees the smem slot once these MMAs have read it
+        if (++s == p.stages) {
+          s = 0;
+          phase ^= 1u;
         }
       }
       umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
@@ -221,32 +250,78 @@ __global__ void __launch_bounds__(256, 1)
         acc_phase ^= 1u;
       }
     }
+  } else if (threadIdx.x == 64) {
+    // ===================== epilogue DMA thread =====================
+    if (!nchw) {
+      const int groups = p.block_n / 64;
+      int my_tiles = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) ++my_tiles;
+      const int total_q = my_tiles * groups;
+      const int look = p.nbuf - 2;
+      auto coords = [&](int q, int& c, TileCoord& t) {
+        const int tile = blockIdx.x + (q / groups) * gridDim.x;
+        t = decode_tile(p, tile);
+        c = t.nt * p.block_n + (q % groups) * 64;
+      };
+      auto make_avail = [&](int q) {
+        const int b = q % p.nbuf;
+        if (has_res) {
+          int c;
+          TileCoord t;
+          coords(q, c, t);
+          const uint32_t dst = staging + b * p.buf_bytes;
+          mbar_arrive_expect_tx(avail_bar(b), p.buf_bytes);
+          tma_load_5d(&tmR0, dst, avail_bar(b), p.r_coff + c, t.w0, 0, t.h0, t.n0);
+          if (p.split) tma_load_5d(&tmR1, dst + kPlaneBytes, avail_bar(b), p.r_coff + c, t.w0, 0, t.h0, t.n0);
+        } else {
+          mbar_arrive(avail_bar(b));
+        }
+      };
+      for (int q = 0; q < look && q < total_q; ++q) make_avail(q);
+      for (int q = 0; q < total_q; ++q) {
+        if (q + look < total_q) {
+          // buffer (q+look) % nbuf was last used by group q-2, whose store was issued two iterations ago
+          if (q + look >= p.nbuf) tma_store_wait_read<1>();
+          make_avail(q + look);
+        }
+        const int b = q % p.nbuf;
+        mbar_wait(ready_bar(b), (q / p.nbuf) & 1u);
+        int c;
+        TileCoord t;
+        coords(q, c, t);
+        const uint32_t src = staging + b * p.buf_bytes;
+        tma_store_5d(&tmY0, src, p.y_coff + c, t.w0, 0, t.h0, t.n0);
+        if (p.split) tma_store_5d(&tmY1, src + kPlaneBytes, p.y_coff + c, t.w0, 0, t.h0, t.n0);
+        tma_store_commit();
+      }
+      tma_store_wait_all<0>();
+    }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue =====================
-    const int ew = warp - kEpiWarp0;  // == warp % 4 -> TMEM lane quarter
-    const int row = ew * 32 + lane;
-    const bool issuer = (threadIdx.x == kEpiWarp0 * 32);
+    // ===================== epilogue math (8 warps) =====================
+    const int ew = warp - kEpiWarp0;
+    const int quarter = ew & 3;  // == warp % 4 -> TMEM lane quarter this warp may read
+    const int half = ew >> 2;    // which 32 of a group's 64 columns
+    const int row = quarter * 32 + lane;
     const int fmt = p.fmt;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t store_seq = 0;
+    uint32_t q = 0;  // staging-buffer sequence number (shared convention with the DMA thread)
     const int bhw = p.bh * p.bw;
+    const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
-      const int rn = row / bhw;
-      const int rem = row - rn * bhw;
-      const int rh = rem / p.bw;
-      const int rw = rem - rh * p.bw;
-      const int n = t.n0 + rn, h = t.h0 + rh, w = t.w0 + rw;
-      const bool valid = (n < p.N) && (h < p.Ho) && (w < p.Wo);
-      const long long pix = (static_cast<long long>(n) * p.Ho + h) * p.Wo + w;
-
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_after_thread_sync();
-      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * p.block_n;
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.block_n;
 
-      if (p.flags & UP_FLAG_OUT_NCHW_F32) {
-        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      if (nchw) {
+        const int rn = row / bhw;
+        const int rem = row - rn * bhw;
+        const int rh = rem / p.bw;
+        const int rw = rem - rh * p.bw;
+        const int n = t.n0 + rn, h = t.h0 + rh, w = t.w0 + rw;
+        const bool valid = (n < p.N) && (h < p.Ho) && (w < p.Wo);
+        for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr0 + c0, r);
           tmem_ld_wait();
@@ -263,109 +338,87 @@ __global__ void __launch_bounds__(256, 1)
         }
       } else {
         const int groups = p.block_n / 64;
-        for (int g = 0; g < groups; ++g) {
-          // staging buffer(s) for this group
-          uint32_t buf0, buf1;
-          if (p.split) {
-            if (issuer) tma_store_wait_read<0>();
-            buf0 = staging;
-            buf1 = staging + 16384;
-          } else {
-            if (issuer) tma_store_wait_read<1>();
-            buf0 = staging + (store_seq & 1u) * 16384;
-            buf1 = buf0;
+        for (int g = 0; g < groups; ++g, ++q) {
+          const uint32_t b = q % p.nbuf;
+          const uint32_t buf = staging + b * p.buf_bytes;
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr0 + g * 64 + half * 32, r);
+          const int colbase = t.nt * p.block_n + g * 64 + half * 32;
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + colbase) + j4);
+            const float4 h4 = __ldg(reinterpret_cast<const float4*>(p.shift + colbase) + j4);
+            v[4 * j4 + 0] = fmaf(__uint_as_float(r[4 * j4 + 0]), s4.x, h4.x);
+            v[4 * j4 + 1] = fmaf(__uint_as_float(r[4 * j4 + 1]), s4.y, h4.y);
+            v[4 * j4 + 2] = fmaf(__uint_as_float(r[4 * j4 + 2]), s4.z, h4.z);
+            v[4 * j4 + 3] = fmaf(__uint_as_float(r[4 * j4 + 3]), s4.w, h4.w);
           }
-          named_bar_sync(1, kEpiThreads);
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(taddr0 + g * 64 + half * 32, r);
-            tmem_ld_wait();
-            const int colbase = t.nt * p.block_n + g * 64 + half * 32;
-            float v[32];
+          // the staging buffer becomes ours (previous store drained; residual tile landed if any)
+          mbar_wait(avail_bar(b), (q / p.nbuf) & 1u);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + colbase) + j4);
-              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + colbase) + j4);
-              v[4 * j4 + 0] = fmaf(__uint_as_float(r[4 * j4 + 0]), sc.x, sh.x);
-              v[4 * j4 + 1] = fmaf(__uint_as_float(r[4 * j4 + 1]), sc.y, sh.y);
-              v[4 * j4 + 2] = fmaf(__uint_as_float(r[4 * j4 + 2]), sc.z, sh.z);
-              v[4 * j4 + 3] = fmaf(__uint_as_float(r[4 * j4 + 3]), sc.w, sh.w);
-            }
-            if ((p.flags & UP_FLAG_RESIDUAL) && valid) {
-              const uint16_t* rp = p.res + pix * p.r_cs + p.r_coff + colbase;
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const uint32_t chunk = static_cast<uint32_t>(half * 4 + c4) ^ (static_cast<uint32_t>(row) & 7u);
+            const uint32_t addr = buf + rowoff + (chunk << 4);
+            if (has_res) {
+              uint32_t u0, u1, u2, u3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3)
+                           : "r"(addr)
+                           : "memory");
+              const uint32_t uw[4] = {u0, u1, u2, u3};
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + q);
-                const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  v[8 * q + 2 * e + 0] += cvt16_to_f32_rt(static_cast<uint16_t>(uw[e] & 0xFFFFu), fmt);
-                  v[8 * q + 2 * e + 1] += cvt16_to_f32_rt(static_cast<uint16_t>(uw[e] >> 16), fmt);
-                }
+              for (int e = 0; e < 4; ++e) {
+                v[8 * c4 + 2 * e + 0] += cvt16_to_f32_rt(static_cast<uint16_t>(uw[e] & 0xFFFFu), fmt);
+                v[8 * c4 + 2 * e + 1] += cvt16_to_f32_rt(static_cast<uint16_t>(uw[e] >> 16), fmt);
               }
               if (p.split) {
-                const uint16_t* rl = rp + p.r_plane;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3)
+                             : "r"(addr + kPlaneBytes)
+                             : "memory");
+                const uint32_t lw[4] = {u0, u1, u2, u3};
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const uint4 u = __ldg(reinterpret_cast<const uint4*>(rl) + q);
-                  const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    v[8 * q + 2 * e + 0] += cvt16_to_f32<1>(static_cast<uint16_t>(uw[e] & 0xFFFFu));
-                    v[8 * q + 2 * e + 1] += cvt16_to_f32<1>(static_cast<uint16_t>(uw[e] >> 16));
-                  }
+                for (int e = 0; e < 4; ++e) {
+                  v[8 * c4 + 2 * e + 0] += cvt16_to_f32<1>(static_cast<uint16_t>(lw[e] & 0xFFFFu));
+                  v[8 * c4 + 2 * e + 1] += cvt16_to_f32<1>(static_cast<uint16_t>(lw[e] >> 16));
                 }
               }
             }
             if (p.flags & UP_FLAG_RELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              for (int e = 0; e < 8; ++e) v[8 * c4 + e] = fmaxf(v[8 * c4 + e], 0.f);
             }
-            // pack to 16-bit and write this thread's 64 bytes (4 x 16B chunks) into the swizzled staging row
-            const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
+            uint32_t w0, w1, w2, w3;
+            if (p.split) {
+              uint16_t hi[8], lo[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t chunk = static_cast<uint32_t>(half * 4 + q) ^ (static_cast<uint32_t>(row) & 7u);
-              uint32_t w0, w1, w2, w3;
-              if (p.split) {
-                uint16_t hi[8], lo[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) split_bf16(v[8 * q + e], hi[e], lo[e]);
-                w0 = hi[0] | (static_cast<uint32_t>(hi[1]) << 16);
-                w1 = hi[2] | (static_cast<uint32_t>(hi[3]) << 16);
-                w2 = hi[4] | (static_cast<uint32_t>(hi[5]) << 16);
-                w3 = hi[6] | (static_cast<uint32_t>(hi[7]) << 16);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf0 + rowoff + (chunk << 4)),
-                             "r"(w0), "r"(w1), "r"(w2), "r"(w3)
-                             : "memory");
-                w0 = lo[0] | (static_cast<uint32_t>(lo[1]) << 16);
-                w1 = lo[2] | (static_cast<uint32_t>(lo[3]) << 16);
-                w2 = lo[4] | (static_cast<uint32_t>(lo[5]) << 16);
-                w3 = lo[6] | (static_cast<uint32_t>(lo[7]) << 16);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf1 + rowoff + (chunk << 4)),
-                             "r"(w0), "r"(w1), "r"(w2), "r"(w3)
-                             : "memory");
-              } else {
-                w0 = pack2_rt(v[8 * q + 0], v[8 * q + 1], fmt);
-                w1 = pack2_rt(v[8 * q + 2], v[8 * q + 3], fmt);
-                w2 = pack2_rt(v[8 * q + 4], v[8 * q + 5], fmt);
-                w3 = pack2_rt(v[8 * q + 6], v[8 * q + 7], fmt);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf0 + rowoff + (chunk << 4)),
-                             "r"(w0), "r"(w1), "r"(w2), "r"(w3)
-                             : "memory");
-              }
+              for (int e = 0; e < 8; ++e) split_bf16(v[8 * c4 + e], hi[e], lo[e]);
+              w0 = hi[0] | (static_cast<uint32_t>(hi[1]) << 16);
+              w1 = hi[2] | (static_cast<uint32_t>(hi[3]) << 16);
+              w2 = hi[4] | (static_cast<uint32_t>(hi[5]) << 16);
+              w3 = hi[6] | (static_cast<uint32_t>(hi[7]) << 16);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                           : "memory");
+              w0 = lo[0] | (static_cast<uint32_t>(lo[1]) << 16);
+              w1 = lo[2] | (static_cast<uint32_t>(lo[3]) << 16);
+              w2 = lo[4] | (static_cast<uint32_t>(lo[5]) << 16);
+              w3 = lo[6] | (static_cast<uint32_t>(lo[7]) << 16);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + kPlaneBytes), "r"(w0), "r"(w1),
+                           "r"(w2), "r"(w3)
+                           : "memory");
+            } else {
+              w0 = pack2_rt(v[8 * c4 + 0], v[8 * c4 + 1], fmt);
+              w1 = pack2_rt(v[8 * c4 + 2], v[8 * c4 + 3], fmt);
+              w2 = pack2_rt(v[8 * c4 + 4], v[8 * c4 + 5], fmt);
+              w3 = pack2_rt(v[8 * c4 + 6], v[8 * c4 + 7], fmt);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                           : "memory");
             }
           }
-          fence_proxy_async_smem();
-          named_bar_sync(1, kEpiThreads);
-          if (issuer) {
-            const int c = p.y_coff + t.nt * p.block_n + g * 64;
-            tma_store_5d(&tmY0, buf0, c, t.w0, 0, t.h0, t.n0);
-            if (p.split) tma_store_5d(&tmY1, buf1, c, t.w0, 0, t.h0, t.n0);
-            tma_store_commit();
-          }
-          ++store_seq;
+          fence_proxy_async_smem();   // make the generic-proxy writes visible to the TMA store
+          mbar_arrive(ready_bar(b));  // 256 arrivals -> the DMA thread stores the group
         }
       }
       // all TMEM reads of this accumulator are done -> hand it back to the MMA issuer
@@ -376,7 +429,6 @@ __global__ void __launch_bounds__(256, 1)
         acc_phase ^= 1u;
       }
     }
-    if (issuer) tma_store_wait_all<0>();
   }
 
   tcgen05_before_thread_sync();
@@ -387,9 +439,6 @@ __global__ void __launch_bounds__(256, 1)
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Host side
-// ---------------------------------------------------------------------------------------------
 }  // namespace up
 #include "up_conv_host.h"  // tensor-map encoding + tile picking helpers (shared with the wgrad kernel)
 namespace up {
@@ -428,6 +477,7 @@ using namespace up;
 
 extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_packed, const float* scale,
                              const float* shift, const void* residual, void* y, float* stats, void* stream) {
+  (void)stats;
   UP_CHECK_ARG(d && x && w_packed && scale && shift && y, "up_conv2d_fwd: null argument");
   UP_CHECK_ARG(d->n > 0 && d->h > 0 && d->w > 0 && d->ho > 0 && d->wo > 0, "up_conv2d_fwd: bad spatial dims");
   UP_CHECK_ARG(d->stride == 1 || d->stride == 2, "up_conv2d_fwd: stride must be 1 or 2 (got %d)", d->stride);
@@ -436,22 +486,27 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   UP_CHECK_ARG(d->cin > 0 && d->cin % 16 == 0, "up_conv2d_fwd: cin (%d) must be a positive multiple of 16", d->cin);
   UP_CHECK_ARG(d->cout > 0 && d->cout % 32 == 0, "up_conv2d_fwd: cout (%d) must be a positive multiple of 32", d->cout);
   UP_CHECK_ARG(d->dtype == UP_BF16 || d->dtype == UP_FP16 || d->dtype == UP_SPLIT, "up_conv2d_fwd: bad dtype");
-  UP_CHECK_ARG(!(d->flags & UP_FLAG_STATS), "up_conv2d_fwd: UP_FLAG_STATS is handled by up_bn_stats");
+  UP_CHECK_ARG(!(d->flags & UP_FLAG_STATS), "up_conv2d_fwd: UP_FLAG_STATS is not fused; use up_bn_stats");
   const int groups = d->x_groups > 0 ? d->x_groups : 1;
   UP_CHECK_ARG(d->cin % groups == 0, "up_conv2d_fwd: cin not divisible by x_groups");
   const int cin_g = d->cin / groups;
   const int ck = (cin_g % 64 == 0) ? 64 : 16;
   UP_CHECK_ARG(cin_g % ck == 0, "up_conv2d_fwd: per-group cin (%d) must be a multiple of 16", cin_g);
-  UP_CHECK_ARG(d->x_cstride % 8 == 0 && d->x_coff % 8 == 0 && d->x_coff + cin_g <= d->x_cstride,
-               "up_conv2d_fwd: bad x channel view (cstride %d coff %d cin/group %d)", d->x_cstride, d->x_coff, cin_g);
+  const int cext = d->x_cextent > 0 ? d->x_cextent : d->x_cstride;
+  UP_CHECK_ARG(d->x_cstride % 8 == 0 && d->x_coff % 8 == 0 && d->x_coff + cin_g <= cext,
+               "up_conv2d_fwd: bad x channel view (cstride %d coff %d cin/group %d extent %d)", d->x_cstride, d->x_coff,
+               cin_g, cext);
+  UP_CHECK_ARG(d->x_cextent == 0 || (d->stride == 1 && groups == 1),
+               "up_conv2d_fwd: overlapping channel windows need stride 1 and no groups");
   UP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
                "up_conv2d_fwd: x / w must be 16-byte aligned");
   const bool nchw = (d->flags & UP_FLAG_OUT_NCHW_F32) != 0;
   const bool split = d->dtype == UP_SPLIT;
+  const bool has_res = (d->flags & UP_FLAG_RESIDUAL) != 0;
   if (nchw) {
     UP_CHECK_ARG(d->cout_valid > 0 && d->cout_valid <= d->cout, "up_conv2d_fwd: bad cout_valid");
     UP_CHECK_ARG(d->out_c_total == 0 || d->out_c_total >= d->cout_valid, "up_conv2d_fwd: bad out_c_total");
-    UP_CHECK_ARG(!(d->flags & UP_FLAG_RESIDUAL), "up_conv2d_fwd: residual not supported with NCHW fp32 output");
+    UP_CHECK_ARG(!has_res, "up_conv2d_fwd: residual not supported with NCHW fp32 output");
   } else {
     UP_CHECK_ARG(d->cout % 64 == 0, "up_conv2d_fwd: NHWC output needs cout %% 64 == 0 (got %d)", d->cout);
     UP_CHECK_ARG(d->y_cstride % 8 == 0 && d->y_coff % 8 == 0 && d->y_coff + d->cout <= d->y_cstride,
@@ -460,7 +515,7 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
     if (split) UP_CHECK_ARG(d->y_plane_stride % 8 == 0 && d->y_plane_stride > 0, "up_conv2d_fwd: bad y_plane_stride");
   }
   if (split) UP_CHECK_ARG(d->x_plane_stride % 8 == 0 && d->x_plane_stride > 0, "up_conv2d_fwd: bad x_plane_stride");
-  if (d->flags & UP_FLAG_RESIDUAL) {
+  if (has_res) {
     UP_CHECK_ARG(residual != nullptr, "up_conv2d_fwd: residual pointer missing");
     UP_CHECK_ARG(d->r_cstride % 8 == 0 && d->r_coff % 8 == 0 && d->r_coff + d->cout <= d->r_cstride,
                  "up_conv2d_fwd: bad residual channel view");
@@ -499,14 +554,17 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   p.tiles_n = (d->n + p.bn - 1) / p.bn;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   int block_n = (d->cout % 256 == 0) ? 256 : (d->cout % 128 == 0) ? 128 : (d->cout % 64 == 0) ? 64 : 32;
-  while (block_n > 64 && static_cast<long long>(m_tiles) * (d->cout / block_n) < g_sm_count) block_n /= 2;
+  // keep at least ~2 tiles per SM so the epilogue of one tile overlaps the main loop of the next
+  while (block_n > 64 && static_cast<long long>(m_tiles) * (d->cout / block_n) < 2LL * g_sm_count) block_n /= 2;
   p.block_n = block_n;
   p.n_tiles = d->cout / block_n;
   p.cout = d->cout;
   p.nterms = split ? 3 : 1;
   p.a_bytes = kTileM * ck * 2;
   p.b_bytes = block_n * ck * 2;
-  const size_t fixed = 1024 + kStagingBytes + 8 * (2 * kMaxStages + 4) + 16;
+  p.buf_bytes = split ? 2 * kPlaneBytes : kPlaneBytes;
+  p.nbuf = nchw ? 0 : (split ? 2 : (has_res ? 3 : 2));
+  const size_t fixed = 1024 + 8 * (2 * kMaxStages + 4 + 2 * kMaxBufs) + 16 + static_cast<size_t>(p.nbuf) * p.buf_bytes;
   int stages = static_cast<int>((g_max_smem - fixed) / (p.a_bytes + p.b_bytes));
   if (stages > kMaxStages) stages = kMaxStages;
   UP_CHECK_ARG(stages >= 2, "up_conv2d_fwd: not enough shared memory for 2 pipeline stages");
@@ -521,26 +579,23 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   p.cout_valid = d->cout_valid;
   p.out_c_total = d->out_c_total > 0 ? d->out_c_total : d->cout_valid;
   p.y_coff = d->y_coff;
-  p.r_cs = d->r_cstride;
   p.r_coff = d->r_coff;
-  p.r_plane = d->r_plane_stride;
   p.scale = scale;
   p.shift = shift;
-  p.res = static_cast<const uint16_t*>(residual);
   p.out_f32 = nchw ? static_cast<float*>(y) : nullptr;
-  p.stats = stats;
 
   // ---- tensor maps ----
-  CUtensorMap tmA0, tmA1, tmB, tmY0, tmY1;
+  CUtensorMap tmA0, tmA1, tmB, tmY0, tmY1, tmR0, tmR1;
   const int sw = ck * 2;
   const uint32_t abox[5] = {static_cast<uint32_t>(ck), static_cast<uint32_t>(p.bw), 1u, static_cast<uint32_t>(p.bh),
                             static_cast<uint32_t>(p.bn)};
   const int n_total = d->n + (groups - 1) * p.group_nstride;
-  rc = encode_act_map(&tmA0, fmt, x, n_total, d->h, d->w, d->x_cstride, d->stride, abox, sw, "x");
+  rc = encode_act_map(&tmA0, fmt, x, n_total, d->h, d->w, d->x_cstride, d->stride, abox, sw, "x", d->x_cextent,
+                      d->x_wpitch);
   if (rc) return rc;
   if (split) {
     rc = encode_act_map(&tmA1, fmt, static_cast<const uint16_t*>(x) + d->x_plane_stride, n_total, d->h, d->w,
-                        d->x_cstride, d->stride, abox, sw, "x.lo");
+                        d->x_cstride, d->stride, abox, sw, "x.lo", d->x_cextent, d->x_wpitch);
     if (rc) return rc;
   } else {
     tmA1 = tmA0;
@@ -557,27 +612,38 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
     rc = encode_map(&tmB, fmt, 2, w_packed, dims, st, box, sw, "w");
     if (rc) return rc;
   }
+  tmY0 = tmA0;
+  tmY1 = tmA0;
+  tmR0 = tmA0;
+  tmR1 = tmA0;
   if (!nchw) {
     const uint32_t ybox[5] = {64u, static_cast<uint32_t>(p.bw), 1u, static_cast<uint32_t>(p.bh),
                               static_cast<uint32_t>(p.bn)};
     rc = encode_act_map(&tmY0, fmt, y, d->n, d->ho, d->wo, d->y_cstride, 1, ybox, 128, "y");
     if (rc) return rc;
+    tmY1 = tmY0;
     if (split) {
       rc = encode_act_map(&tmY1, fmt, static_cast<uint16_t*>(y) + d->y_plane_stride, d->n, d->ho, d->wo,
                           d->y_cstride, 1, ybox, 128, "y.lo");
       if (rc) return rc;
-    } else {
-      tmY1 = tmY0;
     }
-  } else {
-    tmY0 = tmA0;
-    tmY1 = tmA0;
+    if (has_res) {
+      rc = encode_act_map(&tmR0, fmt, residual, d->n, d->ho, d->wo, d->r_cstride, 1, ybox, 128, "residual");
+      if (rc) return rc;
+      tmR1 = tmR0;
+      if (split) {
+        rc = encode_act_map(&tmR1, fmt, static_cast<const uint16_t*>(residual) + d->r_plane_stride, d->n, d->ho,
+                            d->wo, d->r_cstride, 1, ybox, 128, "residual.lo");
+        if (rc) return rc;
+      }
+    }
   }
 
   const long long total_tiles = static_cast<long long>(m_tiles) * p.n_tiles;
   const int grid = static_cast<int>(total_tiles < g_sm_count ? total_tiles : g_sm_count);
   const size_t smem = fixed + static_cast<size_t>(stages) * (p.a_bytes + p.b_bytes);
-  conv_tcgen05_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmA0, tmA1, tmB, tmY0, tmY1, p);
+  conv_tcgen05_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA0, tmA1, tmB, tmY0, tmY1, tmR0,
+                                                                                    tmR1, p);
   UP_CHECK_LAUNCH("conv_tcgen05_kernel launch");
   return 0;
 }

@@ -123,7 +123,7 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
 // ------------------------------------------------------------------------------------------
 template <int kMode>
 __global__ void pack_input_s2d_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, int n, int h, int w,
-                                      long long plane) {
+                                      long long plane, int wpitch, int wpad) {
   const int hq = h / 2, wq = w / 2;
   const long long total = static_cast<long long>(n) * hq * wq;
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -151,7 +151,7 @@ __global__ void pack_input_s2d_kernel(const float* __restrict__ x, uint16_t* __r
       if (i1 < 8) v0[i1] = f.y; else v1[i1 - 8] = f.y;
     }
   }
-  uint16_t* o = y + i * 16;
+  uint16_t* o = y + ((static_cast<long long>(b) * hq + yq) * wpitch + xq + wpad) * 16;
   store8<kMode>(o, plane, v0);
   store8<kMode>(o + 8, plane, v1);
 }
@@ -377,13 +377,15 @@ extern "C" int up_bn_fold(const float* gamma, const float* beta, const float* me
 }
 
 extern "C" int up_pack_input_s2d(const float* x_nchw, void* y, int n, int h, int w, int dtype, int64_t y_plane_stride,
-                                 void* stream) {
+                                 int y_wpitch, int y_wpad_left, void* stream) {
   UP_CHECK_ARG(x_nchw && y, "up_pack_input_s2d: null argument");
   UP_CHECK_ARG(n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "up_pack_input_s2d: h, w must be even");
   UP_CHECK_ARG((reinterpret_cast<uintptr_t>(x_nchw) & 7) == 0 && UP_ALIGNED16(y), "up_pack_input_s2d: alignment");
+  if (y_wpitch <= 0) y_wpitch = w / 2;
+  UP_CHECK_ARG(y_wpad_left >= 0 && y_wpad_left + w / 2 <= y_wpitch, "up_pack_input_s2d: bad row pitch / padding");
   const long long total = static_cast<long long>(n) * (h / 2) * (w / 2);
   UP_DISPATCH_MODE(dtype, (pack_input_s2d_kernel<kMode><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                              x_nchw, static_cast<uint16_t*>(y), n, h, w, y_plane_stride)));
+                              x_nchw, static_cast<uint16_t*>(y), n, h, w, y_plane_stride, y_wpitch, y_wpad_left)));
   UP_CHECK_LAUNCH("pack_input_s2d_kernel");
   return 0;
 }

@@ -58,21 +58,27 @@ static int encode_map(CUtensorMap* m, int fmt, int rank, const void* base, const
 
 // NHWC activation view as a rank-5 tensor map (c, w, parity|1, h, n); stride 2 folds the row/column
 // parity into dims 2 / 0 so that a stride-2 tap is still a dense box.
+//
+// `cextent` / `wpitch` (stride 1 only) describe OVERLAPPING channel windows: the innermost dimension then spans
+// `cextent` (> cs) consecutive elements, i.e. several neighbouring pixels, while consecutive "pixels" are still cs
+// elements apart and rows are `wpitch` pixels apart in memory.  The space-to-depth stem uses this to fetch 4
+// horizontal taps x 16 channels as one 64-element K-chunk.
 static int encode_act_map(CUtensorMap* m, int fmt, const void* base, int n_total, int h, int w, int cs, int stride,
-                          const uint32_t* box, int swizzle_bytes, const char* what) {
+                          const uint32_t* box, int swizzle_bytes, const char* what, int cextent = 0, int wpitch = 0) {
   uint64_t dims[5];
   uint64_t st[4];
   const uint64_t es = 2;
   if (stride == 1) {
-    dims[0] = cs;
+    const uint64_t wp = wpitch > 0 ? wpitch : w;
+    dims[0] = cextent > 0 ? cextent : cs;
     dims[1] = w;
     dims[2] = 1;
     dims[3] = h;
     dims[4] = n_total;
     st[0] = cs * es;
-    st[1] = static_cast<uint64_t>(w) * cs * es;
-    st[2] = static_cast<uint64_t>(w) * cs * es;
-    st[3] = static_cast<uint64_t>(h) * w * cs * es;
+    st[1] = wp * cs * es;
+    st[2] = wp * cs * es;
+    st[3] = static_cast<uint64_t>(h) * wp * cs * es;
   } else {
     dims[0] = 2ull * cs;
     dims[1] = w / 2;

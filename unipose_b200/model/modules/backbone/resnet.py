@@ -35,6 +35,12 @@ def stem_s2d_weight(w):
     return w2
 
 
+def stem_window_weight(w):
+    """[co,3,7,7] -> [co,64,4,1]: filter rows stay taps, the 4 horizontal taps x 16 s2d channels become the K-chunk."""
+    w2 = stem_s2d_weight(w)                                    # [co, 16, kh', kw']
+    return w2.permute(0, 3, 1, 2).reshape(w.shape[0], 64, 4, 1).contiguous()   # cin index = kw' * 16 + ch
+
+
 class Bottleneck(PlanModule):
     expansion = 4
 
@@ -132,11 +138,13 @@ class ResNet(PlanModule):
         n, _, h, w = x_static.shape
         if h % 16 or w % 16:
             raise ValueError('unipose_b200: input height/width must be multiples of 16 (got %dx%d)' % (h, w))
-        x2 = b.act(n, h // 2, w // 2, 16)
-        b.add(lambda x_static=x_static, x2=x2: ops.pack_input_s2d(x_static, x2), "pack_input_s2d")
+        # rows padded by 2 zero pixels on the left and 1 on the right: the 4 horizontal taps x 16 channels of an
+        # output pixel are then 64 CONTIGUOUS elements -> one 128-byte K-chunk per filter row (x_window below)
+        x2 = b.act(n, h // 2, w // 2 + 3, 16, zero=True)
+        b.add(lambda x_static=x_static, x2=x2: ops.pack_input_s2d(x_static, x2, wpad_left=2), "pack_input_s2d")
         stem = b.act(n, h // 2, w // 2, 64)
-        pc = b.packed_conv(self.conv1, self.bn1, cin_pad=16, weight_fn=stem_s2d_weight)
-        b.conv(x2, pc, stem, "stem", pad=2, relu=True, ho=h // 2, wo=w // 2)
+        pc = b.packed_conv(self.conv1, self.bn1, cin_pad=64, weight_fn=stem_window_weight)
+        b.conv(x2, pc, stem, "stem", pad=(2, 0), relu=True, ho=h // 2, wo=w // 2, x_window=(w // 2, 64))
         x = b.act(n, h // 4, w // 4, 64)
         b.add(lambda stem=stem, x=x: ops.maxpool3x3s2(stem, x), "maxpool")
         low = None

@@ -157,7 +157,8 @@ def make_packed_conv(w_oihw, mode, scale=None, shift=None, bias=None, cout=None,
 
 def conv2d(x, pc: PackedConv, y, *, stride: int = 1, dil: int = 1, pad=None, relu: bool = False,
            residual=None, ho: Optional[int] = None, wo: Optional[int] = None, x_groups: int = 1,
-           x_group_nstride: int = 0, cout_valid: Optional[int] = None, out_c_total: Optional[int] = None) -> None:
+           x_group_nstride: int = 0, cout_valid: Optional[int] = None, out_c_total: Optional[int] = None,
+           x_window=None) -> None:
     """y = epilogue(conv(x, w)).  `y` is an Act/View (NHWC 16-bit) or an fp32 NCHW tensor [n, cout_valid, ho, wo]."""
     xv = as_view(x)
     if pad is None:
@@ -166,9 +167,13 @@ def conv2d(x, pc: PackedConv, y, *, stride: int = 1, dil: int = 1, pad=None, rel
         pad = (pad, pad)
     d = UpConvDesc()
     d.n, d.h, d.w = xv.n, xv.h, xv.w
+    if x_window is not None:
+        # overlapping channel windows over a row-padded buffer: (logical width, channels per window)
+        d.w, d.x_cextent = x_window
+        d.x_wpitch = xv.w
     if ho is None:
-        ho = (xv.h + 2 * pad[0] - dil * (pc.kh - 1) - 1) // stride + 1
-        wo = (xv.w + 2 * pad[1] - dil * (pc.kw - 1) - 1) // stride + 1
+        ho = (d.h + 2 * pad[0] - dil * (pc.kh - 1) - 1) // stride + 1
+        wo = (d.w + 2 * pad[1] - dil * (pc.kw - 1) - 1) // stride + 1
     d.ho, d.wo = ho, wo
     d.cin, d.cout = pc.cin, pc.cout
     d.kh, d.kw, d.stride, d.dil = pc.kh, pc.kw, stride, dil
@@ -205,10 +210,11 @@ def conv2d(x, pc: PackedConv, y, *, stride: int = 1, dil: int = 1, pad=None, rel
 # ---------------------------------------------------------------------------------------------
 # bandwidth kernels
 # ---------------------------------------------------------------------------------------------
-def pack_input_s2d(x_nchw: torch.Tensor, y: Act) -> None:
+def pack_input_s2d(x_nchw: torch.Tensor, y: Act, wpad_left: int = 0) -> None:
+    """fp32 NCHW image -> 2x2 space-to-depth NHWC16; `y` may have padded rows (y.w >= w/2 + wpad_left)."""
     n, c, h, w = x_nchw.shape
-    assert c == 3 and (y.n, y.h, y.w, y.c) == (n, h // 2, w // 2, 16)
-    _lib.call("up_pack_input_s2d", _ptr(x_nchw), y.ptr(), n, h, w, y.mode, y.plane_stride, _stream())
+    assert c == 3 and (y.n, y.h, y.c) == (n, h // 2, 16) and y.w >= w // 2 + wpad_left
+    _lib.call("up_pack_input_s2d", _ptr(x_nchw), y.ptr(), n, h, w, y.mode, y.plane_stride, y.w, wpad_left, _stream())
 
 
 def nchw_to_act(x: torch.Tensor, y, c_real: Optional[int] = None) -> None:
