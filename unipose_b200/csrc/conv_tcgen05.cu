@@ -8,8 +8,9 @@
 //             K = taps x input channels (k-block = one tap x `ck` channels, ck in {16,64}).
 //
 // Persistent, warp-specialised CTA (384 threads, 1 CTA / SM):
-//   warp 0 (32 lanes) : TMA producer - every lane owns every 32nd k-block, so the scalar address arithmetic of
-//                       32 k-blocks runs in parallel (a single producer thread was the bottleneck of small-K layers)
+//   warp 0 (32 lanes) : TMA producer - the lanes compute the coordinates of 32 consecutive k-blocks in parallel (the
+//                       scalar address arithmetic of a single producer thread was the bottleneck of small-K layers);
+//                       lane 0 then issues them in order (mbarrier wait, expect_tx, two TMA loads per k-block)
 //   warp 1 lane 0     : tcgen05.mma issuer   (smem ring: full/empty mbarriers; TMEM double buffer: tfull/tempty)
 //   warp 2            : TMEM alloc/dealloc; lane 0 = epilogue DMA thread: TMA-prefetches the residual tile of each
 //                       64-channel group into a staging buffer and TMA-stores the finished group (avail/ready mbarriers)
@@ -23,6 +24,7 @@
 // UP_SPLIT ("fp32-grade") mode: activations and weights are bf16 hi+lo planes; every k-block is issued three times
 // (hi*hi, lo*hi, hi*lo) into the same fp32 accumulator.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "up_internal.h"
 #include "up_ptx.cuh"
@@ -193,17 +195,32 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t a_dst = smem_base + s * stage_bytes;
         const int brow = ((term == 2 ? taps : 0) + kh * p.taps_w + kw) * p.cout + t.nt * p.block_n;
         const CUtensorMap* amap = (term == 1) ? &tmA1 : &tmA0;
-        // phase 2 (in k-block order, one lane at a time): a later k-block may only wait on slots that earlier
-        // k-blocks - owned by lower lanes - have already filled, so the ordered issue cannot deadlock the warp
+        // phase 2: lane 0 issues the k-blocks strictly in order (the slot / phase protocol of the smem ring
+        // assumes in-order production), fetching each k-block's coordinates from the lane that computed them
         const int cnt = min(32, nkb - i0);
+        const int sel = (term == 1) ? 1 : 0;
         for (int l = 0; l < cnt; ++l) {
-          if (lane == l && active) {
-            mbar_wait(empty_bar(s), phase ^ 1u);
-            mbar_arrive_expect_tx(full_bar(s), stage_bytes);
-            tma_load_5d(amap, a_dst, full_bar(s), c, t.w0 + ow, ph, t.h0 + oh, n);
-            tma_load_2d(&tmB, a_dst + p.a_bytes, full_bar(s), chunk * p.ck, brow);
+          const int c_l = __shfl_sync(0xffffffffu, c, l);
+          const int w_l = __shfl_sync(0xffffffffu, t.w0 + ow, l);
+          const int ph_l = __shfl_sync(0xffffffffu, ph, l);
+          const int h_l = __shfl_sync(0xffffffffu, t.h0 + oh, l);
+          const int n_l = __shfl_sync(0xffffffffu, n, l);
+          const uint32_t s_l = __shfl_sync(0xffffffffu, s, l);
+          const uint32_t par_l = __shfl_sync(0xffffffffu, phase ^ 1u, l);
+          const int brow_l = __shfl_sync(0xffffffffu, brow, l);
+          const int bcol_l = __shfl_sync(0xffffffffu, chunk * p.ck, l);
+          const int sel_l = __shfl_sync(0xffffffffu, sel, l);
+          if (lane == 0) {
+            const uint32_t dst = smem_base + s_l * stage_bytes;
+            mbar_wait(empty_bar(s_l), par_l, 16000000000LL);
+            mbar_arrive_expect_tx(full_bar(s_l), stage_bytes);
+            tma_load_5d(sel_l ? &tmA1 : &tmA0, dst, full_bar(s_l), c_l, w_l, ph_l, h_l, n_l);
+            tma_load_2d(&tmB, dst + p.a_bytes, full_bar(s_l), bcol_l, brow_l);
           }
         }
+        (void)active;
+        (void)a_dst;
+        (void)amap;
       }
       kb_base += nkb;
     }
@@ -555,7 +572,11 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   int block_n = (d->cout % 256 == 0) ? 256 : (d->cout % 128 == 0) ? 128 : (d->cout % 64 == 0) ? 64 : 32;
   // keep at least ~2 tiles per SM so the epilogue of one tile overlaps the main loop of the next
-  while (block_n > 64 && static_cast<long long>(m_tiles) * (d->cout / block_n) < 2LL * g_sm_count) block_n /= 2;
+  while (block_n > 64 && static_cast<long long>(m_tiles) * (d->cout / block_n) < g_sm_count) block_n /= 2;
+  if (const char* e = getenv("UP_DEBUG_BLOCKN")) {
+    const int v = atoi(e);
+    if (v >= 32 && d->cout % v == 0 && (nchw || v % 64 == 0)) block_n = v;
+  }
   p.block_n = block_n;
   p.n_tiles = d->cout / block_n;
   p.cout = d->cout;
@@ -564,9 +585,17 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   p.b_bytes = block_n * ck * 2;
   p.buf_bytes = split ? 2 * kPlaneBytes : kPlaneBytes;
   p.nbuf = nchw ? 0 : (split ? 2 : (has_res ? 3 : 2));
+  if (const char* e = getenv("UP_DEBUG_NBUF")) {
+    const int v = atoi(e);
+    if (!nchw && v >= 2 && v <= kMaxBufs) p.nbuf = v;
+  }
   const size_t fixed = 1024 + 8 * (2 * kMaxStages + 4 + 2 * kMaxBufs) + 16 + static_cast<size_t>(p.nbuf) * p.buf_bytes;
   int stages = static_cast<int>((g_max_smem - fixed) / (p.a_bytes + p.b_bytes));
   if (stages > kMaxStages) stages = kMaxStages;
+  if (const char* e = getenv("UP_DEBUG_STAGES")) {
+    const int v = atoi(e);
+    if (v >= 2 && v < stages) stages = v;
+  }
   UP_CHECK_ARG(stages >= 2, "up_conv2d_fwd: not enough shared memory for 2 pipeline stages");
   p.stages = stages;
   p.idesc = make_idesc_f16(static_cast<uint32_t>(fmt), kTileM, static_cast<uint32_t>(block_n));

@@ -48,11 +48,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Spin on an mbarrier phase. A watchdog (≈ several seconds of SM clocks) turns a
 // protocol bug into a trap (launch failure) instead of a hung GPU box.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, long long limit = 8000000000LL) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) {
+    if (clock64() - t0 > limit) {
       printf("up: mbarrier watchdog: block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }
