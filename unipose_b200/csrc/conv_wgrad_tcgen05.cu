@@ -446,14 +446,15 @@ extern "C" int up_conv2d_wgrad(const UpConvDesc* d, const void* x, const void* d
   const uint32_t xbox[5] = {static_cast<uint32_t>(p.ckx), static_cast<uint32_t>(p.bw), 1u,
                             static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
   const int n_total = d->n + (groups - 1) * p.group_nstride;
-  rc = encode_act_map(&tmX0, fmt, x, n_total, d->h, d->w, d->x_cstride, d->stride, xbox, p.ckx * 2, "x");
+  rc = encode_act_map(&tmX0, fmt, x, n_total, d->h, d->w, d->x_cstride, d->stride, xbox, p.ckx * 2, "x", d->x_cextent,
+                      d->x_wpitch);
   if (rc) return rc;
   if (split) {
     rc = encode_act_map(&tmZ1, fmt, static_cast<const uint16_t*>(dz) + d->y_plane_stride, d->n, d->ho, d->wo, d->cout,
                         1, zbox, 128, "dz.lo");
     if (rc) return rc;
     rc = encode_act_map(&tmX1, fmt, static_cast<const uint16_t*>(x) + d->x_plane_stride, n_total, d->h, d->w,
-                        d->x_cstride, d->stride, xbox, p.ckx * 2, "x.lo");
+                        d->x_cstride, d->stride, xbox, p.ckx * 2, "x.lo", d->x_cextent, d->x_wpitch);
     if (rc) return rc;
   } else {
     tmZ1 = tmZ0;

@@ -220,7 +220,8 @@ def pack_input_s2d(x_nchw: torch.Tensor, y: Act, wpad_left: int = 0) -> None:
 def nchw_to_act(x: torch.Tensor, y, c_real: Optional[int] = None) -> None:
     yv = as_view(y)
     n, c, h, w = x.shape
-    assert (yv.n, yv.h, yv.w) == (n, h, w) and x.dtype == torch.float32 and x.is_contiguous()
+    x = x.contiguous()
+    assert (yv.n, yv.h, yv.w) == (n, h, w) and x.dtype == torch.float32
     _lib.call("up_nchw_f32_to_nhwc", _ptr(x), yv.ptr(), n, c, h, w, yv.c, yv.act.c, yv.coff, yv.act.mode,
               yv.act.plane_stride, _stream())
 
@@ -268,3 +269,108 @@ def upsample_bilinear_ac_nchw(x: torch.Tensor, size) -> torch.Tensor:
     _lib.call("up_upsample_bilinear_ac_nchw_f32", _ptr(x.contiguous()), _ptr(out), n, c, h, w, size[0], size[1],
               _stream())
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# training kernels
+# ---------------------------------------------------------------------------------------------
+def _uview(a) -> "_lib.UpView":
+    v = as_view(a)
+    return _lib.UpView(v.ptr(), v.act.c, v.coff, v.act.plane_stride)
+
+
+def _vref(a):
+    return ctypes.byref(_uview(a)) if a is not None else None
+
+
+def conv_desc(x, pc: PackedConv, ho: int, wo: int, *, stride=1, dil=1, pad=(0, 0), x_groups=1, x_group_nstride=0,
+              x_window=None) -> UpConvDesc:
+    """Forward descriptor of a layer (geometry only) - what up_conv2d_wgrad takes."""
+    xv = as_view(x)
+    d = UpConvDesc()
+    d.n, d.h, d.w = xv.n, xv.h, xv.w
+    if x_window is not None:
+        d.w, d.x_cextent = x_window
+        d.x_wpitch = xv.w
+    d.ho, d.wo = ho, wo
+    d.cin, d.cout = pc.cin, pc.cout
+    d.kh, d.kw, d.stride, d.dil = pc.kh, pc.kw, stride, dil
+    d.pad_h, d.pad_w = pad if not isinstance(pad, int) else (pad, pad)
+    d.x_cstride, d.x_coff = xv.act.c, xv.coff
+    d.x_groups, d.x_group_nstride = x_groups, x_group_nstride
+    d.dtype = pc.mode
+    d.x_plane_stride = xv.act.plane_stride
+    return d
+
+
+def wgrad_scratch_bytes(d: UpConvDesc) -> int:
+    return int(_lib.load().up_conv2d_wgrad_scratch_bytes(ctypes.byref(d)))
+
+
+def conv2d_wgrad(d: UpConvDesc, x, dz: Act, dw: torch.Tensor, scratch: torch.Tensor, accumulate: bool = False) -> None:
+    """dw[cout_real, cin_real, kh, kw] (+)= wgrad(x, dz); dz is a dense [n, ho, wo, cout_pad] Act."""
+    xv = as_view(x)
+    assert dz.c == d.cout and (dz.n, dz.h, dz.w) == (d.n, d.ho, d.wo), ((dz.n, dz.h, dz.w, dz.c), (d.n, d.ho, d.wo, d.cout))
+    assert dw.dtype == torch.float32 and dw.is_contiguous()
+    d.y_cstride, d.y_coff, d.y_plane_stride = dz.c, 0, dz.plane_stride
+    _lib.call("up_conv2d_wgrad", ctypes.byref(d), xv.ptr(), dz.ptr(), _ptr(dw), dw.shape[0], dw.shape[1],
+              _ptr(scratch), scratch.numel() * scratch.element_size(), 1 if accumulate else 0, _stream())
+
+
+def bn_stats(z, c: int, sums: torch.Tensor) -> None:
+    zv = as_view(z)
+    _lib.call("up_bn_stats", _vref(zv), zv.n * zv.h * zv.w, c, zv.act.mode, _ptr(sums), _stream())
+
+
+def bn_finalize(sums, count, bn, scale, shift, save_mean, save_invstd, c_real: int, c: int, update_running=True):
+    rm = bn.running_mean if (update_running and bn.running_mean is not None) else None
+    rv = bn.running_var if (update_running and bn.running_var is not None) else None
+    mom = 0.1 if bn.momentum is None else float(bn.momentum)
+    _lib.call("up_bn_finalize", _ptr(sums), count, _ptr(bn.weight.detach()), _ptr(bn.bias.detach()), _ptr(rm), _ptr(rv),
+              mom, float(bn.eps), _ptr(scale), _ptr(shift), _ptr(save_mean), _ptr(save_invstd), c_real, c, _stream())
+
+
+def scale_shift_act(z, y, scale, shift, *, relu: bool, residual=None, mask=None) -> None:
+    zv = as_view(z)
+    _lib.call("up_scale_shift_act", _vref(zv), _vref(y), _vref(residual), _vref(mask), _ptr(scale), _ptr(shift),
+              zv.n * zv.h * zv.w, zv.c, 1 if relu else 0, zv.act.mode, _stream())
+
+
+def bn_bwd(dy, y, z, dz, dres, save_mean, save_invstd, gamma, sums, c_real: int, relu: bool, dgamma, dbeta) -> None:
+    dv = as_view(dy)
+    npix = dv.n * dv.h * dv.w
+    _lib.call("up_bn_bwd_reduce", _vref(dv), _vref(y) if relu else None, _vref(z), _ptr(save_mean), _ptr(save_invstd),
+              npix, dv.c, 1 if relu else 0, dv.act.mode, _ptr(sums), _stream())
+    _lib.call("up_bn_bwd_apply", _vref(dv), _vref(y) if relu else None, _vref(z), _vref(dz), _vref(dres),
+              _ptr(save_mean), _ptr(save_invstd), _ptr(gamma), _ptr(sums), npix, c_real, dv.c, 1 if relu else 0,
+              dv.act.mode, _ptr(dgamma), _ptr(dbeta), _stream())
+
+
+def ew(a, out, *, m=None, op: int = 0, accumulate: bool = False) -> None:
+    """out (+)= a | a*m | a*(m>0)   (op 0 / 1 / 2)."""
+    av = as_view(a)
+    _lib.call("up_ew_mul", _vref(av), _vref(m), _vref(out), av.n * av.h * av.w, av.c, op, 1 if accumulate else 0,
+              av.act.mode, _stream())
+
+
+def maxpool3x3s2_bwd(x, dy, dx, accumulate: bool = False) -> None:
+    xv = as_view(x)
+    _lib.call("up_maxpool3x3s2_bwd", _vref(xv), _vref(dy), _vref(dx), xv.n, xv.h, xv.w, xv.c, 1 if accumulate else 0,
+              xv.act.mode, _stream())
+
+
+def upsample_bilinear_ac_bwd(dy, dx, accumulate: bool = False) -> None:
+    dyv, dxv = as_view(dy), as_view(dx)
+    _lib.call("up_upsample_bilinear_ac_bwd", _vref(dyv), _vref(dxv), dxv.n, dxv.h, dxv.w, dyv.h, dyv.w, dxv.c,
+              1 if accumulate else 0, dxv.act.mode, _stream())
+
+
+def add_broadcast(g, dx, mult: float, accumulate: bool) -> None:
+    dxv = as_view(dx)
+    _lib.call("up_add_broadcast", _vref(g), _vref(dxv), dxv.n, dxv.h * dxv.w, dxv.c, float(mult),
+              1 if accumulate else 0, dxv.act.mode, _stream())
+
+
+def zero_insert2x(x, y) -> None:
+    xv = as_view(x)
+    _lib.call("up_zero_insert2x", _vref(xv), _vref(y), xv.n, xv.h, xv.w, xv.c, xv.act.mode, _stream())
