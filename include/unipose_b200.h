@@ -149,6 +149,10 @@ int up_upsample_bilinear_ac(const void* x, void* y, int n, int h, int w, int ho,
 int up_global_avgpool(const void* x, void* y, int n, int h, int w, int c, int x_cstride, int x_coff,
                       int y_cstride, int y_coff, int dtype, int64_t x_plane_stride, int64_t y_plane_stride,
                       void* stream);
+/* Sum over h*w (adjoint of up_broadcast_hw): x NHWC view -> 16-bit [n,1,1,c] view. */
+int up_global_sumpool(const void* x, void* y, int n, int h, int w, int c, int x_cstride, int x_coff,
+                      int y_cstride, int y_coff, int dtype, int64_t x_plane_stride, int64_t y_plane_stride,
+                      void* stream);
 /* Broadcast a [n,1,1,c] tensor over ho x wo (bilinear from 1x1 with align_corners, wasp.py:83). */
 int up_broadcast_hw(const void* x, void* y, int n, int ho, int wo, int c, int x_cstride, int x_coff,
                     int y_cstride, int y_coff, int dtype, int64_t x_plane_stride, int64_t y_plane_stride,

@@ -1,0 +1,130 @@
+"""GPU parity of the training path (train-mode forward + backward through the whole network) against torch
+autograd over the CPU oracle graph on identical weights, inputs and dropout masks (unipose.py:113-124)."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import evaluate_oracle as E
+from oracle import unipose_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_l2(a, b):
+    a = a.detach().double().cpu().flatten()
+    b = b.detach().double().cpu().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _setup(n=4, size=96, seed=0, precision="fp32"):
+    from unipose_b200.model.unipose import unipose
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = unipose(dataset="MPII", num_classes=16, precision=precision)
+    sd = O.synth_state_dict(16, seed=seed)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().train()
+    x = O.synth_input(n, size, size, seed=seed)
+    hs = size // 8
+    target = torch.from_numpy(E.gaussian_heatmaps(n, 16, hs, hs, seed=seed + 3))
+    g = torch.Generator().manual_seed(seed + 9)
+    masks = []
+    for shape, p in (((n, 256, size // 16, size // 16), 0.5), ((n, 256, hs, hs), 0.5), ((n, 256, hs, hs), 0.1)):
+        masks.append((torch.rand(shape, generator=g) >= p).float() / (1.0 - p))
+    return m, sd, x, target, masks
+
+
+def _oracle_step(sd, x, target, masks):
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+          for k, v in sd.items()}
+    heat = O.unipose_forward(x, sd, training=True, dropout_masks=masks)
+    loss = F.mse_loss(heat, target)
+    loss.backward()
+    return heat.detach(), loss.detach(), sd
+
+
+CHECK = ["backbone.conv1.weight", "backbone.bn1.weight", "backbone.layer1.0.conv1.weight",
+         "backbone.layer1.0.downsample.0.weight", "backbone.layer2.0.conv2.weight", "backbone.layer3.11.conv2.weight",
+         "backbone.layer3.22.bn3.bias", "backbone.layer4.2.conv2.weight", "wasp.aspp1.atrous_conv.weight",
+         "wasp.aspp3.atrous_conv.weight", "wasp.conv2.weight", "wasp.global_avg_pool.1.weight",
+         "wasp.global_avg_pool.2.weight", "wasp.conv1.weight", "wasp.bn1.weight", "decoder.conv1.weight",
+         "decoder.last_conv.0.weight", "decoder.last_conv.4.weight", "decoder.last_conv.5.bias",
+         "decoder.last_conv.8.weight", "decoder.last_conv.8.bias"]
+
+
+def test_train_step_matches_oracle_autograd():
+    m, sd, x, target, masks = _setup()
+    from unipose_b200 import train
+    heat = train.forward_train(m, x.cuda(), dropout_masks=[t.cuda() for t in masks])
+    assert heat.requires_grad and heat.shape == (4, 17, 12, 12)
+    loss = F.mse_loss(heat, target.cuda())
+    loss.backward()
+    ref_heat, ref_loss, ref_sd = _oracle_step(sd, x, target, masks)
+    assert _rel_l2(heat, ref_heat) < 2e-3
+    assert abs(float(loss) - float(ref_loss)) < 2e-3 * float(ref_loss)
+    params = dict(m.named_parameters())
+    worst = {}
+    for k in CHECK:
+        assert params[k].grad is not None, k
+        worst[k] = _rel_l2(params[k].grad, ref_sd[k].grad)
+    print("grad rel-L2 errors:", {k: "%.2e" % v for k, v in worst.items()})
+    assert max(worst.values()) < 1e-2, worst
+    # dead parameters of the reference stay without gradient (decoder.py:20-21)
+    assert params["decoder.conv2.weight"].grad is None and params["decoder.bn2.weight"].grad is None
+    # running statistics were updated like torch's (momentum 0.1, unbiased variance)
+    bufs = dict(m.named_buffers())
+    for k in ("backbone.bn1.running_mean", "backbone.layer3.5.bn2.running_var", "wasp.bn1.running_var",
+              "decoder.last_conv.1.running_mean"):
+        assert _rel_l2(bufs[k], ref_sd[k]) < 2e-3, k
+    assert int(bufs["backbone.bn1.num_batches_tracked"]) == 1
+
+
+def test_reference_training_loop_runs_unchanged():
+    """optimizer.zero_grad(); heat = model(x); loss = MSELoss(heat, target); loss.backward(); optimizer.step()."""
+    m, sd, x, target, masks = _setup(n=2, size=64, seed=1, precision="bf16")
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    crit = torch.nn.MSELoss().cuda()
+    losses = []
+    xc, tc = x.cuda(), target.cuda()
+    for _ in range(3):
+        opt.zero_grad()
+        heat = m(xc)
+        loss = crit(heat, tc)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)), losses
+    assert losses[-1] < losses[0], losses
+
+
+def test_fused_train_step_matches_manual_adam():
+    from unipose_b200 import train
+    m, sd, x, target, masks = _setup(n=2, size=64, seed=2, precision="fp32")
+    for mod in m.modules():     # dropout off so that both paths see the same network
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    ts = train.TrainStep(m, lr=1e-3)
+    before = {k: v.detach().clone() for k, v in m.named_parameters()}
+    loss = ts.step(x.cuda(), target.cuda())
+    torch.cuda.synchronize()
+    # oracle: same step with torch.optim.Adam on the CPU graph
+    sd2 = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+           for k, v in sd.items()}
+    heat = O.unipose_forward(x, sd2, training=True)
+    ref_loss = F.mse_loss(heat, target)
+    ref_loss.backward()
+    live = [k for k, v in sd2.items() if getattr(v, "grad", None) is not None]
+    opt = torch.optim.Adam([sd2[k] for k in live], lr=1e-3)
+    opt.step()
+    assert abs(float(loss) - float(ref_loss)) < 2e-3 * float(ref_loss)
+    after = dict(m.named_parameters())
+    for k in ("backbone.layer3.11.conv2.weight", "wasp.conv2.weight", "decoder.last_conv.8.bias"):
+        # Adam's first step moves every weight by ~lr * sign(grad): compare the update direction
+        upd = (after[k].detach().cpu() - before[k].cpu())
+        ref_upd = (sd2[k].detach() - sd[k])
+        agree = (torch.sign(upd) == torch.sign(ref_upd)).float().mean()
+        assert agree > 0.97, (k, float(agree))
+    assert torch.equal(after["decoder.conv2.weight"].detach().cpu(), before["decoder.conv2.weight"].cpu())

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "up_upsample_bilinear_ac": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P],
     "up_global_avgpool": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P],
     "up_broadcast_hw": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P],
+    "up_global_sumpool": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P],
     "up_upsample_bilinear_ac_nchw_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "up_avgpool9s8p1_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "up_convlstm_cell0_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

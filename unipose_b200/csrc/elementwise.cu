@@ -294,7 +294,7 @@ __global__ void upsample_bilinear_ac_nchw_kernel(const float* __restrict__ x, fl
 // one block per (image, 64 channels): 8 channel-octets x 32 pixel lanes
 template <int kMode>
 __global__ void global_avgpool_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int hw, int c, int xcs,
-                                      int xcoff, int ycs, int ycoff, long long xplane, long long yplane) {
+                                      int xcoff, int ycs, int ycoff, long long xplane, long long yplane, int sum_only) {
   const int blocks_per_img = c / 64;
   const int b = blockIdx.x / blocks_per_img;
   const int cg = blockIdx.x % blocks_per_img;
@@ -318,7 +318,7 @@ __global__ void global_avgpool_kernel(const uint16_t* __restrict__ x, uint16_t* 
   if (threadIdx.x < 64) {
     float s = 0.f;
     for (int q = 0; q < 32; ++q) s += red[q][threadIdx.x];
-    red[0][threadIdx.x] = s / static_cast<float>(hw);
+    red[0][threadIdx.x] = sum_only ? s : s / static_cast<float>(hw);
   }
   __syncthreads();
   if (threadIdx.x < 8) {
@@ -474,8 +474,21 @@ extern "C" int up_global_avgpool(const void* x, void* y, int n, int h, int w, in
   UP_CHECK_ARG(c % 64 == 0, "up_global_avgpool: c must be a multiple of 64");
   UP_DISPATCH_MODE(dtype, (global_avgpool_kernel<kMode><<<n*(c / 64), 256, 0, (cudaStream_t)stream>>>(
                               static_cast<const uint16_t*>(x), static_cast<uint16_t*>(y), h * w, c, x_cstride, x_coff,
-                              y_cstride, y_coff, x_plane_stride, y_plane_stride)));
+                              y_cstride, y_coff, x_plane_stride, y_plane_stride, 0)));
   UP_CHECK_LAUNCH("global_avgpool_kernel");
+  return 0;
+}
+
+extern "C" int up_global_sumpool(const void* x, void* y, int n, int h, int w, int c, int x_cstride, int x_coff,
+                                 int y_cstride, int y_coff, int dtype, int64_t x_plane_stride, int64_t y_plane_stride,
+                                 void* stream) {
+  int rc = check_views("up_global_sumpool", x, y, c, x_cstride, x_coff, y_cstride, y_coff);
+  if (rc) return rc;
+  UP_CHECK_ARG(c % 64 == 0, "up_global_sumpool: c must be a multiple of 64");
+  UP_DISPATCH_MODE(dtype, (global_avgpool_kernel<kMode><<<n*(c / 64), 256, 0, (cudaStream_t)stream>>>(
+                              static_cast<const uint16_t*>(x), static_cast<uint16_t*>(y), h * w, c, x_cstride, x_coff,
+                              y_cstride, y_coff, x_plane_stride, y_plane_stride, 1)));
+  UP_CHECK_LAUNCH("global_sumpool_kernel");
   return 0;
 }
 

@@ -256,6 +256,13 @@ def global_avgpool(x, y) -> None:
               xv.act.mode, xv.act.plane_stride, yv.act.plane_stride, _stream())
 
 
+def global_sumpool(x, y) -> None:
+    xv, yv = as_view(x), as_view(y)
+    assert xv.c == yv.c and xv.n == yv.n and yv.h == 1 and yv.w == 1
+    _lib.call("up_global_sumpool", xv.ptr(), yv.ptr(), xv.n, xv.h, xv.w, xv.c, xv.act.c, xv.coff, yv.act.c, yv.coff,
+              xv.act.mode, xv.act.plane_stride, yv.act.plane_stride, _stream())
+
+
 def broadcast_hw(x, y) -> None:
     xv, yv = as_view(x), as_view(y)
     assert xv.c == yv.c and xv.n == yv.n and xv.h == 1 and xv.w == 1
@@ -307,12 +314,15 @@ def wgrad_scratch_bytes(d: UpConvDesc) -> int:
     return int(_lib.load().up_conv2d_wgrad_scratch_bytes(ctypes.byref(d)))
 
 
-def conv2d_wgrad(d: UpConvDesc, x, dz: Act, dw: torch.Tensor, scratch: torch.Tensor, accumulate: bool = False) -> None:
-    """dw[cout_real, cin_real, kh, kw] (+)= wgrad(x, dz); dz is a dense [n, ho, wo, cout_pad] Act."""
+def conv2d_wgrad(d: UpConvDesc, x, dz, dw: torch.Tensor, scratch: torch.Tensor, accumulate: bool = False) -> None:
+    """dw[cout_real, cin_real, kh, kw] (+)= wgrad(x, dz); dz is a dense [n, ho, wo, cout_pad] Act (or an image
+    sub-range of one)."""
     xv = as_view(x)
-    assert dz.c == d.cout and (dz.n, dz.h, dz.w) == (d.n, d.ho, d.wo), ((dz.n, dz.h, dz.w, dz.c), (d.n, d.ho, d.wo, d.cout))
+    dz = as_view(dz)
+    assert dz.coff == 0 and dz.c == dz.act.c == d.cout and (dz.n, dz.h, dz.w) == (d.n, d.ho, d.wo), \
+        ((dz.n, dz.h, dz.w, dz.c), (d.n, d.ho, d.wo, d.cout))
     assert dw.dtype == torch.float32 and dw.is_contiguous()
-    d.y_cstride, d.y_coff, d.y_plane_stride = dz.c, 0, dz.plane_stride
+    d.y_cstride, d.y_coff, d.y_plane_stride = dz.c, 0, dz.act.plane_stride
     _lib.call("up_conv2d_wgrad", ctypes.byref(d), xv.ptr(), dz.ptr(), _ptr(dw), dw.shape[0], dw.shape[1],
               _ptr(scratch), scratch.numel() * scratch.element_size(), 1 if accumulate else 0, _stream())
 

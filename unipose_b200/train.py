@@ -1,0 +1,562 @@
+"""Training path (forward in .train() mode + backward) of the image model on the B200 kernels.
+
+`model(input)` in train mode returns heat-maps that carry a grad_fn: the reference's own training loop
+(unipose.py:113-124: optimizer.zero_grad(); heat = model(x); loss = MSELoss(heat, target); loss.backward();
+optimizer.step()) runs unchanged.  One torch.autograd.Function spans the whole network; its forward / backward
+replay two static kernel plans:
+
+  forward   per conv+BN unit: tcgen05 conv (raw output z) -> up_bn_stats -> up_bn_finalize (batch statistics, running
+            stats update) -> up_scale_shift_act (normalise + residual + ReLU + dropout mask)
+  backward  reverse tape: up_bn_bwd_* (ReLU gate + BatchNorm backward, dgamma/dbeta, residual gradient) ->
+            tcgen05 wgrad (MN-major operands) -> dgrad = the forward conv kernel on the flipped/transposed filter
+            (gradient accumulation across branches rides on its residual input)
+
+`TrainStep` adds the fused tail used by the bench / multi-GPU training: up_mse_fwd_bwd, one NCCL all-reduce of the
+flat gradient buffer, up_adam_step.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import engine, ops
+from .ops import Act, PackedConv, View, as_view, round_up
+
+
+def _region(v: View):
+    return (id(v.act), v.n_off, v.n_off + v.n, v.coff, v.coff + v.c)
+
+
+class TrainPlan:
+    """Forward + backward op lists over static buffers for one (input shape, precision)."""
+
+    def __init__(self, device, precision: str):
+        self.device = torch.device(device)
+        self.precision = precision
+        self.mode = ops.mode_of(precision)
+        self.fwd: List = []
+        self.bwd: List = []
+        self.tape: List = []
+        self.buffers: List = []
+        self.pack_jobs: List = []          # refilled every step (weights change every step)
+        self.grads: Dict[int, Act] = {}    # id(forward Act) -> gradient Act
+        self.written: List[Tuple] = []     # gradient regions that already hold a value
+        self.pgrad: Dict[int, torch.Tensor] = {}
+        self.pgrad_written = set()
+        self.params: List[nn.Parameter] = []
+        self.masks: List[Tuple[Act, float]] = []
+        self.bn_modules: List[nn.BatchNorm2d] = []
+        self.scratch_bytes = 0
+        self.live_params: List[nn.Parameter] = []
+        self._live_ids = set()
+        self.flat_g: Optional[torch.Tensor] = None
+        self.scratch: Optional[torch.Tensor] = None
+        self.input: Optional[torch.Tensor] = None
+        self.heat: Optional[torch.Tensor] = None
+        self.dheat: Optional[torch.Tensor] = None
+
+    # ---- buffers -------------------------------------------------------------------------------
+    def act(self, n, h, w, c, zero=False) -> Act:
+        a = Act(n, h, w, c, self.mode, self.device, zero=zero)
+        self.buffers.append(a)
+        return a
+
+    def tensor(self, shape, dtype=torch.float32, zero=True) -> torch.Tensor:
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+        self.buffers.append(t)
+        return t
+
+    def grad_act(self, a: Act) -> Act:
+        g = self.grads.get(id(a))
+        if g is None:
+            g = self.act(a.n, a.h, a.w, a.c)
+            self.grads[id(a)] = g
+        return g
+
+    def grad_view(self, v) -> View:
+        v = as_view(v)
+        return View(self.grad_act(v.act), coff=v.coff, c=v.c, n_off=v.n_off, n=v.n)
+
+    def is_written(self, gv: View) -> bool:
+        a, n0, n1, c0, c1 = _region(gv)
+        for (b, m0, m1, d0, d1) in self.written:
+            if a == b and n0 < m1 and m0 < n1 and c0 < d1 and d0 < c1:
+                return True
+        return False
+
+    def mark_written(self, gv: View) -> None:
+        self.written.append(_region(gv))
+
+    def has_grad(self, v) -> bool:
+        v = as_view(v)
+        g = self.grads.get(id(v.act))
+        if g is None:
+            return False
+        return self.is_written(View(g, coff=v.coff, c=v.c, n_off=v.n_off, n=v.n))
+
+    def param_grad(self, p: nn.Parameter) -> torch.Tensor:
+        g = self.pgrad.get(id(p))
+        if g is None:
+            g = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+            self.pgrad[id(p)] = g
+            self.params.append(p)
+        return g
+
+    # ---- weights ---------------------------------------------------------------------------------
+    def packed(self, weight_src, cout: int, cin: int, bias=None) -> PackedConv:
+        """Packed weights refreshed every step from `weight_src()` (an OIHW fp32 tensor); scale 1, shift = bias."""
+        w0 = weight_src()
+        co_r, ci_r, kh, kw = w0.shape
+        planes = 2 if self.mode == ops.UP_SPLIT else 1
+        dt = torch.float16 if self.mode == ops.UP_FP16 else torch.bfloat16
+        wbuf = torch.empty((planes, kh * kw, cout, cin), dtype=dt, device=self.device)
+        scale = torch.zeros(cout, dtype=torch.float32, device=self.device)
+        scale[:co_r] = 1.0
+        shift = torch.zeros(cout, dtype=torch.float32, device=self.device)
+        pc = PackedConv(wbuf, scale, shift, kh, kw, cout, cin, co_r, ci_r, self.mode)
+
+        def fill():
+            w = weight_src().float().contiguous()
+            ops._lib.call("up_pack_conv_weight", ops._ptr(w), ops._ptr(wbuf), co_r, ci_r, kh, kw, cout, cin, self.mode,
+                          kh * kw * cout * cin, ops._stream())
+            if bias is not None:
+                shift[:co_r] = bias.detach().float()
+        self.pack_jobs.append(fill)
+        return pc
+
+    # ---- ops with adjoints --------------------------------------------------------------------------
+    def conv_unit(self, x, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], *, relu: bool, residual=None, stride=1,
+                  dil=1, pad=None, mask=None, x_groups=1, x_group_nstride=0, x_window=None, weight_fn=None,
+                  weight_fn_inv=None, cin_pad=None, cout_pad=None, x_needs_grad=True, out=None, nchw_out=None):
+        """conv (+ train-mode BatchNorm) (+ residual) (+ ReLU) (+ dropout mask); records its backward."""
+        xv = as_view(x)
+        w_src = (lambda: conv.weight.detach()) if weight_fn is None else (lambda: weight_fn(conv.weight.detach()))
+        w0 = w_src()
+        co_r, ci_r, kh, kw = w0.shape
+        cout = cout_pad or round_up(co_r, 64)
+        cin = cin_pad or round_up(ci_r, 16)
+        if pad is None:
+            pad = (dil * (kh - 1) // 2, dil * (kw - 1) // 2)
+        if isinstance(pad, int):
+            pad = (pad, pad)
+        h_in, w_in = xv.h, (x_window[0] if x_window is not None else xv.w)
+        ho = (h_in + 2 * pad[0] - dil * (kh - 1) - 1) // stride + 1
+        wo = (w_in + 2 * pad[1] - dil * (kw - 1) - 1) // stride + 1
+        if x_window is not None:
+            ho, wo = h_in, w_in          # the stem: explicit output size, asymmetric padding
+        n = xv.n
+        pc = self.packed(w_src, cout, cin, bias=None if bn is not None else conv.bias)
+        kw_conv = dict(stride=stride, dil=dil, pad=pad, ho=ho, wo=wo, x_groups=x_groups,
+                       x_group_nstride=x_group_nstride, x_window=x_window)
+        z = out if (bn is None and out is not None) else self.act(n, ho, wo, cout)
+        if bn is None and out is not None:
+            z = as_view(out)
+            assert (z.n, z.h, z.w, z.c) == (n, ho, wo, cout)
+        for prm in ([conv.weight] + ([conv.bias] if (conv.bias is not None and bn is None) else []) +
+                    ([bn.weight, bn.bias] if bn is not None else [])):
+            if id(prm) not in self._live_ids:
+                self._live_ids.add(id(prm))
+                self.live_params.append(prm)
+        rec = dict(x=xv, conv=conv, bn=bn, relu=relu, residual=residual, mask=mask, pc=pc, z=z, stride=stride, dil=dil,
+                   pad=pad, ho=ho, wo=wo, x_groups=x_groups, x_group_nstride=x_group_nstride, x_window=x_window,
+                   weight_fn=weight_fn, weight_fn_inv=weight_fn_inv, x_needs_grad=x_needs_grad, cout=cout, cin=cin,
+                   co_r=co_r, ci_r=ci_r, kh=kh, kw=kw, nchw_out=nchw_out)
+        if nchw_out is not None:
+            # network head: conv + bias straight into the fp32 NCHW heat-map tensor
+            self.fwd.append(lambda: ops.conv2d(xv, pc, nchw_out, cout_valid=co_r, **kw_conv))
+            rec["y"] = None
+            self.tape.append(lambda: self._conv_unit_bwd(rec))
+            return nchw_out
+        self.fwd.append(lambda: ops.conv2d(xv, pc, z, **kw_conv))
+        if bn is None:
+            y = z
+            if relu or mask is not None or residual is not None:
+                raise NotImplementedError("conv without BatchNorm only supports a plain (bias) epilogue in training")
+        else:
+            c = cout
+            sums = self.tensor((2 * c,), dtype=torch.float64)
+            scale, shift, mean, invstd = (self.tensor((c,)) for _ in range(4))
+            y = out if out is not None else self.act(n, ho, wo, cout)
+            count = n * ho * wo
+            self.bn_modules.append(bn)
+            self.fwd.append(lambda: ops.bn_stats(z, c, sums))
+            self.fwd.append(lambda: ops.bn_finalize(sums, count, bn, scale, shift, mean, invstd, co_r, c))
+            self.fwd.append(lambda: ops.scale_shift_act(z, y, scale, shift, relu=relu, residual=residual, mask=mask))
+            rec.update(sums=sums, mean=mean, invstd=invstd)
+        rec["y"] = y
+        self.tape.append(lambda: self._conv_unit_bwd(rec))
+        return y
+
+    def _conv_unit_bwd(self, r) -> None:
+        xv, conv, bn, pc, z = r["x"], r["conv"], r["bn"], r["pc"], r["z"]
+        n, ho, wo, cout = z.n, z.h, z.w, z.c
+        # ---- gradient w.r.t. the conv output z ----
+        if r["nchw_out"] is not None:
+            dz = self.act(n, ho, wo, cout, zero=True)
+            dheat = self.dheat
+            self.bwd.append(lambda: ops.nchw_to_act(dheat, dz))
+            if conv.bias is not None:
+                bsums = self.tensor((2 * cout,), dtype=torch.float64)
+                gb = self.param_grad(conv.bias)
+                self.bwd.append(lambda: ops.bn_stats(dz, cout, bsums))
+                self.bwd.append(lambda: gb.copy_(bsums[:r["co_r"]]))
+        else:
+            y = r["y"]
+            if not self.has_grad(y):
+                return
+            dy = self.grad_view(y)
+            if r["mask"] is not None:
+                tmp = self.act(n, ho, wo, cout)
+                mask = r["mask"]
+                self.bwd.append(lambda: ops.ew(dy, tmp, m=mask, op=1))
+                dy = as_view(tmp)
+            if bn is None:
+                dz = dy          # plain conv: dz is the incoming gradient itself
+            else:
+                dz = self.act(n, ho, wo, cout)
+                dres, dres_tmp, rv = None, None, None
+                if r["residual"] is not None:
+                    rv = self.grad_view(r["residual"])
+                    if self.is_written(rv):
+                        dres_tmp = self.act(n, ho, wo, cout)
+                        dres = dres_tmp
+                    else:
+                        dres = rv
+                        self.mark_written(rv)
+                dgamma, dbeta = self.param_grad(bn.weight), self.param_grad(bn.bias)
+                sums, mean, invstd, relu, co_r = r["sums"], r["mean"], r["invstd"], r["relu"], r["co_r"]
+                self.bwd.append(lambda: ops.bn_bwd(dy, y, z, dz, dres, mean, invstd, bn.weight.detach(), sums, co_r,
+                                                   relu, dgamma, dbeta))
+                if dres_tmp is not None:
+                    self.bwd.append(lambda: ops.ew(dres_tmp, rv, accumulate=True))
+        dzv = as_view(dz)
+        # ---- weight gradient ----
+        d = ops.conv_desc(xv, pc, ho, wo, stride=r["stride"], dil=r["dil"], pad=r["pad"], x_groups=r["x_groups"],
+                          x_group_nstride=r["x_group_nstride"], x_window=r["x_window"])
+        self.scratch_bytes = max(self.scratch_bytes, ops.wgrad_scratch_bytes(d))
+        gw = self.param_grad(conv.weight)
+        acc = id(conv.weight) in self.pgrad_written
+        self.pgrad_written.add(id(conv.weight))
+        if r["weight_fn"] is None:
+            self.bwd.append(lambda: ops.conv2d_wgrad(d, xv, dzv, gw, self.scratch, accumulate=acc))
+        else:
+            gtmp = self.tensor((r["co_r"], r["ci_r"], r["kh"], r["kw"]))
+            inv = r["weight_fn_inv"]
+            self.bwd.append(lambda: ops.conv2d_wgrad(d, xv, dzv, gtmp, self.scratch, accumulate=False))
+            if acc:
+                self.bwd.append(lambda: gw.add_(inv(gtmp)))
+            else:
+                self.bwd.append(lambda: gw.copy_(inv(gtmp)))
+        # ---- input gradient: the forward kernel on the flipped / transposed filter ----
+        if not r["x_needs_grad"]:
+            return
+        kh, kw, dil, stride = r["kh"], r["kw"], r["dil"], r["stride"]
+        pad_t = (dil * (kh - 1) - r["pad"][0], dil * (kw - 1) - r["pad"][1])
+        src = dzv
+        if stride == 2:
+            up = self.act(n, 2 * ho, 2 * wo, cout)
+            self.bwd.append(lambda: ops.zero_insert2x(dzv, up))
+            src = as_view(up)
+        groups = r["x_groups"]
+        cg_real = r["ci_r"] // groups
+        cg_pad = r["cin"] // groups
+        wfn = r["weight_fn"]
+        for g in range(groups):
+            def w_t(g=g):
+                w = conv.weight.detach()
+                if wfn is not None:
+                    w = wfn(w)
+                w = w[:, g * cg_real:(g + 1) * cg_real]
+                return w.flip(2, 3).transpose(0, 1)
+            pct = self.packed(w_t, cout=cg_pad if groups > 1 else xv.c, cin=cout)
+            xg = View(self.grad_act(xv.act), coff=xv.coff, c=xv.c, n_off=xv.n_off + g * r["x_group_nstride"], n=xv.n)
+            res = xg if self.is_written(xg) else None
+            self.mark_written(xg)
+            self.bwd.append(lambda src=src, pct=pct, xg=xg, res=res: ops.conv2d(
+                src, pct, xg, dil=dil, pad=pad_t, ho=xv.h, wo=xv.w, residual=res))
+
+    def maxpool(self, x, y) -> None:
+        xv, yv = as_view(x), as_view(y)
+        self.fwd.append(lambda: ops.maxpool3x3s2(xv, yv))
+
+        def bwd():
+            if not self.has_grad(yv):
+                return
+            dy, dx = self.grad_view(yv), self.grad_view(xv)
+            acc = self.is_written(dx)
+            self.mark_written(dx)
+            self.bwd.append(lambda: ops.maxpool3x3s2_bwd(xv, dy, dx, accumulate=acc))
+        self.tape.append(bwd)
+
+    def upsample(self, x, y) -> None:
+        xv, yv = as_view(x), as_view(y)
+        self.fwd.append(lambda: ops.upsample_bilinear_ac(xv, yv))
+
+        def bwd():
+            if not self.has_grad(yv):
+                return
+            dy, dx = self.grad_view(yv), self.grad_view(xv)
+            acc = self.is_written(dx)
+            self.mark_written(dx)
+            self.bwd.append(lambda: ops.upsample_bilinear_ac_bwd(dy, dx, accumulate=acc))
+        self.tape.append(bwd)
+
+    def global_avgpool(self, x, g) -> None:
+        xv, gv = as_view(x), as_view(g)
+        self.fwd.append(lambda: ops.global_avgpool(xv, gv))
+
+        def bwd():
+            if not self.has_grad(gv):
+                return
+            dg, dx = self.grad_view(gv), self.grad_view(xv)
+            acc = self.is_written(dx)
+            self.mark_written(dx)
+            self.bwd.append(lambda: ops.add_broadcast(dg, dx, 1.0 / (xv.h * xv.w), accumulate=acc))
+        self.tape.append(bwd)
+
+    def broadcast_hw(self, g, y) -> None:
+        gv, yv = as_view(g), as_view(y)
+        self.fwd.append(lambda: ops.broadcast_hw(gv, yv))
+
+        def bwd():
+            if not self.has_grad(yv):
+                return
+            dy, dg = self.grad_view(yv), self.grad_view(gv)
+            assert not self.is_written(dg)
+            self.mark_written(dg)
+            self.bwd.append(lambda: ops.global_sumpool(dy, dg))
+        self.tape.append(bwd)
+
+    # ---- assembly --------------------------------------------------------------------------------
+    def finalize(self, flat: bool = False) -> None:
+        """Emit the backward ops (reverse tape).  flat=True: every live parameter's gradient is a view of ONE flat
+        fp32 buffer (self.flat_g) - what the all-reduce and the fused Adam step operate on."""
+        if flat:
+            total = sum(q.numel() for q in self.live_params)
+            self.flat_g = torch.zeros(total, dtype=torch.float32, device=self.device)
+            off = 0
+            for q in self.live_params:
+                self.pgrad[id(q)] = self.flat_g[off:off + q.numel()].view(q.shape)
+                self.params.append(q)
+                off += q.numel()
+        for t in reversed(self.tape):
+            t()
+        self.scratch = torch.empty(max(self.scratch_bytes // 4, 1), dtype=torch.float32, device=self.device)
+
+    def run_forward(self, x: torch.Tensor, masks: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+        self.input.copy_(x)
+        for job in self.pack_jobs:
+            job()
+        self._fill_masks(masks)
+        for op in self.fwd:
+            op()
+        for bn in self.bn_modules:
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked.add_(1)
+        return self.heat
+
+    def run_backward(self, dheat: torch.Tensor) -> None:
+        self.dheat.copy_(dheat)
+        for op in self.bwd:
+            op()
+
+    def _fill_masks(self, given) -> None:
+        for i, (act, p) in enumerate(self.masks):
+            if given is not None:
+                ops.nchw_to_act(given[i].float().contiguous(), act)
+                continue
+            keep = (torch.rand((act.n, act.h, act.w, act.c), device=self.device) >= p)
+            s = 1.0 / (1.0 - p)
+            if self.mode == ops.UP_SPLIT:
+                hi = torch.tensor(s, dtype=torch.bfloat16)
+                lo = torch.tensor(s - float(hi), dtype=torch.bfloat16)
+                act.t[0] = keep.to(act.t.dtype) * hi.to(self.device)
+                act.t[1] = keep.to(act.t.dtype) * lo.to(self.device)
+            else:
+                act.t[0] = keep.to(act.t.dtype) * s
+
+
+# ----------------------------------------------------------------------------------------------------
+# network emission (mirrors the eval-mode plan of model/unipose.py, with train-mode BatchNorm + dropout)
+# ----------------------------------------------------------------------------------------------------
+def _stem_window_weight_inv(g: torch.Tensor) -> torch.Tensor:
+    """Adjoint of resnet.stem_window_weight: [co,64,4,1] gradient -> [co,3,7,7]."""
+    co = g.shape[0]
+    g2 = g.reshape(co, 4, 16, 4).permute(0, 2, 3, 1)      # [co, ch16, kh', kw']
+    out = g.new_zeros((co, 3, 7, 7))
+    for a in range(4):
+        for ph in range(2):
+            kh = 2 * (a - 2) + ph + 3
+            if not 0 <= kh < 7:
+                continue
+            for bb in range(4):
+                for pw in range(2):
+                    kw = 2 * (bb - 2) + pw + 3
+                    if 0 <= kw < 7:
+                        c0 = (ph * 2 + pw) * 3
+                        out[:, :, kh, kw] = g2[:, c0:c0 + 3, a, bb]
+    return out
+
+
+def build_image_train_plan(model, shape, device, precision: str, flat: bool = False) -> TrainPlan:
+    from .model.modules.backbone.resnet import stem_window_weight
+    n, _, h, w = shape
+    if h % 16 or w % 16:
+        raise ValueError("unipose_b200: input height/width must be multiples of 16")
+    tp = TrainPlan(device, precision)
+    tp.input = torch.zeros(shape, dtype=torch.float32, device=device)
+    bb, wasp, dec = model.backbone, model.wasp, model.decoder
+    for m in model.modules():
+        if isinstance(m, nn.BatchNorm2d) and not m.training:
+            raise NotImplementedError("unipose_b200: training with frozen (eval-mode) BatchNorm layers is not supported yet")
+
+    # ---- backbone ----
+    x2 = tp.act(n, h // 2, w // 2 + 3, 16, zero=True)
+    tp.fwd.append(lambda: ops.pack_input_s2d(tp.input, x2, wpad_left=2))
+    stem = tp.conv_unit(x2, bb.conv1, bb.bn1, relu=True, pad=(2, 0), x_window=(w // 2, 64), cin_pad=64,
+                        weight_fn=stem_window_weight, weight_fn_inv=_stem_window_weight_inv, x_needs_grad=False)
+    x = tp.act(n, h // 4, w // 4, 64)
+    tp.maxpool(stem, x)
+    low = None
+    for name in ("layer1", "layer2", "layer3", "layer4"):
+        for blk in getattr(bb, name):
+            s, d = blk.stride, blk.dilation
+            t1 = tp.conv_unit(x, blk.conv1, blk.bn1, relu=True)
+            t2 = tp.conv_unit(t1, blk.conv2, blk.bn2, relu=True, stride=s, dil=d, pad=d)
+            res = x
+            if blk.downsample is not None:
+                res = tp.conv_unit(x, blk.downsample[0], blk.downsample[1], relu=False, stride=s, pad=0)
+            x = tp.conv_unit(t2, blk.conv3, blk.bn3, relu=True, residual=res)
+        if name == "layer1":
+            low = x
+    feat = x
+    hh, ww = feat.h, feat.w
+
+    # ---- WASP (wasp.py:66-90) ----
+    S = tp.act(4 * n, hh, ww, 256)
+    br = [View(S, n_off=i * n, n=n) for i in range(4)]
+    aspp = [wasp.aspp1, wasp.aspp2, wasp.aspp3, wasp.aspp4]
+    src = feat
+    for i, a in enumerate(aspp):
+        c = a.atrous_conv
+        tp.conv_unit(src, c, a.bn, relu=True, dil=c.dilation[0], pad=c.padding[0], out=br[i])
+        src = br[i]
+    T = tp.conv_unit(S, wasp.conv2, None, relu=False)
+    U = tp.act(5 * n, hh, ww, 256)
+    tp.conv_unit(T, wasp.conv2, None, relu=False, out=View(U, n_off=0, n=4 * n))
+    g = tp.act(n, 1, 1, feat.c)
+    tp.global_avgpool(feat, g)
+    gap_seq = wasp.global_avg_pool
+    gap_bn = gap_seq[2] if isinstance(gap_seq[2], nn.BatchNorm2d) else None
+    if gap_bn is None:
+        raise NotImplementedError("unipose_b200: training the video WASP (no BatchNorm in the pooling branch) is not supported yet")
+    g2 = tp.conv_unit(g, gap_seq[1], gap_bn, relu=True)
+    tp.broadcast_hw(g2, View(U, n_off=4 * n, n=n))
+    mask_w = tp.act(n, hh, ww, 256)
+    tp.masks.append((mask_w, wasp.dropout.p))
+    wout = tp.conv_unit(View(U, n_off=0, n=n), wasp.conv1, wasp.bn1, relu=True, x_groups=5, x_group_nstride=n,
+                        mask=mask_w)
+
+    # ---- decoder (decoder.py:38-56) ----
+    lo = tp.conv_unit(low, dec.conv1, dec.bn1, relu=True, cout_pad=64)
+    hc, wc = (low.h - 1) // 2 + 1, (low.w - 1) // 2 + 1
+    cat = tp.act(n, hc, wc, 320, zero=True)
+    tp.maxpool(lo, View(cat, coff=256, c=64))
+    tp.upsample(wout, View(cat, coff=0, c=256))
+    lc = dec.last_conv
+    m1 = tp.act(n, hc, wc, 256)
+    m2 = tp.act(n, hc, wc, 256)
+    tp.masks.append((m1, lc[3].p))
+    tp.masks.append((m2, lc[7].p))
+    d1 = tp.conv_unit(cat, lc[0], lc[1], relu=True, pad=1, cin_pad=320, mask=m1)
+    d2 = tp.conv_unit(d1, lc[4], lc[5], relu=True, pad=1, mask=m2)
+    tp.heat = torch.zeros((n, dec.num_out, hc, wc), dtype=torch.float32, device=device)
+    tp.dheat = torch.zeros_like(tp.heat)
+    tp.conv_unit(d2, lc[8], None, relu=False, nchw_out=tp.heat)
+    tp.finalize(flat=flat)
+    return tp
+
+
+class _TrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan: TrainPlan, masks, x, *params):
+        ctx.plan = plan
+        heat = plan.run_forward(x.detach().float(), masks)
+        return heat.clone()
+
+    @staticmethod
+    def backward(ctx, dheat):
+        plan: TrainPlan = ctx.plan
+        plan.run_backward(dheat.detach().float().contiguous())
+        grads = tuple(plan.pgrad[id(p)].clone() for p in plan.params)
+        return (None, None, None) + grads
+
+
+def forward_train(model, input: torch.Tensor, dropout_masks=None) -> torch.Tensor:
+    """Train-mode forward of model/unipose.unipose; the result carries a grad_fn whose backward runs the B200 plan.
+    `dropout_masks`: optional three pre-scaled fp32 NCHW masks (wasp, decoder 0.5, decoder 0.1) for parity tests."""
+    if getattr(model, "stride", 8) != 8:
+        raise NotImplementedError("unipose_b200: training supports stride=8 outputs (the reference's training setting)")
+    key = ("train", tuple(input.shape), model._precision(), input.device.index)
+    plan = model._plans.get(key)
+    if plan is None:
+        plan = build_image_train_plan(model, tuple(input.shape), input.device, model._precision())
+        model._plans[key] = plan
+    return _TrainFn.apply(plan, dropout_masks, input, *plan.params)
+
+
+# ----------------------------------------------------------------------------------------------------
+# fused training step: forward, MSE, backward, (all-reduce), Adam  -  unipose.py:107-124
+# ----------------------------------------------------------------------------------------------------
+class TrainStep:
+    """One optimisation step of the reference's training loop on flat fp32 buffers.
+
+    `step(input, target)` = forward (train-mode BN, dropout) -> nn.MSELoss (up_mse_fwd_bwd) -> backward ->
+    ONE NCCL all-reduce of the flat gradient buffer when torch.distributed is initialised (data parallel over the
+    batch, BatchNorm stays per-GPU as in the reference) -> Adam (up_adam_step) on the flat parameter buffer.
+    Parameters that the reference leaves without gradient (decoder.conv2 / bn2) are never touched."""
+
+    def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
+        self.plan: Optional[TrainPlan] = None
+        self.t = 0
+
+    def _setup(self, x: torch.Tensor) -> None:
+        m = self.model
+        self.plan = build_image_train_plan(m, tuple(x.shape), x.device, m._precision(), flat=True)
+        p = self.plan
+        self.flat_g = p.flat_g
+        self.flat_p = torch.empty_like(self.flat_g)
+        self.exp_avg = torch.zeros_like(self.flat_p)
+        self.exp_avg_sq = torch.zeros_like(self.flat_p)
+        off = 0
+        with torch.no_grad():
+            for q in p.params:        # the parameters become views of the flat buffer (state_dict() still works)
+                nq = q.numel()
+                self.flat_p[off:off + nq].copy_(q.detach().reshape(-1))
+                q.data = self.flat_p[off:off + nq].view(q.shape)
+                off += nq
+        self.loss = torch.zeros(1, dtype=torch.float32, device=x.device)
+        self.loss_scratch = torch.zeros(1, dtype=torch.float64, device=x.device)
+
+    def step(self, x: torch.Tensor, target: torch.Tensor, lr: Optional[float] = None) -> torch.Tensor:
+        import torch.distributed as dist
+        if self.plan is None:
+            self._setup(x)
+        p = self.plan
+        heat = p.run_forward(x)
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        ops._lib.call("up_mse_fwd_bwd", ops._ptr(heat), ops._ptr(target), ops._ptr(self.loss), ops._ptr(p.dheat),
+                      ops._ptr(self.loss_scratch), heat.numel(), 1.0 / world, ops._stream())
+        for op in p.bwd:
+            op()
+        if world > 1:
+            dist.all_reduce(self.flat_g)       # gradients were pre-scaled by 1/world in the MSE kernel
+        self.t += 1
+        ops._lib.call("up_adam_step", ops._ptr(self.flat_p), ops._ptr(self.flat_g), ops._ptr(self.exp_avg),
+                      ops._ptr(self.exp_avg_sq), self.flat_p.numel(), float(self.lr if lr is None else lr),
+                      float(self.betas[0]), float(self.betas[1]), float(self.eps), self.t, ops._stream())
+        return self.loss
