@@ -211,7 +211,7 @@ class TrainPlan:
             if r["mask"] is not None:
                 tmp = self.act(n, ho, wo, cout)
                 mask = r["mask"]
-                self.bwd.append(lambda: ops.ew(dy, tmp, m=mask, op=1))
+                self.bwd.append(lambda dy=dy, tmp=tmp, mask=mask: ops.ew(dy, tmp, m=mask, op=1))
                 dy = as_view(tmp)
             if bn is None:
                 dz = dy          # plain conv: dz is the incoming gradient itself
