@@ -1,0 +1,33 @@
+"""Time the fused training step (config 3 per-GPU shape: MPII 384x384, batch 32, bf16) on one GPU."""
+import argparse, os, sys, time, warnings
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from unipose_b200 import synth, train
+from unipose_b200.model.unipose import unipose
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=32)
+ap.add_argument("--size", type=int, default=384)
+ap.add_argument("--precision", default="bf16")
+ap.add_argument("--steps", type=int, default=5)
+a = ap.parse_args()
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    m = unipose(dataset="MPII", num_classes=16, precision=a.precision)
+synth.trained_like_init_(m, 0)
+m = m.cuda().train()
+x = synth.mpii_like_input(a.batch, a.size, a.size).cuda()
+t = torch.rand(a.batch, 17, a.size // 8, a.size // 8, device="cuda")
+ts = train.TrainStep(m)
+for _ in range(2):
+    loss = ts.step(x, t)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.steps):
+    loss = ts.step(x, t)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.steps
+print("train step: %.2f ms  -> %.1f frames/s  (loss %.5f, fwd ops %d, bwd ops %d, mem %.1f GB)" % (
+    ms, a.batch / ms * 1e3, float(loss), len(ts.plan.fwd), len(ts.plan.bwd), torch.cuda.max_memory_allocated() / 2**30))

@@ -543,18 +543,17 @@ class TrainStep:
         self.loss_scratch = torch.zeros(1, dtype=torch.float64, device=x.device)
 
     def step(self, x: torch.Tensor, target: torch.Tensor, lr: Optional[float] = None) -> torch.Tensor:
-        import torch.distributed as dist
+        from . import parallel
         if self.plan is None:
             self._setup(x)
         p = self.plan
         heat = p.run_forward(x)
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        world = parallel.world()[1]
         ops._lib.call("up_mse_fwd_bwd", ops._ptr(heat), ops._ptr(target), ops._ptr(self.loss), ops._ptr(p.dheat),
                       ops._ptr(self.loss_scratch), heat.numel(), 1.0 / world, ops._stream())
         for op in p.bwd:
             op()
-        if world > 1:
-            dist.all_reduce(self.flat_g)       # gradients were pre-scaled by 1/world in the MSE kernel
+        parallel.allreduce_sum_(self.flat_g)   # gradients were pre-scaled by 1/world in the MSE kernel
         self.t += 1
         ops._lib.call("up_adam_step", ops._ptr(self.flat_p), ops._ptr(self.flat_g), ops._ptr(self.exp_avg),
                       ops._ptr(self.exp_avg_sq), self.flat_p.numel(), float(self.lr if lr is None else lr),
