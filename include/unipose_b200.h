@@ -45,7 +45,9 @@ typedef enum UpDtype {
 
 enum {
   UP_FLAG_RELU = 1,          /* y = max(y, 0) after scale/shift(/residual) */
-  UP_FLAG_RESIDUAL = 2,      /* y += residual (same NHWC geometry as y) before ReLU */
+  UP_FLAG_RESIDUAL = 2,      /* the residual tile (same NHWC geometry as y) is accumulated INSIDE the tensor-core
+                                pipeline (identity MMA into the fp32 accumulator): y = act(scale*(conv + res) + shift).
+                                Callers fold a BatchNorm scale into the weights and pass scale = 1. */
   UP_FLAG_OUT_NCHW_F32 = 4,  /* write fp32 NCHW [n, cout_valid, ho, wo] instead of 16-bit NHWC */
   UP_FLAG_STATS = 8          /* also accumulate per-channel sum / sum-of-squares of the stored output
                                 (train-mode BatchNorm statistics) into stats[2*cout] with atomics */

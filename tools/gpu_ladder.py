@@ -67,8 +67,8 @@ def run_case(idx: int) -> dict:
     if c.get("ident"):
         scale.fill_(1.0)
         shift.zero_()
-    if c.get("bias"):
-        scale.fill_(1.0)
+    if c.get("bias") or c.get("residual"):
+        scale.fill_(1.0)   # with a residual the add happens before scale/shift: BN scale is folded into the weights
 
     # ---- device operands ----
     if groups > 1:

@@ -51,6 +51,8 @@ struct ConvKParams {
   int cout;
   int nterms;
   int stages, nbuf;
+  int res_terms;   // residual k-blocks per 64-channel group (0 = none, 1, or 2 in split mode)
+  uint32_t idesc_res;
   uint32_t a_bytes, b_bytes, buf_bytes;
   uint32_t idesc;
   uint32_t tmem_cols;
@@ -117,7 +119,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
   const uint32_t staging = smem_base + p.stages * stage_bytes;
-  const uint32_t bars = staging + p.nbuf * p.buf_bytes;
+  const uint32_t ident = staging + p.nbuf * p.buf_bytes;  // 64x64 identity B tile (residual add as an MMA), 8 KB
+  const uint32_t bars = ident + (p.res_terms ? 8192u : 0u);
   // barriers (8 bytes each): full[8] empty[8] tfull[2] tempty[2] avail[4] ready[4]; then the TMEM base slot
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
@@ -156,6 +159,23 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 2) {
     tmem_alloc(tmem_slot, p.tmem_cols);
   }
+  if (p.res_terms) {
+    // K-major, 128B-swizzled identity: row n holds a single 1.0 at k = n (16-byte chunk n/8 lands at (n/8)^(n&7))
+    const uint32_t one = p.fmt == 1 ? 0x3F80u : 0x3C00u;
+    for (uint32_t i = threadIdx.x; i < 8192u / 16u; i += blockDim.x) {
+      const uint32_t n = i >> 3, chunk = i & 7u;
+      const uint32_t src_chunk = chunk ^ (n & 7u);  // logical chunk stored at this physical position
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      if (src_chunk == (n >> 3)) {
+        const uint32_t e = n & 7u;
+        w[e >> 1] = one << ((e & 1u) * 16u);
+      }
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ident + i * 16u), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                   "r"(w[3])
+                   : "memory");
+    }
+    fence_proxy_async_smem();
+  }
   tcgen05_before_thread_sync();
   __syncthreads();
   tcgen05_after_thread_sync();
@@ -171,11 +191,15 @@ __global__ void __launch_bounds__(kThreads, 1)
       tap_range(p, p.taps_h, p.pad_h, t.h0, p.bh, p.Hq, kh_lo, kh_hi);
       tap_range(p, p.taps_w, p.pad_w, t.w0, p.bw, p.Wq, kw_lo, kw_hi);
       const int nw = kw_hi - kw_lo + 1;
-      const int nkb = (kh_hi - kh_lo + 1) * nw * p.chunks * p.nterms;
+      const int nkb_conv = (kh_hi - kh_lo + 1) * nw * p.chunks * p.nterms;
+      const int groups = p.block_n >> 6;
+      const int nkb = nkb_conv + groups * p.res_terms;   // + residual tiles fed through the MMA pipe
       for (int i0 = 0; i0 < nkb; i0 += 32) {
         // phase 1 (all lanes in parallel): coordinates of k-block i0 + lane
         const int i = i0 + lane;
         const bool active = i < nkb;
+        const bool is_res = i >= nkb_conv;
+        const int ri = i - nkb_conv;                       // residual k-block: group ri / res_terms, plane ri % res_terms
         const int term = i % p.nterms;
         const int j = i / p.nterms;
         const int chunk = j % p.chunks;
@@ -198,13 +222,23 @@ __global__ void __launch_bounds__(kThreads, 1)
         // phase 2: lane 0 issues the k-blocks strictly in order (the slot / phase protocol of the smem ring
         // assumes in-order production), fetching each k-block's coordinates from the lane that computed them
         const int cnt = min(32, nkb - i0);
-        const int sel = (term == 1) ? 1 : 0;
+        int sel = (term == 1) ? 1 : 0;
+        int cc_c = c, cc_w = t.w0 + ow, cc_p = ph, cc_h = t.h0 + oh, cc_n = n;
+        if (is_res) {
+          const int rg = p.res_terms ? ri / p.res_terms : 0;
+          sel = 2 + (p.res_terms ? ri % p.res_terms : 0);  // 2 = residual hi plane, 3 = residual lo plane
+          cc_c = p.r_coff + t.nt * p.block_n + rg * 64;
+          cc_w = t.w0;
+          cc_p = 0;
+          cc_h = t.h0;
+          cc_n = t.n0;
+        }
         for (int l = 0; l < cnt; ++l) {
-          const int c_l = __shfl_sync(0xffffffffu, c, l);
-          const int w_l = __shfl_sync(0xffffffffu, t.w0 + ow, l);
-          const int ph_l = __shfl_sync(0xffffffffu, ph, l);
-          const int h_l = __shfl_sync(0xffffffffu, t.h0 + oh, l);
-          const int n_l = __shfl_sync(0xffffffffu, n, l);
+          const int c_l = __shfl_sync(0xffffffffu, cc_c, l);
+          const int w_l = __shfl_sync(0xffffffffu, cc_w, l);
+          const int ph_l = __shfl_sync(0xffffffffu, cc_p, l);
+          const int h_l = __shfl_sync(0xffffffffu, cc_h, l);
+          const int n_l = __shfl_sync(0xffffffffu, cc_n, l);
           const uint32_t s_l = __shfl_sync(0xffffffffu, s, l);
           const uint32_t par_l = __shfl_sync(0xffffffffu, phase ^ 1u, l);
           const int brow_l = __shfl_sync(0xffffffffu, brow, l);
@@ -213,9 +247,15 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (lane == 0) {
             const uint32_t dst = smem_base + s_l * stage_bytes;
             mbar_wait(empty_bar(s_l), par_l, 16000000000LL);
-            mbar_arrive_expect_tx(full_bar(s_l), stage_bytes);
-            tma_load_5d(sel_l ? &tmA1 : &tmA0, dst, full_bar(s_l), c_l, w_l, ph_l, h_l, n_l);
-            tma_load_2d(&tmB, dst + p.a_bytes, full_bar(s_l), bcol_l, brow_l);
+            if (sel_l >= 2) {
+              // residual tile [128 px x 64 ch] -> the A slot; its B operand is the resident identity tile
+              mbar_arrive_expect_tx(full_bar(s_l), p.a_bytes);
+              tma_load_5d(sel_l == 3 ? &tmR1 : &tmR0, dst, full_bar(s_l), c_l, w_l, ph_l, h_l, n_l);
+            } else {
+              mbar_arrive_expect_tx(full_bar(s_l), stage_bytes);
+              tma_load_5d(sel_l ? &tmA1 : &tmA0, dst, full_bar(s_l), c_l, w_l, ph_l, h_l, n_l);
+              tma_load_2d(&tmB, dst + p.a_bytes, full_bar(s_l), bcol_l, brow_l);
+            }
           }
         }
         (void)active;
@@ -235,12 +275,14 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint64_t adesc0 = make_smem_desc_kmajor(smem_base, sw_bytes);
     const uint64_t bdesc0 = make_smem_desc_kmajor(smem_base + p.a_bytes, sw_bytes);
     const uint32_t stage_step = stage_bytes >> 4;
+    const uint64_t identdesc = make_smem_desc_kmajor(ident, 128);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       int kh_lo, kh_hi, kw_lo, kw_hi;
       tap_range(p, p.taps_h, p.pad_h, t.h0, p.bh, p.Hq, kh_lo, kh_hi);
       tap_range(p, p.taps_w, p.pad_w, t.w0, p.bw, p.Wq, kw_lo, kw_hi);
-      const int nkb = (kh_hi - kh_lo + 1) * (kw_hi - kw_lo + 1) * p.chunks * p.nterms;
+      const int nkb_conv = (kh_hi - kh_lo + 1) * (kw_hi - kw_lo + 1) * p.chunks * p.nterms;
+      const int nkb = nkb_conv + (p.block_n >> 6) * p.res_terms;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tcgen05_after_thread_sync();
       const uint32_t tmem_d = tmem_base + acc * p.block_n;
@@ -249,11 +291,19 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_wait(full_bar(s), phase);
         tcgen05_after_thread_sync();
         const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage_step * s);
-        const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage_step * s);
-        for (int k = 0; k < kk; ++k) {
-          // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in 16-byte units
-          umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, accumulate);
-          accumulate = 1;
+        if (kb >= nkb_conv) {
+          // residual group: D[:, g*64 .. g*64+63] += R_tile x I  (exact: products with 1.0, fp32 accumulate)
+          const int rg = (kb - nkb_conv) / p.res_terms;
+          for (int k = 0; k < 4; ++k) {
+            umma_f16(tmem_d + rg * 64, adesc + 2u * k, identdesc + 2u * k, p.idesc_res, 1u);
+          }
+        } else {
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage_step * s);
+          for (int k = 0; k < kk; ++k) {
+            // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in 16-byte units
+            umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, accumulate);
+            accumulate = 1;
+          }
         }
         umma_commit(empty_bar(s));  // frees the smem slot once these MMAs have read it
         if (++s == p.stages) {
@@ -280,20 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         t = decode_tile(p, tile);
         c = t.nt * p.block_n + (q % groups) * 64;
       };
-      auto make_avail = [&](int q) {
-        const int b = q % p.nbuf;
-        if (has_res) {
-          int c;
-          TileCoord t;
-          coords(q, c, t);
-          const uint32_t dst = staging + b * p.buf_bytes;
-          mbar_arrive_expect_tx(avail_bar(b), p.buf_bytes);
-          tma_load_5d(&tmR0, dst, avail_bar(b), p.r_coff + c, t.w0, 0, t.h0, t.n0);
-          if (p.split) tma_load_5d(&tmR1, dst + kPlaneBytes, avail_bar(b), p.r_coff + c, t.w0, 0, t.h0, t.n0);
-        } else {
-          mbar_arrive(avail_bar(b));
-        }
-      };
+      auto make_avail = [&](int q) { mbar_arrive(avail_bar(q % p.nbuf)); };
       for (int q = 0; q < look && q < total_q; ++q) make_avail(q);
       for (int q = 0; q < total_q; ++q) {
         if (q + look < total_q) {
@@ -372,37 +409,12 @@ __global__ void __launch_bounds__(kThreads, 1)
             v[4 * j4 + 2] = fmaf(__uint_as_float(r[4 * j4 + 2]), s4.z, h4.z);
             v[4 * j4 + 3] = fmaf(__uint_as_float(r[4 * j4 + 3]), s4.w, h4.w);
           }
-          // the staging buffer becomes ours (previous store drained; residual tile landed if any)
+          // the staging buffer becomes ours (its previous TMA store has drained)
           mbar_wait(avail_bar(b), (q / p.nbuf) & 1u);
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             const uint32_t chunk = static_cast<uint32_t>(half * 4 + c4) ^ (static_cast<uint32_t>(row) & 7u);
             const uint32_t addr = buf + rowoff + (chunk << 4);
-            if (has_res) {
-              uint32_t u0, u1, u2, u3;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3)
-                           : "r"(addr)
-                           : "memory");
-              const uint32_t uw[4] = {u0, u1, u2, u3};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[8 * c4 + 2 * e + 0] += cvt16_to_f32_rt(static_cast<uint16_t>(uw[e] & 0xFFFFu), fmt);
-                v[8 * c4 + 2 * e + 1] += cvt16_to_f32_rt(static_cast<uint16_t>(uw[e] >> 16), fmt);
-              }
-              if (p.split) {
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3)
-                             : "r"(addr + kPlaneBytes)
-                             : "memory");
-                const uint32_t lw[4] = {u0, u1, u2, u3};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  v[8 * c4 + 2 * e + 0] += cvt16_to_f32<1>(static_cast<uint16_t>(lw[e] & 0xFFFFu));
-                  v[8 * c4 + 2 * e + 1] += cvt16_to_f32<1>(static_cast<uint16_t>(lw[e] >> 16));
-                }
-              }
-            }
             if (p.flags & UP_FLAG_RELU) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[8 * c4 + e] = fmaxf(v[8 * c4 + e], 0.f);
@@ -584,12 +596,16 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   p.a_bytes = kTileM * ck * 2;
   p.b_bytes = block_n * ck * 2;
   p.buf_bytes = split ? 2 * kPlaneBytes : kPlaneBytes;
-  p.nbuf = nchw ? 0 : (split ? 2 : (has_res ? 3 : 2));
+  p.nbuf = nchw ? 0 : 2;
+  p.res_terms = has_res ? (split ? 2 : 1) : 0;
+  p.idesc_res = make_idesc_f16(static_cast<uint32_t>(fmt), kTileM, 64u);
+  if (has_res) UP_CHECK_ARG(ck == 64, "up_conv2d_fwd: residual needs cin to be a multiple of 64");
   if (const char* e = getenv("UP_DEBUG_NBUF")) {
     const int v = atoi(e);
     if (!nchw && v >= 2 && v <= kMaxBufs) p.nbuf = v;
   }
-  const size_t fixed = 1024 + 8 * (2 * kMaxStages + 4 + 2 * kMaxBufs) + 16 + static_cast<size_t>(p.nbuf) * p.buf_bytes;
+  const size_t fixed = 1024 + 8 * (2 * kMaxStages + 4 + 2 * kMaxBufs) + 16 + static_cast<size_t>(p.nbuf) * p.buf_bytes +
+                       (has_res ? 8192 : 0);
   int stages = static_cast<int>((g_max_smem - fixed) / (p.a_bytes + p.b_bytes));
   if (stages > kMaxStages) stages = kMaxStages;
   if (const char* e = getenv("UP_DEBUG_STAGES")) {

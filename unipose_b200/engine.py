@@ -86,25 +86,32 @@ class Builder:
         shift = torch.zeros(cout, dtype=torch.float32, device=self.device)
         pc = PackedConv(wbuf, scale, shift, kh, kw, cout, cin, co_r, ci_r, self.mode)
 
+        fold_scale = torch.empty(cout, dtype=torch.float32, device=self.device) if bn is not None else None
+
         def fill():
             w = conv.weight.detach()
             if weight_fn is not None:
                 w = weight_fn(w)
-            w = w.float().contiguous()
-            ops._lib.call("up_pack_conv_weight", ops._ptr(w), ops._ptr(wbuf), co_r, ci_r, kh, kw, cout, cin, self.mode,
-                          kh * kw * cout * cin, ops._stream())
+            w = w.float()
+            scale.zero_()
+            scale[:co_r] = 1.0
             if bn is not None:
+                # eval-mode BatchNorm: the per-channel scale is folded into the filter (w' = w * gamma/sqrt(var+eps)),
+                # the shift stays in the epilogue.  The residual of a bottleneck is added inside the tensor-core
+                # pipeline BEFORE the epilogue, so the epilogue itself must not scale.
                 ops._lib.call("up_bn_fold", ops._ptr(bn.weight.detach().float().contiguous()),
                               ops._ptr(bn.bias.detach().float().contiguous()),
                               ops._ptr(bn.running_mean.float().contiguous()),
-                              ops._ptr(bn.running_var.float().contiguous()), float(bn.eps), ops._ptr(scale),
+                              ops._ptr(bn.running_var.float().contiguous()), float(bn.eps), ops._ptr(fold_scale),
                               ops._ptr(shift), co_r, cout, ops._stream())
+                w = w * fold_scale[:co_r].view(-1, 1, 1, 1)
             else:
-                scale.zero_()
-                scale[:co_r] = 1.0
                 shift.zero_()
                 if conv.bias is not None:
                     shift[:co_r] = conv.bias.detach().float()
+            w = w.contiguous()
+            ops._lib.call("up_pack_conv_weight", ops._ptr(w), ops._ptr(wbuf), co_r, ci_r, kh, kw, cout, cin, self.mode,
+                          kh * kw * cout * cin, ops._stream())
 
         srcs = [conv.weight] + ([conv.bias] if conv.bias is not None else [])
         if bn is not None:
