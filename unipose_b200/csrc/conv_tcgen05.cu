@@ -148,11 +148,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiThreads);
+      mbar_init(tempty_bar(a), kEpiThreads / 32);
     }
     for (int b = 0; b < kMaxBufs; ++b) {
       mbar_init(avail_bar(b), 1);
-      mbar_init(ready_bar(b), kEpiThreads);
+      mbar_init(ready_bar(b), kEpiThreads / 32);
     }
     fence_barrier_init();
   }
@@ -180,6 +180,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tcgen05_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, identity tile) overlapped the
+  // tail of the previous kernel; from here on we read its output.  Let our own dependents get scheduled early.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ===================== TMA producer (32 lanes, lane i owns k-blocks i, i+32, ...) =====================
@@ -324,19 +328,18 @@ __global__ void __launch_bounds__(kThreads, 1)
       int my_tiles = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) ++my_tiles;
       const int total_q = my_tiles * groups;
-      const int look = p.nbuf - 2;
       auto coords = [&](int q, int& c, TileCoord& t) {
         const int tile = blockIdx.x + (q / groups) * gridDim.x;
         t = decode_tile(p, tile);
         c = t.nt * p.block_n + (q % groups) * 64;
       };
-      auto make_avail = [&](int q) { mbar_arrive(avail_bar(q % p.nbuf)); };
-      for (int q = 0; q < look && q < total_q; ++q) make_avail(q);
+      // Two staging buffers, one group of look-ahead: while the epilogue warps fill buffer q%2, this thread waits for
+      // the TMA store of group q-1 to finish READING the other buffer and hands it out for group q+1.
+      mbar_arrive(avail_bar(0));
       for (int q = 0; q < total_q; ++q) {
-        if (q + look < total_q) {
-          // buffer (q+look) % nbuf was last used by group q-2, whose store was issued two iterations ago
-          if (q + look >= p.nbuf) tma_store_wait_read<1>();
-          make_avail(q + look);
+        if (q + 1 < total_q) {
+          if (q >= 1) tma_store_wait_read<0>();
+          mbar_arrive(avail_bar((q + 1) % p.nbuf));
         }
         const int b = q % p.nbuf;
         mbar_wait(ready_bar(b), (q / p.nbuf) & 1u);
@@ -447,12 +450,14 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           }
           fence_proxy_async_smem();   // make the generic-proxy writes visible to the TMA store
-          mbar_arrive(ready_bar(b));  // 256 arrivals -> the DMA thread stores the group
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ready_bar(b));  // one arrival per warp (8) -> the DMA thread stores the group
         }
       }
       // all TMEM reads of this accumulator are done -> hand it back to the MMA issuer
       tcgen05_before_thread_sync();
-      mbar_arrive(tempty_bar(acc));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -687,8 +692,22 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   const long long total_tiles = static_cast<long long>(m_tiles) * p.n_tiles;
   const int grid = static_cast<int>(total_tiles < g_sm_count ? total_tiles : g_sm_count);
   const size_t smem = fixed + static_cast<size_t>(stages) * (p.a_bytes + p.b_bytes);
-  conv_tcgen05_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA0, tmA1, tmB, tmY0, tmY1, tmR0,
-                                                                                    tmR1, p);
-  UP_CHECK_LAUNCH("conv_tcgen05_kernel launch");
+  static const bool use_pdl = []() {
+    const char* e = getenv("UP_PDL");
+    return !(e && e[0] == '0');
+  }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  rc = check_cuda(cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel, tmA0, tmA1, tmB, tmY0, tmY1, tmR0, tmR1, p),
+                  "conv_tcgen05_kernel launch");
+  if (rc) return rc;
   return 0;
 }
