@@ -51,6 +51,7 @@ struct ConvKParams {
   int cout;
   int nterms;
   int stages, nbuf;
+  int cluster;     // CTAs per cluster (1, 2 or 4): they share one weight tile per k-block via TMA multicast
   int res_terms;   // residual k-blocks per 64-channel group (0 = none, 1, or 2 in split mode)
   uint32_t idesc_res;
   uint32_t a_bytes, b_bytes, buf_bytes;
@@ -68,14 +69,16 @@ struct TileCoord {
   int n0, h0, w0, nt;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile) {
+// Work item -> tile.  The CTAs of a cluster take the SAME (nt, tw, th) and consecutive image groups tn, so they
+// walk identical k-block sequences (same in-bounds taps, same weight tiles) - the precondition for multicast.
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int work, int crank) {
   TileCoord t;
-  t.nt = tile % p.n_tiles;
-  int mt = tile / p.n_tiles;
+  t.nt = work % p.n_tiles;
+  int mt = work / p.n_tiles;
   int tw = mt % p.tiles_w;
   mt /= p.tiles_w;
   int th = mt % p.tiles_h;
-  int tn = mt / p.tiles_h;
+  int tn = (mt / p.tiles_h) * p.cluster + crank;
   t.n0 = tn * p.bn;
   t.h0 = th * p.bh;
   t.w0 = tw * p.bw;
@@ -134,7 +137,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+  uint32_t crank = 0;
+  if (p.cluster > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int first_work = blockIdx.x / p.cluster;
+  const int work_step = gridDim.x / p.cluster;
+  const int total_tiles = (p.tiles_n / p.cluster) * p.tiles_h * p.tiles_w * p.n_tiles;
   const bool nchw = (p.flags & UP_FLAG_OUT_NCHW_F32) != 0;
   const bool has_res = (p.flags & UP_FLAG_RESIDUAL) != 0;
 
@@ -144,7 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (!nchw) tma_prefetch_desc(&tmY0);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), p.cluster);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -178,6 +185,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   tcgen05_before_thread_sync();
   __syncthreads();
+  if (p.cluster > 1) {
+    // peers multicast into our smem and arrive on our mbarriers: nobody may start before all are initialised
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   tcgen05_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot_ptr;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, identity tile) overlapped the
@@ -189,8 +201,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ===================== TMA producer (32 lanes, lane i owns k-blocks i, i+32, ...) =====================
     uint32_t kb_base = 0;
     const int taps = p.taps_h * p.taps_w;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int tile = first_work; tile < total_tiles; tile += work_step) {
+      const TileCoord t = decode_tile(p, tile, crank);
       int kh_lo, kh_hi, kw_lo, kw_hi;
       tap_range(p, p.taps_h, p.pad_h, t.h0, p.bh, p.Hq, kh_lo, kh_hi);
       tap_range(p, p.taps_w, p.pad_w, t.w0, p.bw, p.Wq, kw_lo, kw_hi);
@@ -258,7 +270,15 @@ __global__ void __launch_bounds__(kThreads, 1)
             } else {
               mbar_arrive_expect_tx(full_bar(s_l), stage_bytes);
               tma_load_5d(sel_l ? &tmA1 : &tmA0, dst, full_bar(s_l), c_l, w_l, ph_l, h_l, n_l);
-              tma_load_2d(&tmB, dst + p.a_bytes, full_bar(s_l), bcol_l, brow_l);
+              if (p.cluster > 1) {
+                // each CTA fetches 1/cluster of the weight rows and multicasts them to every CTA of the cluster
+                const uint32_t sub_rows = static_cast<uint32_t>(p.block_n / p.cluster);
+                tma_load_2d_mc(&tmB, dst + p.a_bytes + crank * sub_rows * static_cast<uint32_t>(p.ck) * 2u, full_bar(s_l),
+                               bcol_l, brow_l + static_cast<int>(crank * sub_rows),
+                               static_cast<uint16_t>((1u << p.cluster) - 1u));
+              } else {
+                tma_load_2d(&tmB, dst + p.a_bytes, full_bar(s_l), bcol_l, brow_l);
+              }
             }
           }
         }
@@ -280,8 +300,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint64_t bdesc0 = make_smem_desc_kmajor(smem_base + p.a_bytes, sw_bytes);
     const uint32_t stage_step = stage_bytes >> 4;
     const uint64_t identdesc = make_smem_desc_kmajor(ident, 128);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int tile = first_work; tile < total_tiles; tile += work_step) {
+      const TileCoord t = decode_tile(p, tile, crank);
       int kh_lo, kh_hi, kw_lo, kw_hi;
       tap_range(p, p.taps_h, p.pad_h, t.h0, p.bh, p.Hq, kh_lo, kh_hi);
       tap_range(p, p.taps_w, p.pad_w, t.w0, p.bw, p.Wq, kw_lo, kw_hi);
@@ -309,7 +329,9 @@ __global__ void __launch_bounds__(kThreads, 1)
             accumulate = 1;
           }
         }
-        umma_commit(empty_bar(s));  // frees the smem slot once these MMAs have read it
+        // frees the smem slot once these MMAs have read it - in every CTA of the cluster (peers multicast into it)
+        if (p.cluster > 1) umma_commit_mc(empty_bar(s), static_cast<uint16_t>((1u << p.cluster) - 1u));
+        else umma_commit(empty_bar(s));
         if (++s == p.stages) {
           s = 0;
           phase ^= 1u;
@@ -326,11 +348,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (!nchw) {
       const int groups = p.block_n / 64;
       int my_tiles = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) ++my_tiles;
+      for (int tile = first_work; tile < total_tiles; tile += work_step) ++my_tiles;
       const int total_q = my_tiles * groups;
       auto coords = [&](int q, int& c, TileCoord& t) {
-        const int tile = blockIdx.x + (q / groups) * gridDim.x;
-        t = decode_tile(p, tile);
+        const int tile = first_work + (q / groups) * work_step;
+        t = decode_tile(p, tile, crank);
         c = t.nt * p.block_n + (q % groups) * 64;
       };
       // Two staging buffers, one group of look-ahead: while the epilogue warps fill buffer q%2, this thread waits for
@@ -365,8 +387,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint32_t q = 0;  // staging-buffer sequence number (shared convention with the DMA thread)
     const int bhw = p.bh * p.bw;
     const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int tile = first_work; tile < total_tiles; tile += work_step) {
+      const TileCoord t = decode_tile(p, tile, crank);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_after_thread_sync();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.block_n;
@@ -467,6 +489,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   tcgen05_before_thread_sync();
   __syncthreads();
+  if (p.cluster > 1) {
+    // a CTA must not exit while a peer can still multicast into its smem or arrive on its barriers
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   if (warp == 2) {
     tcgen05_after_thread_sync();
     tmem_dealloc(tmem_base, p.tmem_cols);
@@ -603,6 +630,19 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   p.buf_bytes = split ? 2 * kPlaneBytes : kPlaneBytes;
   p.nbuf = nchw ? 0 : 2;
   p.res_terms = has_res ? (split ? 2 : 1) : 0;
+  // cluster along the image-group direction: largest of 4 / 2 that divides tiles_n and leaves >= 8 weight rows per CTA
+  p.cluster = 1;
+  {
+    int want = 2;   // 148 SMs pack perfectly into 74 pairs; clusters of 4 strand SMs (GPC sizes 16/18/20)
+    if (const char* e = getenv("UP_CLUSTER")) want = atoi(e);
+    for (int c = 4; c >= 2; c /= 2) {
+      if (c <= want && p.tiles_n % c == 0 && (block_n / c) % 8 == 0 &&
+          static_cast<long long>(m_tiles) * (d->cout / block_n) >= 2LL * c) {
+        p.cluster = c;
+        break;
+      }
+    }
+  }
   p.idesc_res = make_idesc_f16(static_cast<uint32_t>(fmt), kTileM, 64u);
   if (has_res) UP_CHECK_ARG(ck == 64, "up_conv2d_fwd: residual needs cin to be a multiple of 64");
   if (const char* e = getenv("UP_DEBUG_NBUF")) {
@@ -654,7 +694,7 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
     const int taps = d->kh * d->kw;
     const uint64_t dims[2] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(split ? 2 : 1) * taps * d->cout};
     const uint64_t st[1] = {static_cast<uint64_t>(d->cin) * 2};
-    const uint32_t box[2] = {static_cast<uint32_t>(ck), static_cast<uint32_t>(block_n)};
+    const uint32_t box[2] = {static_cast<uint32_t>(ck), static_cast<uint32_t>(block_n / p.cluster)};
     if (split) {
       UP_CHECK_ARG(d->w_plane_stride == static_cast<int64_t>(taps) * d->cout * d->cin,
                    "up_conv2d_fwd: split weights must have contiguous planes (w_plane_stride = taps*cout*cin)");
@@ -689,9 +729,35 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
     }
   }
 
-  const long long total_tiles = static_cast<long long>(m_tiles) * p.n_tiles;
-  const int grid = static_cast<int>(total_tiles < g_sm_count ? total_tiles : g_sm_count);
+  const long long total_work = static_cast<long long>(m_tiles / p.cluster) * p.n_tiles;
   const size_t smem = fixed + static_cast<size_t>(stages) * (p.a_bytes + p.b_bytes);
+  int max_clusters = g_sm_count / p.cluster;
+  if (p.cluster > 1) {
+    // persistent kernel: never launch more clusters than can be co-resident
+    static int cached[5] = {0, 0, 0, 0, 0};
+    if (cached[p.cluster] == 0) {
+      cudaLaunchConfig_t occ{};
+      occ.gridDim = dim3(g_sm_count / p.cluster * p.cluster);
+      occ.blockDim = dim3(kThreads);
+      occ.dynamicSmemBytes = g_max_smem;
+      cudaLaunchAttribute oa[1];
+      oa[0].id = cudaLaunchAttributeClusterDimension;
+      oa[0].val.clusterDim.x = p.cluster;
+      oa[0].val.clusterDim.y = 1;
+      oa[0].val.clusterDim.z = 1;
+      occ.attrs = oa;
+      occ.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, conv_tcgen05_kernel, &occ) == cudaSuccess && nc > 0) {
+        cached[p.cluster] = nc;
+      } else {
+        (void)cudaGetLastError();
+        cached[p.cluster] = g_sm_count / p.cluster;
+      }
+    }
+    if (cached[p.cluster] < max_clusters) max_clusters = cached[p.cluster];
+  }
+  const int grid = static_cast<int>(total_work < max_clusters ? total_work : max_clusters) * p.cluster;
   static const bool use_pdl = []() {
     const char* e = getenv("UP_PDL");
     return !(e && e[0] == '0');
@@ -701,11 +767,22 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = static_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (p.cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = p.cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   rc = check_cuda(cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel, tmA0, tmA1, tmB, tmY0, tmY1, tmR0, tmR1, p),
                   "conv_tcgen05_kernel launch");
   if (rc) return rc;

@@ -89,6 +89,16 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint32_t dst, 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// Multicast variant: the box lands at the same smem offset (and signals the same-offset mbarrier) in every CTA of
+// the cluster whose bit is set in `mask`.
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* m, uint32_t dst, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint32_t dst, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
   asm volatile(
@@ -141,6 +151,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 // Make the mbarrier track completion of all tcgen05 async ops previously issued by this thread.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// Same, arriving on the same-offset mbarrier of every CTA in `mask`.
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   bar),
+               "h"(mask)
+               : "memory");
 }
 
 // TMEM -> registers: this thread's lane (32x32b shape: lane = 32*(warp%4) + laneid), 32 consecutive columns.
