@@ -51,6 +51,8 @@ struct ConvKParams {
   int cout;
   int nterms;
   int stages, nbuf;
+  int pair;        // 1: the two CTAs of a cluster issue ONE tcgen05.mma.cta_group::2 (M = 256) per k-step; each holds
+                   //    its own 128 activation rows and HALF of the weight tile -> half the smem fill + operand reads
   int cluster;     // CTAs per cluster (1, 2 or 4): they share one weight tile per k-block via TMA multicast
   int res_terms;   // residual k-blocks per 64-channel group (0 = none, 1, or 2 in split mode)
   uint32_t idesc_res;
@@ -150,12 +152,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     tma_prefetch_desc(&tmB);
     if (!nchw) tma_prefetch_desc(&tmY0);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), p.cluster);
+      mbar_init(full_bar(s), p.pair ? 2 : 1);                 // pair: both CTAs' producers arrive on the leader's
+      mbar_init(empty_bar(s), p.pair ? 1 : p.cluster);        // pair: one multicast commit from the leader's issuer
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiThreads / 32);
+      mbar_init(tempty_bar(a), (kEpiThreads / 32) * (p.pair ? 2 : 1));   // pair: epilogue warps of both CTAs
     }
     for (int b = 0; b < kMaxBufs; ++b) {
       mbar_init(avail_bar(b), 1);
@@ -164,7 +166,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, p.tmem_cols);
+    if (p.pair) tmem_alloc_2cta(tmem_slot, p.tmem_cols);
+    else tmem_alloc(tmem_slot, p.tmem_cols);
   }
   if (p.res_terms) {
     // K-major, 128B-swizzled identity: row n holds a single 1.0 at k = n (16-byte chunk n/8 lands at (n/8)^(n&7))
@@ -173,8 +176,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t n = i >> 3, chunk = i & 7u;
       const uint32_t src_chunk = chunk ^ (n & 7u);  // logical chunk stored at this physical position
       uint32_t w[4] = {0u, 0u, 0u, 0u};
-      if (src_chunk == (n >> 3)) {
-        const uint32_t e = n & 7u;
+      // pair mode: this CTA supplies rows [32*rank, 32*rank+32) of the 64x64 identity as its half of the B operand
+      const uint32_t gn = p.pair ? (n + 32u * crank) : n;
+      if ((p.pair == 0 || n < 32u) && src_chunk == (gn >> 3)) {
+        const uint32_t e = gn & 7u;
         w[e >> 1] = one << ((e & 1u) * 16u);
       }
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ident + i * 16u), "r"(w[0]), "r"(w[1]), "r"(w[2]),
@@ -263,7 +268,19 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (lane == 0) {
             const uint32_t dst = smem_base + s_l * stage_bytes;
             mbar_wait(empty_bar(s_l), par_l, 16000000000LL);
-            if (sel_l >= 2) {
+            if (p.pair) {
+              // CTA pair: bytes of BOTH CTAs are credited to the leader's barrier (count 2: one arrive per producer)
+              const uint32_t mine = (sel_l >= 2) ? p.a_bytes : (p.a_bytes + p.b_bytes);   // b_bytes = this CTA's half
+              if (crank == 0) mbar_arrive_expect_tx(full_bar(s_l), 2u * mine);
+              else mbar_arrive_remote(full_bar(s_l), 0u);
+              if (sel_l >= 2) {
+                tma_load_5d_2cta(sel_l == 3 ? &tmR1 : &tmR0, dst, full_bar(s_l), c_l, w_l, ph_l, h_l, n_l);
+              } else {
+                tma_load_5d_2cta(sel_l ? &tmA1 : &tmA0, dst, full_bar(s_l), c_l, w_l, ph_l, h_l, n_l);
+                tma_load_2d_2cta(&tmB, dst + p.a_bytes, full_bar(s_l), bcol_l,
+                                 brow_l + static_cast<int>(crank) * (p.block_n >> 1));
+              }
+            } else if (sel_l >= 2) {
               // residual tile [128 px x 64 ch] -> the A slot; its B operand is the resident identity tile
               mbar_arrive_expect_tx(full_bar(s_l), p.a_bytes);
               tma_load_5d(sel_l == 3 ? &tmR1 : &tmR0, dst, full_bar(s_l), c_l, w_l, ph_l, h_l, n_l);
@@ -288,8 +305,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       kb_base += nkb;
     }
-  } else if (threadIdx.x == 32) {
-    // ===================== MMA issuer =====================
+  } else if (threadIdx.x == 32 && (p.pair == 0 || crank == 0)) {
+    // ===================== MMA issuer (pair mode: leader CTA only) =====================
     int s = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -319,25 +336,29 @@ __global__ void __launch_bounds__(kThreads, 1)
           // residual group: D[:, g*64 .. g*64+63] += R_tile x I  (exact: products with 1.0, fp32 accumulate)
           const int rg = (kb - nkb_conv) / p.res_terms;
           for (int k = 0; k < 4; ++k) {
-            umma_f16(tmem_d + rg * 64, adesc + 2u * k, identdesc + 2u * k, p.idesc_res, 1u);
+            if (p.pair) umma_f16_2cta(tmem_d + rg * 64, adesc + 2u * k, identdesc + 2u * k, p.idesc_res, 1u);
+            else umma_f16(tmem_d + rg * 64, adesc + 2u * k, identdesc + 2u * k, p.idesc_res, 1u);
           }
         } else {
           const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage_step * s);
           for (int k = 0; k < kk; ++k) {
             // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in 16-byte units
-            umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, accumulate);
+            if (p.pair) umma_f16_2cta(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, accumulate);
+            else umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, accumulate);
             accumulate = 1;
           }
         }
         // frees the smem slot once these MMAs have read it - in every CTA of the cluster (peers multicast into it)
-        if (p.cluster > 1) umma_commit_mc(empty_bar(s), static_cast<uint16_t>((1u << p.cluster) - 1u));
+        if (p.pair) umma_commit_2cta_mc(empty_bar(s), 3);
+        else if (p.cluster > 1) umma_commit_mc(empty_bar(s), static_cast<uint16_t>((1u << p.cluster) - 1u));
         else umma_commit(empty_bar(s));
         if (++s == p.stages) {
           s = 0;
           phase ^= 1u;
         }
       }
-      umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+      if (p.pair) umma_commit_2cta_mc(tfull_bar(acc), 3);   // accumulator halves complete in both CTAs
+      else umma_commit(tfull_bar(acc));                     // accumulator complete -> epilogue
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -479,7 +500,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       // all TMEM reads of this accumulator are done -> hand it back to the MMA issuer
       tcgen05_before_thread_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (p.pair && crank != 0) mbar_arrive_remote(tempty_bar(acc), 0u);
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -496,7 +520,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   if (warp == 2) {
     tcgen05_after_thread_sync();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (p.pair) tmem_dealloc_2cta(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -643,7 +668,16 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
       }
     }
   }
-  p.idesc_res = make_idesc_f16(static_cast<uint32_t>(fmt), kTileM, 64u);
+  p.pair = 0;
+  if (p.cluster == 2 && block_n >= 64) {
+    const char* e = getenv("UP_PAIR");
+    p.pair = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!p.pair && !getenv("UP_CLUSTER")) p.cluster = 1;   // plain multicast clusters measured slower than independent CTAs
+  if (p.pair) p.b_bytes = static_cast<uint32_t>(block_n / 2) * ck * 2;   // each CTA of the pair holds half of the weight tile
+  p.idesc = make_idesc_f16(static_cast<uint32_t>(fmt), p.pair ? 256u : kTileM, static_cast<uint32_t>(block_n));
+  p.idesc_res = make_idesc_f16(static_cast<uint32_t>(fmt), p.pair ? 256u : kTileM, 64u);
+  p.idesc_res = 0;
   if (has_res) UP_CHECK_ARG(ck == 64, "up_conv2d_fwd: residual needs cin to be a multiple of 64");
   if (const char* e = getenv("UP_DEBUG_NBUF")) {
     const int v = atoi(e);
@@ -659,7 +693,7 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   }
   UP_CHECK_ARG(stages >= 2, "up_conv2d_fwd: not enough shared memory for 2 pipeline stages");
   p.stages = stages;
-  p.idesc = make_idesc_f16(static_cast<uint32_t>(fmt), kTileM, static_cast<uint32_t>(block_n));
+  // NOTE: filled again below once the cluster / pair decision is known
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(2 * block_n)) cols *= 2;
   p.tmem_cols = cols;
