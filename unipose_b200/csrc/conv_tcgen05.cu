@@ -114,6 +114,8 @@ __device__ __forceinline__ void tap_range(const ConvKParams& p, int taps, int pa
   }
 }
 
+// kPair selects tcgen05 cta_group::2 everywhere: PTX requires ONE cta_group per kernel, hence two instantiations.
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
     conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                         const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY0,
@@ -152,12 +154,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     tma_prefetch_desc(&tmB);
     if (!nchw) tma_prefetch_desc(&tmY0);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar(s), p.pair ? 2 : 1);                 // pair: both CTAs' producers arrive on the leader's
-      mbar_init(empty_bar(s), p.pair ? 1 : p.cluster);        // pair: one multicast commit from the leader's issuer
+      mbar_init(full_bar(s), kPair ? 2 : 1);                 // pair: both CTAs' producers arrive on the leader's
+      mbar_init(empty_bar(s), kPair ? 1 : p.cluster);        // pair: one multicast commit from the leader's issuer
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), (kEpiThreads / 32) * (p.pair ? 2 : 1));   // pair: epilogue warps of both CTAs
+      mbar_init(tempty_bar(a), (kEpiThreads / 32) * (kPair ? 2 : 1));   // pair: epilogue warps of both CTAs
     }
     for (int b = 0; b < kMaxBufs; ++b) {
       mbar_init(avail_bar(b), 1);
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     fence_barrier_init();
   }
   if (warp == 2) {
-    if (p.pair) tmem_alloc_2cta(tmem_slot, p.tmem_cols);
+    if constexpr (kPair) tmem_alloc_2cta(tmem_slot, p.tmem_cols);
     else tmem_alloc(tmem_slot, p.tmem_cols);
   }
   if (p.res_terms) {
@@ -177,8 +179,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t src_chunk = chunk ^ (n & 7u);  // logical chunk stored at this physical position
       uint32_t w[4] = {0u, 0u, 0u, 0u};
       // pair mode: this CTA supplies rows [32*rank, 32*rank+32) of the 64x64 identity as its half of the B operand
-      const uint32_t gn = p.pair ? (n + 32u * crank) : n;
-      if ((p.pair == 0 || n < 32u) && src_chunk == (gn >> 3)) {
+      const uint32_t gn = kPair ? (n + 32u * crank) : n;
+      if ((!kPair || n < 32u) && src_chunk == (gn >> 3)) {
         const uint32_t e = gn & 7u;
         w[e >> 1] = one << ((e & 1u) * 16u);
       }
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (lane == 0) {
             const uint32_t dst = smem_base + s_l * stage_bytes;
             mbar_wait(empty_bar(s_l), par_l, 16000000000LL);
-            if (p.pair) {
+            if constexpr (kPair) {
               // CTA pair: bytes of BOTH CTAs are credited to the leader's barrier (count 2: one arrive per producer)
               const uint32_t mine = (sel_l >= 2) ? p.a_bytes : (p.a_bytes + p.b_bytes);   // b_bytes = this CTA's half
               if (crank == 0) mbar_arrive_expect_tx(full_bar(s_l), 2u * mine);
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       kb_base += nkb;
     }
-  } else if (threadIdx.x == 32 && (p.pair == 0 || crank == 0)) {
+  } else if (threadIdx.x == 32 && (!kPair || crank == 0)) {
     // ===================== MMA issuer (pair mode: leader CTA only) =====================
     int s = 0;
     uint32_t phase = 0;
@@ -336,20 +338,20 @@ __global__ void __launch_bounds__(kThreads, 1)
           // residual group: D[:, g*64 .. g*64+63] += R_tile x I  (exact: products with 1.0, fp32 accumulate)
           const int rg = (kb - nkb_conv) / p.res_terms;
           for (int k = 0; k < 4; ++k) {
-            if (p.pair) umma_f16_2cta(tmem_d + rg * 64, adesc + 2u * k, identdesc + 2u * k, p.idesc_res, 1u);
+            if constexpr (kPair) umma_f16_2cta(tmem_d + rg * 64, adesc + 2u * k, identdesc + 2u * k, p.idesc_res, 1u);
             else umma_f16(tmem_d + rg * 64, adesc + 2u * k, identdesc + 2u * k, p.idesc_res, 1u);
           }
         } else {
           const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage_step * s);
           for (int k = 0; k < kk; ++k) {
             // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in 16-byte units
-            if (p.pair) umma_f16_2cta(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, accumulate);
+            if constexpr (kPair) umma_f16_2cta(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, accumulate);
             else umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, accumulate);
             accumulate = 1;
           }
         }
         // frees the smem slot once these MMAs have read it - in every CTA of the cluster (peers multicast into it)
-        if (p.pair) umma_commit_2cta_mc(empty_bar(s), 3);
+        if constexpr (kPair) umma_commit_2cta_mc(empty_bar(s), 3);
         else if (p.cluster > 1) umma_commit_mc(empty_bar(s), static_cast<uint16_t>((1u << p.cluster) - 1u));
         else umma_commit(empty_bar(s));
         if (++s == p.stages) {
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           phase ^= 1u;
         }
       }
-      if (p.pair) umma_commit_2cta_mc(tfull_bar(acc), 3);   // accumulator halves complete in both CTAs
+      if constexpr (kPair) umma_commit_2cta_mc(tfull_bar(acc), 3);   // accumulator halves complete in both CTAs
       else umma_commit(tfull_bar(acc));                     // accumulator complete -> epilogue
       if (++acc == 2) {
         acc = 0;
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       tcgen05_before_thread_sync();
       __syncwarp();
       if (lane == 0) {
-        if (p.pair && crank != 0) mbar_arrive_remote(tempty_bar(acc), 0u);
+        if (kPair && crank != 0) mbar_arrive_remote(tempty_bar(acc), 0u);
         else mbar_arrive(tempty_bar(acc));
       }
       if (++acc == 2) {
@@ -520,7 +522,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   if (warp == 2) {
     tcgen05_after_thread_sync();
-    if (p.pair) tmem_dealloc_2cta(tmem_base, p.tmem_cols);
+    if constexpr (kPair) tmem_dealloc_2cta(tmem_base, p.tmem_cols);
     else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
@@ -548,9 +550,13 @@ static int ensure_device() {
     g_max_smem = prop.sharedMemPerBlockOptin;
   }
   if (!g_attr_set) {
-    int rc = check_cuda(cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    int rc = check_cuda(cudaFuncSetAttribute(conv_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(g_max_smem)),
                         "cudaFuncSetAttribute(max dynamic smem)");
+    if (rc) return rc;
+    rc = check_cuda(cudaFuncSetAttribute(conv_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(g_max_smem)),
+                    "cudaFuncSetAttribute(max dynamic smem, pair)");
     if (rc) return rc;
     g_attr_set = true;
   }
@@ -782,7 +788,7 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
       occ.attrs = oa;
       occ.numAttrs = 1;
       int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, conv_tcgen05_kernel, &occ) == cudaSuccess && nc > 0) {
+      if (cudaOccupancyMaxActiveClusters(&nc, conv_tcgen05_kernel<true>, &occ) == cudaSuccess && nc > 0) {
         cached[p.cluster] = nc;
       } else {
         (void)cudaGetLastError();
@@ -817,7 +823,8 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  rc = check_cuda(cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel, tmA0, tmA1, tmB, tmY0, tmY1, tmR0, tmR1, p),
+  rc = check_cuda(p.pair ? cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel<true>, tmA0, tmA1, tmB, tmY0, tmY1, tmR0, tmR1, p)
+                         : cudaLaunchKernelEx(&cfg, conv_tcgen05_kernel<false>, tmA0, tmA1, tmB, tmY0, tmY1, tmR0, tmR1, p),
                   "conv_tcgen05_kernel launch");
   if (rc) return rc;
   return 0;
