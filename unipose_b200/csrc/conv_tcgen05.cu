@@ -683,7 +683,6 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   if (p.pair) p.b_bytes = static_cast<uint32_t>(block_n / 2) * ck * 2;   // each CTA of the pair holds half of the weight tile
   p.idesc = make_idesc_f16(static_cast<uint32_t>(fmt), p.pair ? 256u : kTileM, static_cast<uint32_t>(block_n));
   p.idesc_res = make_idesc_f16(static_cast<uint32_t>(fmt), p.pair ? 256u : kTileM, 64u);
-  p.idesc_res = 0;
   if (has_res) UP_CHECK_ARG(ck == 64, "up_conv2d_fwd: residual needs cin to be a multiple of 64");
   if (const char* e = getenv("UP_DEBUG_NBUF")) {
     const int v = atoi(e);
