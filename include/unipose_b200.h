@@ -112,6 +112,10 @@ typedef struct UpConvDesc {
 int up_conv2d_fwd(const UpConvDesc* desc, const void* x, const void* w_packed, const float* scale,
                   const float* shift, const void* residual, void* y, float* stats, void* stream);
 
+/* Debug aid (UP_DEBUG_TIMING=1 in the environment): per-CTA phase timestamps (ns) of the last up_conv2d_fwd launch,
+ * 160 CTAs x 16 slots, copied to host memory (synchronising). */
+int up_debug_conv_timing(unsigned long long* h_out);
+
 /* Pack OIHW fp32 weights [cout_real][cin_real][kh][kw] -> 16-bit [plane][kh*kw][cout][cin]
  * (zero padded).  dtype UP_SPLIT writes two bf16 planes `w_plane_stride` elements apart. */
 int up_pack_conv_weight(const float* w_oihw, void* w_packed, int cout_real, int cin_real, int kh, int kw,

@@ -64,6 +64,7 @@ _SIGNATURES = {
     "up_dist_acc": [_P, _P, _I, _I, _D, _P],
     "up_mse_fwd_bwd": [_P, _P, _P, _P, _P, _L, _F, _P],
     "up_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P],
+    "up_debug_conv_timing": [_P],
     "up_conv2d_wgrad": [POINTER(UpConvDesc), _P, _P, _P, _I, _I, _P, _L, _I, _P],
     "up_bn_stats": [_P, _L, _I, _I, _P, _P],
     "up_bn_finalize": [_P, _L, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _I, _I, _P],
@@ -98,6 +99,10 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
+    override = os.environ.get("UNIPOSE_B200_LIB")     # A/B testing of kernel builds (tools only)
+    if override:
+        build_if_missing = False
+        path = override
     if build_if_missing:
         try:
             path = _build.build_library()

@@ -31,6 +31,16 @@
 
 namespace up {
 
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define UP_STAMP(slot)                                                       \
+  do {                                                                       \
+    if (p.dbg) p.dbg[blockIdx.x * 16 + (slot)] = gtimer();                   \
+  } while (0)
+
 constexpr int kMaxStages = 8;
 constexpr int kMaxBufs = 4;
 constexpr int kTileM = 128;
@@ -65,6 +75,7 @@ struct ConvKParams {
   const float* scale;
   const float* shift;
   float* out_f32;
+  unsigned long long* dbg;   // optional per-CTA phase timestamps (globaltimer ns): UP_DEBUG_TIMING=1
 };
 
 struct TileCoord {
@@ -141,6 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) UP_STAMP(0);   // kernel entry
   uint32_t crank = 0;
   if (p.cluster > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   const int first_work = blockIdx.x / p.cluster;
@@ -201,7 +213,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_base = *tmem_slot_ptr;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, identity tile) overlapped the
   // tail of the previous kernel; from here on we read its output.  Let our own dependents get scheduled early.
+  if (threadIdx.x == 0) UP_STAMP(1);   // prologue done
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0) UP_STAMP(2);   // dependencies resolved
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
@@ -332,6 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t accumulate = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(full_bar(s), phase);
+        if (tile == first_work && kb == 0) UP_STAMP(3);   // first operands landed
         tcgen05_after_thread_sync();
         const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage_step * s);
         if (kb >= nkb_conv) {
@@ -359,6 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           phase ^= 1u;
         }
       }
+      if (tile == first_work) UP_STAMP(4);                 // all MMAs of the first tile issued
       if constexpr (kPair) umma_commit_2cta_mc(tfull_bar(acc), 3);   // accumulator halves complete in both CTAs
       else umma_commit(tfull_bar(acc));                     // accumulator complete -> epilogue
       if (++acc == 2) {
@@ -396,7 +412,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (p.split) tma_store_5d(&tmY1, src + kPlaneBytes, p.y_coff + c, t.w0, 0, t.h0, t.n0);
         tma_store_commit();
       }
+      UP_STAMP(7);                  // last store issued
       tma_store_wait_all<0>();
+      UP_STAMP(8);                  // stores complete
     }
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue math (8 warps) =====================
@@ -413,6 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int tile = first_work; tile < total_tiles; tile += work_step) {
       const TileCoord t = decode_tile(p, tile, crank);
       mbar_wait(tfull_bar(acc), acc_phase);
+      if (tile == first_work && threadIdx.x == kEpiWarp0 * 32) UP_STAMP(5);   // first accumulator complete
       tcgen05_after_thread_sync();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.block_n;
 
@@ -500,6 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
       // all TMEM reads of this accumulator are done -> hand it back to the MMA issuer
+      if (tile == first_work && threadIdx.x == kEpiWarp0 * 32) UP_STAMP(6);     // first tile's epilogue math done
       tcgen05_before_thread_sync();
       __syncwarp();
       if (lane == 0) {
@@ -515,6 +535,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   tcgen05_before_thread_sync();
   __syncthreads();
+  if (threadIdx.x == 0) UP_STAMP(9);   // all roles done
   if (p.cluster > 1) {
     // a CTA must not exit while a peer can still multicast into its smem or arrive on its barriers
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -532,6 +553,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 namespace up {
 
 static int g_sm_count = 0;
+static unsigned long long* g_dbg_last = nullptr;
 static size_t g_max_smem = 0;
 static bool g_attr_set = false;
 
@@ -566,6 +588,13 @@ static int ensure_device() {
 }  // namespace up
 
 using namespace up;
+
+// Debug only (UP_DEBUG_TIMING=1): copies the phase timestamps of the last conv launch (160 CTAs x 16 slots) to the host.
+extern "C" int up_debug_conv_timing(unsigned long long* h_out) {
+  if (!g_dbg_last) return up::fail(UP_ERR_INVALID, "no timing buffer (set UP_DEBUG_TIMING=1)");
+  return up::check_cuda(cudaMemcpy(h_out, g_dbg_last, 160 * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost),
+                        "cudaMemcpy(timing)");
+}
 
 extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_packed, const float* scale,
                              const float* shift, const void* residual, void* y, float* stats, void* stream) {
@@ -677,7 +706,7 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   p.pair = 0;
   if (p.cluster == 2 && block_n >= 64) {
     const char* e = getenv("UP_PAIR");
-    p.pair = (e && e[0] == '0') ? 0 : 1;
+    p.pair = (e && e[0] == '1') ? 1 : 0;   // opt-in: measured slower than independent CTAs on most layers (round 1)
   }
   if (!p.pair && !getenv("UP_CLUSTER")) p.cluster = 1;   // plain multicast clusters measured slower than independent CTAs
   if (p.pair) p.b_bytes = static_cast<uint32_t>(block_n / 2) * ck * 2;   // each CTA of the pair holds half of the weight tile
@@ -712,6 +741,14 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   p.scale = scale;
   p.shift = shift;
   p.out_f32 = nchw ? static_cast<float*>(y) : nullptr;
+  p.dbg = nullptr;
+  if (getenv("UP_DEBUG_TIMING")) {
+    static unsigned long long* dbuf = nullptr;
+    if (!dbuf) cudaMalloc(&dbuf, 160 * 16 * sizeof(unsigned long long));
+    cudaMemsetAsync(dbuf, 0, 160 * 16 * sizeof(unsigned long long), static_cast<cudaStream_t>(stream));
+    p.dbg = dbuf;
+    g_dbg_last = dbuf;
+  }
 
   // ---- tensor maps ----
   CUtensorMap tmA0, tmA1, tmB, tmY0, tmY1, tmR0, tmR1;
