@@ -676,7 +676,9 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   int block_n = (d->cout % 256 == 0) ? 256 : (d->cout % 128 == 0) ? 128 : (d->cout % 64 == 0) ? 64 : 32;
   // keep at least ~2 tiles per SM so the epilogue of one tile overlaps the main loop of the next
-  while (block_n > 64 && static_cast<long long>(m_tiles) * (d->cout / block_n) < g_sm_count) block_n /= 2;
+  // The kernel is bound by the bytes each SM has to ingest per MMA (A 16 KB + B block_n*128 B per k-block at ~48 B/clk),
+  // so wide N tiles win even when that leaves a single wave; only shrink when more than ~40% of the SMs would idle.
+  while (block_n > 64 && static_cast<long long>(m_tiles) * (d->cout / block_n) * 10 < 6LL * g_sm_count) block_n /= 2;
   if (const char* e = getenv("UP_DEBUG_BLOCKN")) {
     const int v = atoi(e);
     if (v >= 32 && d->cout % v == 0 && (nchw || v % 64 == 0)) block_n = v;
