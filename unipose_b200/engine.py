@@ -66,13 +66,21 @@ class Builder:
         self.plan.buffers.append(t)
         return t
 
-    def add(self, fn: Callable[[], None], name: str = "") -> None:
-        self.plan.ops.append((name, fn))
+    def add(self, fn: Callable[[], None], name: str = "", side: bool = False) -> None:
+        """Record a launch.  side=True puts it on the plan's side stream (between fork() and join()), so an
+        independent branch (e.g. WASP's image-level pooling branch) overlaps the main chain inside the CUDA graph."""
+        self.plan.ops.append((name, fn, side))
+
+    def fork(self) -> None:
+        self.plan.ops.append(("fork", None, False))
+
+    def join(self) -> None:
+        self.plan.ops.append(("join", None, False))
 
     # ---- conv (+ folded eval BatchNorm / bias) ----
     def packed_conv(self, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], cin_pad: Optional[int] = None,
                     cout_pad: Optional[int] = None, weight_fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
-                    nchw_out: bool = False) -> PackedConv:
+                    nchw_out: bool = False, extra_sources: Sequence[torch.Tensor] = ()) -> PackedConv:
         """Allocate packed buffers for `conv` (+`bn` folded as eval-mode scale/shift) and register the job that
         (re)fills them from the live parameters."""
         w0 = conv.weight if weight_fn is None else weight_fn(conv.weight.detach())
@@ -113,14 +121,14 @@ class Builder:
             ops._lib.call("up_pack_conv_weight", ops._ptr(w), ops._ptr(wbuf), co_r, ci_r, kh, kw, cout, cin, self.mode,
                           kh * kw * cout * cin, ops._stream())
 
-        srcs = [conv.weight] + ([conv.bias] if conv.bias is not None else [])
+        srcs = [conv.weight] + ([conv.bias] if conv.bias is not None else []) + list(extra_sources)
         if bn is not None:
             srcs += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
         self.plan.pack_jobs.append(_PackJob(srcs, fill))
         return pc
 
-    def conv(self, x, pc: PackedConv, y, name: str = "conv", **kw) -> None:
-        self.add(lambda: ops.conv2d(x, pc, y, **kw), name)
+    def conv(self, x, pc: PackedConv, y, name: str = "conv", side: bool = False, **kw) -> None:
+        self.add(lambda: ops.conv2d(x, pc, y, **kw), name, side=side)
 
 
 class Plan:
@@ -129,7 +137,8 @@ class Plan:
         self.precision = precision
         self.mode = ops.mode_of(precision)
         self.buffers: List = []
-        self.ops: List[Tuple[str, Callable[[], None]]] = []
+        self.ops: List[Tuple[str, Optional[Callable[[], None]], bool]] = []
+        self.side_stream: Optional[torch.cuda.Stream] = None
         self.pack_jobs: List[_PackJob] = []
         self.inputs: List[torch.Tensor] = []
         self.outputs: List[torch.Tensor] = []
@@ -155,8 +164,20 @@ class Plan:
         return changed
 
     def _launch_all(self) -> None:
-        for _name, fn in self.ops:
-            fn()
+        main = torch.cuda.current_stream(self.device)
+        for name, fn, side in self.ops:
+            if fn is None:
+                if self.side_stream is None:
+                    self.side_stream = torch.cuda.Stream(device=self.device)
+                if name == "fork":
+                    self.side_stream.wait_stream(main)
+                else:
+                    main.wait_stream(self.side_stream)
+            elif side:
+                with torch.cuda.stream(self.side_stream):
+                    fn()
+            else:
+                fn()
 
     def run(self, *inputs: torch.Tensor) -> List[torch.Tensor]:
         assert len(inputs) == len(self.inputs)
@@ -176,5 +197,5 @@ class Plan:
             self.graph.replay()
         else:
             self._launch_all()
-        self.launches = len(self.ops)
+        self.launches = sum(1 for _n, fn, _s in self.ops if fn is not None)
         return self.outputs

@@ -5,9 +5,10 @@ Kernel plan for x [N, h, w, 2048] (all NHWC 16-bit, BN folded into the conv epil
 
     aspp1 1x1 2048->256          -> S[0:N]          (S stacks the four cascade outputs along n)
     aspp2/3/4 3x3 d18/12/6       -> S[N:2N], S[2N:3N], S[3N:4N]   (taps that fall outside the map are skipped)
-    conv2 1x1 (shared weights)   S -> T, T -> U[0:4N]              (two launches over M = 4N*h*w instead of eight)
-    GAP -> 1x1 -> BN -> ReLU -> broadcast                -> U[4N:5N]
-    conv1 1x1 1280->256 + bn1 + ReLU reads U as a 5-group K-split (no concat buffer) -> out
+    GAP -> 1x1 -> BN -> ReLU -> broadcast                -> S[4N:5N]   (side stream, overlaps the cascade)
+    conv1' 1x1 1280->256 + bn1 + ReLU reads S as a 5-group K-split (no concat buffer) -> out, where
+    conv1' = conv1 with the shared conv2 applied twice folded into its weights (eval only; the training plan in
+    train.py keeps conv2 as two launches over M = 4N*h*w)
 """
 import torch
 import torch.nn as nn
@@ -75,30 +76,38 @@ class wasp(PlanModule):
     def _inplanes(backbone):
         return 2048
 
+    def _folded_conv1_weight(self, w1):
+        """Inference-only algebra: conv1(cat(conv2(conv2(x_i)), x5)) == conv1'(cat(x_i, x5)) with
+        W1'_i = W1_i . W2 . W2 (fp32 on the host side of the pack job) - the two shared-1x1 launches over 4N*h*w
+        pixels disappear (wasp.py:72-88).  Training keeps the unfolded graph (train.py)."""
+        w2 = self.conv2.weight.detach().float()[:, :, 0, 0]
+        w22 = w2 @ w2
+        w1m = w1.float()[:, :, 0, 0]
+        parts = [w1m[:, i * 256:(i + 1) * 256] @ w22 for i in range(4)] + [w1m[:, 1024:]]
+        return torch.cat(parts, dim=1)[:, :, None, None].contiguous()
+
     def _emit(self, b, x):
         n, h, w = x.n, x.h, x.w
-        S = b.act(4 * n, h, w, 256)
-        branch = [View(S, n_off=i * n, n=n) for i in range(4)]
+        S = b.act(5 * n, h, w, 256)      # the four cascade outputs + the broadcast pooling branch, stacked along n
+        branch = [View(S, n_off=i * n, n=n) for i in range(5)]
+        # image-level branch on the side stream: GAP -> 1x1 (-> BN) -> ReLU -> bilinear from 1x1 == broadcast
+        b.fork()
+        g = b.act(n, 1, 1, x.c)
+        b.add(lambda: ops.global_avgpool(x, g), "wasp.gap", side=True)
+        g2 = b.act(n, 1, 1, 256)
+        gap_bn = self.global_avg_pool[2] if self._gap_has_bn else None
+        b.conv(g, b.packed_conv(self.global_avg_pool[1], gap_bn), g2, "wasp.gap_conv", side=True, relu=True)
+        b.add(lambda: ops.broadcast_hw(g2, branch[4]), "wasp.gap_broadcast", side=True)
+        # the waterfall: 1x1, then three dilated 3x3 feeding each other (wasp.py:67-70)
         self.aspp1._emit(b, x, branch[0])
         self.aspp2._emit(b, branch[0], branch[1])
         self.aspp3._emit(b, branch[1], branch[2])
         self.aspp4._emit(b, branch[2], branch[3])
-        # shared 1x1 conv2 applied twice to every branch, no BN / ReLU in between (wasp.py:72-80)
-        pc2 = b.packed_conv(self.conv2, None)
-        T = b.act(4 * n, h, w, 256)
-        U = b.act(5 * n, h, w, 256)
-        b.conv(S, pc2, T, "wasp.conv2a")
-        b.conv(T, pc2, View(U, n_off=0, n=4 * n), "wasp.conv2b")
-        # image-level branch: GAP -> 1x1 (-> BN) -> ReLU -> bilinear from 1x1 == broadcast (wasp.py:82-83)
-        g = b.act(n, 1, 1, x.c)
-        b.add(lambda: ops.global_avgpool(x, g), "wasp.gap")
-        g2 = b.act(n, 1, 1, 256)
-        gap_bn = self.global_avg_pool[2] if self._gap_has_bn else None
-        b.conv(g, b.packed_conv(self.global_avg_pool[1], gap_bn), g2, "wasp.gap_conv", relu=True)
-        b.add(lambda: ops.broadcast_hw(g2, View(U, n_off=4 * n, n=n)), "wasp.gap_broadcast")
+        b.join()
         out = b.act(n, h, w, 256)
-        b.conv(View(U, n_off=0, n=n), b.packed_conv(self.conv1, self.bn1), out, "wasp.conv1", relu=True,
-               x_groups=5, x_group_nstride=n)
+        pc1 = b.packed_conv(self.conv1, self.bn1, weight_fn=self._folded_conv1_weight,
+                            extra_sources=[self.conv2.weight])
+        b.conv(branch[0], pc1, out, "wasp.conv1", relu=True, x_groups=5, x_group_nstride=n)
         return out   # nn.Dropout(0.5) is the identity in eval mode (wasp.py:90)
 
 
