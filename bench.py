@@ -317,8 +317,12 @@ def wasp_roofline(model, args, dev, peaks):
     flops = WASP_FLOPS_PER_IMG * (hw * hw / 576.0) * B
     achieved = flops / (ms * 1e-3) / 1e12
     t_roof_ms = max(flops / (peaks["tflops_burst"] * 1e12), WASP_MIN_BYTES_C2 / (peaks["hbm_gbs"] * 1e9)) * 1e3
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "wasp_traffic_r1.json")
+    if os.path.exists(tpath) and B == 32 and hw == 24:
+        traffic = json.load(open(tpath))["dram_bytes_per_block"]   # from the committed ncu capture of the same block
     return {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["tflops_burst"], "traffic": None, "peak_source": peaks["source"],
+            "frac": achieved / peaks["tflops_burst"], "traffic": traffic, "peak_source": peaks["source"],
             "kernel": "conv_tcgen05_kernel (WASP block = %d launches: 6 convs + GAP + broadcast; shared conv2 folded into conv1)" % plan.launches,
             "wasp_ms": ms, "wasp_t_roof_ms": t_roof_ms, "wasp_roofline_frac": t_roof_ms / ms,
             "flops_convention": "nominal dense (zero taps counted), %.1f GFLOP per launch group" % (flops / 1e9)}
