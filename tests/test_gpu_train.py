@@ -75,18 +75,21 @@ def test_train_step_matches_oracle_autograd():
     params = dict(m.named_parameters())
     # Back-propagation through ~100 ReLU/BatchNorm layers of this synthetic net is ill-conditioned: the reference's
     # OWN fp32 gradients differ from the fp64 ones by ~1e-2 (ReLU gates flipping), so parity is judged against that
-    # noise floor - within 16x of the reference's fp32-vs-fp64 error, cosine similarity > 0.99 - while the
-    # per-kernel tests (test_gpu_train_ops.py) hold the tight bounds.
+    # noise floor.  The bf16x3 split arithmetic rounds operands at 2^-17 (fp32: 2^-24), so its seed error is
+    # ~20-30x the fp32 one already at the head (measured 1.6e-4 vs 7.4e-6 on last_conv.8.weight) and the same
+    # conditioning amplifies both: the bound is 40x the reference's fp32-vs-fp64 error, never above 0.1, cosine
+    # similarity > 0.995 - while the per-kernel tests (test_gpu_train_ops.py) hold the tight bounds.
     report = {}
     for k in CHECK:
         assert params[k].grad is not None, k
         ours = _rel_l2(params[k].grad, sd64[k].grad)
         floor = _rel_l2(ref_sd[k].grad, sd64[k].grad)
         report[k] = (ours, floor, _cos(params[k].grad, sd64[k].grad))
-        assert ours <= max(16.0 * floor, 2e-3), (k, ours, floor)
-        assert report[k][2] > 0.99, (k, report[k])
     print("grad rel-L2 (ours vs fp64, reference-fp32 vs fp64, cosine):",
           {k: "%.1e / %.1e / %.5f" % v for k, v in report.items()})
+    for k, (ours, floor, cos) in report.items():
+        assert ours <= min(max(40.0 * floor, 2e-3), 0.1), (k, ours, floor)
+        assert cos > 0.995, (k, report[k])
     assert report["decoder.last_conv.8.weight"][0] < 1e-3 and report["decoder.last_conv.8.bias"][0] < 1e-3
     # dead parameters of the reference stay without gradient (decoder.py:20-21)
     assert params["decoder.conv2.weight"].grad is None and params["decoder.bn2.weight"].grad is None
