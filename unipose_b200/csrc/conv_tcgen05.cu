@@ -64,7 +64,9 @@ struct ConvKParams {
   int pair;        // 1: the two CTAs of a cluster issue ONE tcgen05.mma.cta_group::2 (M = 256) per k-step; each holds
                    //    its own 128 activation rows and HALF of the weight tile -> half the smem fill + operand reads
   int cluster;     // CTAs per cluster (1, 2 or 4): they share one weight tile per k-block via TMA multicast
-  int res_terms;   // residual k-blocks per 64-channel group (0 = none, 1, or 2 in split mode)
+  int res_terms;   // residual tiles (128 px x 64 ch, 16 KB) per 64-channel group (0 = none, 1, or 2 in split mode)
+  int res_per_slot;  // how many of them share one ring slot (the slot is a_bytes + b_bytes wide)
+  int bsplit;        // experiment (UP_DEBUG_BSPLIT): fetch the weight tile with this many TMA instructions
   uint32_t idesc_res;
   uint32_t a_bytes, b_bytes, buf_bytes;
   uint32_t idesc;
@@ -122,6 +124,89 @@ __device__ __forceinline__ void tap_range(const ConvKParams& p, int taps, int pa
       lo = min(lo, k);
       hi = max(hi, k);
     }
+  }
+}
+
+// ---- epilogue of one 128 x block_n tile, NHWC 16-bit output ---------------------------------------------------
+// kMode: 0 = fp16, 1 = bf16, 2 = bf16 hi/lo split.  cvt.*x2 packs two values per instruction and applies the ReLU.
+template <int kMode, bool kRelu>
+__device__ __forceinline__ uint32_t epi_pack2(float lo_elem, float hi_elem) {
+  uint32_t d;
+  if constexpr (kMode == 0) {
+    if constexpr (kRelu) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  } else {
+    if constexpr (kRelu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  }
+  return d;
+}
+
+struct EpiCtx {
+  const float* scale;    // first of this warp's 32 columns of group 0
+  const float* shift;
+  uint32_t taddr;        // TMEM address of the same columns (lane quarter in the upper half)
+  uint32_t row_smem;     // staging buffer 0 + this thread's 128-byte row
+  uint32_t buf_bytes, nbuf;
+  uint32_t chunk0;       // first 16-byte chunk of the row this warp fills (0 or 4)
+  uint32_t row7;         // row & 7: the 128B-swizzle XOR
+  uint32_t avail0;       // avail[0] barrier; ready[b] = avail0 + 8 * (kMaxBufs + b)
+  int lane;
+  int groups;
+};
+
+// Groups of 64 columns.  The accumulator registers are dead once scale/shift have been applied, so the tcgen05.ld of
+// group g+1 is issued right there and flies while group g is packed, written to the staging buffer and handed over.
+template <int kMode, bool kRelu>
+__device__ __forceinline__ void epi_tile(const EpiCtx& c, uint32_t& q) {
+  uint32_t r[32];
+  tmem_ld_32x32b_x32(c.taddr, r);
+  for (int g = 0; g < c.groups; ++g, ++q) {
+    const float4* sc = reinterpret_cast<const float4*>(c.scale + g * 64);
+    const float4* sh = reinterpret_cast<const float4*>(c.shift + g * 64);
+    float v[32];
+    tmem_ld_wait();
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 s4 = __ldg(sc + j4);
+      const float4 h4 = __ldg(sh + j4);
+      v[4 * j4 + 0] = fmaf(__uint_as_float(r[4 * j4 + 0]), s4.x, h4.x);
+      v[4 * j4 + 1] = fmaf(__uint_as_float(r[4 * j4 + 1]), s4.y, h4.y);
+      v[4 * j4 + 2] = fmaf(__uint_as_float(r[4 * j4 + 2]), s4.z, h4.z);
+      v[4 * j4 + 3] = fmaf(__uint_as_float(r[4 * j4 + 3]), s4.w, h4.w);
+    }
+    if (g + 1 < c.groups) tmem_ld_32x32b_x32(c.taddr + (g + 1) * 64, r);
+    uint32_t w[16], wl[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      if constexpr (kMode == 2) {
+        const float a = kRelu ? fmaxf(v[2 * e], 0.f) : v[2 * e];
+        const float b = kRelu ? fmaxf(v[2 * e + 1], 0.f) : v[2 * e + 1];
+        w[e] = epi_pack2<1, false>(a, b);
+        wl[e] = epi_pack2<1, false>(a - __uint_as_float(w[e] << 16), b - __uint_as_float(w[e] & 0xFFFF0000u));
+      } else {
+        w[e] = epi_pack2<kMode, kRelu>(v[2 * e], v[2 * e + 1]);
+      }
+    }
+    const uint32_t b = q % c.nbuf;
+    // the staging buffer becomes ours (its previous TMA store has drained)
+    mbar_wait(c.avail0 + 8u * b, (q / c.nbuf) & 1u);
+    const uint32_t rowaddr = c.row_smem + b * c.buf_bytes;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      const uint32_t addr = rowaddr + (((c.chunk0 + c4) ^ c.row7) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[4 * c4]), "r"(w[4 * c4 + 1]),
+                   "r"(w[4 * c4 + 2]), "r"(w[4 * c4 + 3])
+                   : "memory");
+      if constexpr (kMode == 2) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + kPlaneBytes), "r"(wl[4 * c4]),
+                     "r"(wl[4 * c4 + 1]), "r"(wl[4 * c4 + 2]), "r"(wl[4 * c4 + 3])
+                     : "memory");
+      }
+    }
+    fence_proxy_async_smem();   // make the generic-proxy writes visible to the TMA store
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(c.avail0 + 8u * (kMaxBufs + b));  // one arrival per warp (8) -> the DMA thread stores
   }
 }
 
@@ -218,111 +303,117 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (threadIdx.x == 0) UP_STAMP(2);   // dependencies resolved
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  if (warp == 0) {
-    // ===================== TMA producer (32 lanes, lane i owns k-blocks i, i+32, ...) =====================
-    uint32_t kb_base = 0;
+  if (warp == 0 || warp == 3) {
+    // ===================== TMA producers (two warps: even / odd k-blocks) =====================
+    // Each warp walks the whole (tap, channel chunk, term) loop nest with warp-uniform values - pure increments, no
+    // divisions, no cross-lane traffic - and its lane 0 issues the copies of every second k-block.  A k-block's slot
+    // and barrier parity follow from its sequence number alone, and a producer cannot run more than `stages`
+    // k-blocks ahead of the MMA issuer, so the two issue streams need no ordering between them.
+    const int which = warp == 3 ? 1 : 0;
+    uint32_t s = 0, wait_par = 1;   // slot and the parity of its `empty` barrier to wait for (fresh barrier: passes)
+    int issued = 0;
     const int taps = p.taps_h * p.taps_w;
+    const int res_units = (p.block_n >> 6) * p.res_terms;
     for (int tile = first_work; tile < total_tiles; tile += work_step) {
       const TileCoord t = decode_tile(p, tile, crank);
       int kh_lo, kh_hi, kw_lo, kw_hi;
       tap_range(p, p.taps_h, p.pad_h, t.h0, p.bh, p.Hq, kh_lo, kh_hi);
       tap_range(p, p.taps_w, p.pad_w, t.w0, p.bw, p.Wq, kw_lo, kw_hi);
-      const int nw = kw_hi - kw_lo + 1;
-      const int nkb_conv = (kh_hi - kh_lo + 1) * nw * p.chunks * p.nterms;
-      const int groups = p.block_n >> 6;
-      const int nkb = nkb_conv + groups * p.res_terms;   // + residual tiles fed through the MMA pipe
-      for (int i0 = 0; i0 < nkb; i0 += 32) {
-        // phase 1 (all lanes in parallel): coordinates of k-block i0 + lane
-        const int i = i0 + lane;
-        const bool active = i < nkb;
-        const bool is_res = i >= nkb_conv;
-        const int ri = i - nkb_conv;                       // residual k-block: group ri / res_terms, plane ri % res_terms
-        const int term = i % p.nterms;
-        const int j = i / p.nterms;
-        const int chunk = j % p.chunks;
-        const int a = j / p.chunks;
-        const int kh = kh_lo + a / nw;
-        const int kw = kw_lo + a % nw;
-        int oh, ow, ph, pw;
+      const int brow_nt = t.nt * p.block_n;
+      for (int kh = kh_lo; kh <= kh_hi; ++kh) {
+        int oh, ph;
         tap_offset(p, kh, p.pad_h, oh, ph);
-        tap_offset(p, kw, p.pad_w, ow, pw);
-        const int g = chunk / p.chunks_per_group;
-        const int cc = chunk - g * p.chunks_per_group;
-        const int c = p.x_coff + cc * p.ck + pw * p.x_cs;
-        const int n = t.n0 + g * p.group_nstride;
-        const uint32_t kb = kb_base + i;
-        const uint32_t s = kb % p.stages;
-        const uint32_t phase = (kb / p.stages) & 1u;
-        const uint32_t a_dst = smem_base + s * stage_bytes;
-        const int brow = ((term == 2 ? taps : 0) + kh * p.taps_w + kw) * p.cout + t.nt * p.block_n;
-        const CUtensorMap* amap = (term == 1) ? &tmA1 : &tmA0;
-        // phase 2: lane 0 issues the k-blocks strictly in order (the slot / phase protocol of the smem ring
-        // assumes in-order production), fetching each k-block's coordinates from the lane that computed them
-        const int cnt = min(32, nkb - i0);
-        int sel = (term == 1) ? 1 : 0;
-        int cc_c = c, cc_w = t.w0 + ow, cc_p = ph, cc_h = t.h0 + oh, cc_n = n;
-        if (is_res) {
-          const int rg = p.res_terms ? ri / p.res_terms : 0;
-          sel = 2 + (p.res_terms ? ri % p.res_terms : 0);  // 2 = residual hi plane, 3 = residual lo plane
-          cc_c = p.r_coff + t.nt * p.block_n + rg * 64;
-          cc_w = t.w0;
-          cc_p = 0;
-          cc_h = t.h0;
-          cc_n = t.n0;
-        }
-        for (int l = 0; l < cnt; ++l) {
-          const int c_l = __shfl_sync(0xffffffffu, cc_c, l);
-          const int w_l = __shfl_sync(0xffffffffu, cc_w, l);
-          const int ph_l = __shfl_sync(0xffffffffu, cc_p, l);
-          const int h_l = __shfl_sync(0xffffffffu, cc_h, l);
-          const int n_l = __shfl_sync(0xffffffffu, cc_n, l);
-          const uint32_t s_l = __shfl_sync(0xffffffffu, s, l);
-          const uint32_t par_l = __shfl_sync(0xffffffffu, phase ^ 1u, l);
-          const int brow_l = __shfl_sync(0xffffffffu, brow, l);
-          const int bcol_l = __shfl_sync(0xffffffffu, chunk * p.ck, l);
-          const int sel_l = __shfl_sync(0xffffffffu, sel, l);
-          if (lane == 0) {
-            const uint32_t dst = smem_base + s_l * stage_bytes;
-            mbar_wait(empty_bar(s_l), par_l, 16000000000LL);
-            if constexpr (kPair) {
-              // CTA pair: bytes of BOTH CTAs are credited to the leader's barrier (count 2: one arrive per producer)
-              const uint32_t mine = (sel_l >= 2) ? p.a_bytes : (p.a_bytes + p.b_bytes);   // b_bytes = this CTA's half
-              if (crank == 0) mbar_arrive_expect_tx(full_bar(s_l), 2u * mine);
-              else mbar_arrive_remote(full_bar(s_l), 0u);
-              if (sel_l >= 2) {
-                tma_load_5d_2cta(sel_l == 3 ? &tmR1 : &tmR0, dst, full_bar(s_l), c_l, w_l, ph_l, h_l, n_l);
-              } else {
-                tma_load_5d_2cta(sel_l ? &tmA1 : &tmA0, dst, full_bar(s_l), c_l, w_l, ph_l, h_l, n_l);
-                tma_load_2d_2cta(&tmB, dst + p.a_bytes, full_bar(s_l), bcol_l,
-                                 brow_l + static_cast<int>(crank) * (p.block_n >> 1));
+        for (int kw = kw_lo; kw <= kw_hi; ++kw) {
+          int ow, pw;
+          tap_offset(p, kw, p.pad_w, ow, pw);
+          const int brow_tap = (kh * p.taps_w + kw) * p.cout + brow_nt;
+          const int cbase = p.x_coff + pw * p.x_cs;
+          int g = 0, cc = 0;
+          for (int chunk = 0; chunk < p.chunks; ++chunk) {
+            const int c = cbase + cc * p.ck;
+            const int n = t.n0 + g * p.group_nstride;
+            for (int term = 0; term < p.nterms; ++term) {
+              // split mode: hi*hi (A0, B0), lo*hi (A1, B0), hi*lo (A0, B1)
+              const CUtensorMap* amap = (term == 1) ? &tmA1 : &tmA0;
+              const int brow = brow_tap + (term == 2 ? taps * p.cout : 0);
+              const uint32_t dst = smem_base + s * stage_bytes;
+              const bool mine = (issued & 1) == which;
+              if (mine) mbar_wait(empty_bar(s), wait_par, 16000000000LL);
+              if (mine && elect_one()) {
+                if constexpr (kPair) {
+                  // CTA pair: bytes of BOTH CTAs are credited to the leader's barrier (count 2: one arrive each)
+                  const uint32_t mine = p.a_bytes + p.b_bytes;   // b_bytes = this CTA's half of the weight tile
+                  if (crank == 0) mbar_arrive_expect_tx(full_bar(s), 2u * mine);
+                  else mbar_arrive_remote(full_bar(s), 0u);
+                  tma_load_5d_2cta(amap, dst, full_bar(s), c, t.w0 + ow, ph, t.h0 + oh, n);
+                  tma_load_2d_2cta(&tmB, dst + p.a_bytes, full_bar(s), chunk * p.ck,
+                                   brow + static_cast<int>(crank) * (p.block_n >> 1));
+                } else {
+                  mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+                  tma_load_5d(amap, dst, full_bar(s), c, t.w0 + ow, ph, t.h0 + oh, n);
+                  if (p.cluster > 1) {
+                    // each CTA fetches 1/cluster of the weight rows and multicasts them to every CTA of the cluster
+                    const uint32_t sub_rows = static_cast<uint32_t>(p.block_n / p.cluster);
+                    tma_load_2d_mc(&tmB, dst + p.a_bytes + crank * sub_rows * static_cast<uint32_t>(p.ck) * 2u,
+                                   full_bar(s), chunk * p.ck, brow + static_cast<int>(crank * sub_rows),
+                                   static_cast<uint16_t>((1u << p.cluster) - 1u));
+                  } else {
+                    const uint32_t part_rows = static_cast<uint32_t>(p.block_n / p.bsplit);
+                    for (int j = 0; j < p.bsplit; ++j)
+                      tma_load_2d(&tmB, dst + p.a_bytes + j * part_rows * static_cast<uint32_t>(p.ck) * 2u, full_bar(s),
+                                  chunk * p.ck, brow + static_cast<int>(j * part_rows));
+                  }
+                }
+                if (issued == 0) UP_STAMP(10);   // first k-block issued
+                if (issued == 4) UP_STAMP(11);   // fifth k-block issued (slots were free)
               }
-            } else if (sel_l >= 2) {
-              // residual tile [128 px x 64 ch] -> the A slot; its B operand is the resident identity tile
-              mbar_arrive_expect_tx(full_bar(s_l), p.a_bytes);
-              tma_load_5d(sel_l == 3 ? &tmR1 : &tmR0, dst, full_bar(s_l), c_l, w_l, ph_l, h_l, n_l);
-            } else {
-              mbar_arrive_expect_tx(full_bar(s_l), stage_bytes);
-              tma_load_5d(sel_l ? &tmA1 : &tmA0, dst, full_bar(s_l), c_l, w_l, ph_l, h_l, n_l);
-              if (p.cluster > 1) {
-                // each CTA fetches 1/cluster of the weight rows and multicasts them to every CTA of the cluster
-                const uint32_t sub_rows = static_cast<uint32_t>(p.block_n / p.cluster);
-                tma_load_2d_mc(&tmB, dst + p.a_bytes + crank * sub_rows * static_cast<uint32_t>(p.ck) * 2u, full_bar(s_l),
-                               bcol_l, brow_l + static_cast<int>(crank * sub_rows),
-                               static_cast<uint16_t>((1u << p.cluster) - 1u));
-              } else {
-                tma_load_2d(&tmB, dst + p.a_bytes, full_bar(s_l), bcol_l, brow_l);
+              ++issued;
+              if (++s == static_cast<uint32_t>(p.stages)) {
+                s = 0;
+                wait_par ^= 1u;
               }
+            }
+            if (++cc == p.chunks_per_group) {
+              cc = 0;
+              ++g;
             }
           }
         }
-        (void)active;
-        (void)a_dst;
-        (void)amap;
       }
-      kb_base += nkb;
+      // residual slots: up to res_per_slot tiles [128 px x 64 ch] side by side; their B operand is the resident identity
+      for (int u0 = 0; u0 < res_units; u0 += p.res_per_slot) {
+        const int u_end = min(u0 + p.res_per_slot, res_units);
+        const uint32_t dst = smem_base + s * stage_bytes;
+        const bool mine = (issued & 1) == which;
+        if (mine) mbar_wait(empty_bar(s), wait_par, 16000000000LL);
+        if (mine && elect_one()) {
+          const uint32_t bytes = static_cast<uint32_t>(u_end - u0) * p.a_bytes;
+          if constexpr (kPair) {
+            if (crank == 0) mbar_arrive_expect_tx(full_bar(s), 2u * bytes);
+            else mbar_arrive_remote(full_bar(s), 0u);
+          } else {
+            mbar_arrive_expect_tx(full_bar(s), bytes);
+          }
+          for (int u = u0; u < u_end; ++u) {
+            const int rg = u / p.res_terms;
+            const CUtensorMap* rmap = (u - rg * p.res_terms) ? &tmR1 : &tmR0;   // hi / lo plane of the residual
+            const int rc = p.r_coff + brow_nt + rg * 64;
+            const uint32_t rdst = dst + static_cast<uint32_t>(u - u0) * p.a_bytes;
+            if constexpr (kPair) tma_load_5d_2cta(rmap, rdst, full_bar(s), rc, t.w0, 0, t.h0, t.n0);
+            else tma_load_5d(rmap, rdst, full_bar(s), rc, t.w0, 0, t.h0, t.n0);
+          }
+        }
+        ++issued;
+        if (++s == static_cast<uint32_t>(p.stages)) {
+          s = 0;
+          wait_par ^= 1u;
+        }
+      }
     }
-  } else if (threadIdx.x == 32 && (!kPair || crank == 0)) {
+  } else if (warp == 1 && (!kPair || crank == 0)) {
     // ===================== MMA issuer (pair mode: leader CTA only) =====================
+    // The whole warp runs the loop converged (warp-uniform descriptors stay in uniform registers); one elected lane
+    // issues the tcgen05 instructions.
     int s = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -339,44 +430,56 @@ __global__ void __launch_bounds__(kThreads, 1)
       tap_range(p, p.taps_h, p.pad_h, t.h0, p.bh, p.Hq, kh_lo, kh_hi);
       tap_range(p, p.taps_w, p.pad_w, t.w0, p.bw, p.Wq, kw_lo, kw_hi);
       const int nkb_conv = (kh_hi - kh_lo + 1) * (kw_hi - kw_lo + 1) * p.chunks * p.nterms;
-      const int nkb = nkb_conv + (p.block_n >> 6) * p.res_terms;
+      const int res_units = (p.block_n >> 6) * p.res_terms;
+      const int nkb = nkb_conv + (p.res_terms ? (res_units + p.res_per_slot - 1) / p.res_per_slot : 0);
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tcgen05_after_thread_sync();
       const uint32_t tmem_d = tmem_base + acc * p.block_n;
       uint32_t accumulate = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(full_bar(s), phase);
-        if (tile == first_work && kb == 0) UP_STAMP(3);   // first operands landed
         tcgen05_after_thread_sync();
         const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage_step * s);
-        if (kb >= nkb_conv) {
-          // residual group: D[:, g*64 .. g*64+63] += R_tile x I  (exact: products with 1.0, fp32 accumulate)
-          const int rg = (kb - nkb_conv) / p.res_terms;
-          for (int k = 0; k < 4; ++k) {
-            if constexpr (kPair) umma_f16_2cta(tmem_d + rg * 64, adesc + 2u * k, identdesc + 2u * k, p.idesc_res, 1u);
-            else umma_f16(tmem_d + rg * 64, adesc + 2u * k, identdesc + 2u * k, p.idesc_res, 1u);
+        if (elect_one()) {
+          if (tile == first_work && kb == 0) UP_STAMP(3);   // first operands landed
+          if (tile == first_work && kb == 2) UP_STAMP(12);  // third k-block landed
+          if (kb >= nkb_conv) {
+            // residual tiles of this slot: D[:, g*64 .. g*64+63] += R_tile x I  (exact: products with 1.0)
+            const int u0 = (kb - nkb_conv) * p.res_per_slot;
+            const int u_end = min(u0 + p.res_per_slot, res_units);
+            for (int u = u0; u < u_end; ++u) {
+              const int rg = u / p.res_terms;
+              const uint64_t rdesc = adesc + static_cast<uint64_t>((p.a_bytes >> 4) * (u - u0));
+              for (int k = 0; k < 4; ++k) {
+                if constexpr (kPair) umma_f16_2cta(tmem_d + rg * 64, rdesc + 2u * k, identdesc + 2u * k, p.idesc_res, 1u);
+                else umma_f16(tmem_d + rg * 64, rdesc + 2u * k, identdesc + 2u * k, p.idesc_res, 1u);
+              }
+            }
+          } else {
+            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage_step * s);
+            for (int k = 0; k < kk; ++k) {
+              // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in 16-byte units
+              if constexpr (kPair) umma_f16_2cta(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, (kb | k) ? 1u : 0u);
+              else umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, (kb | k) ? 1u : 0u);
+            }
           }
-        } else {
-          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage_step * s);
-          for (int k = 0; k < kk; ++k) {
-            // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in 16-byte units
-            if constexpr (kPair) umma_f16_2cta(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, accumulate);
-            else umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, accumulate);
-            accumulate = 1;
+          // frees the smem slot once these MMAs have read it - in every CTA of the cluster (peers multicast into it)
+          if constexpr (kPair) umma_commit_2cta_mc(empty_bar(s), 3);
+          else if (p.cluster > 1) umma_commit_mc(empty_bar(s), static_cast<uint16_t>((1u << p.cluster) - 1u));
+          else umma_commit(empty_bar(s));
+          if (tile == first_work && kb == 2) UP_STAMP(13);  // ... and its MMAs + commit issued
+          if (kb == nkb - 1) {
+            if (tile == first_work) UP_STAMP(4);                 // all MMAs of the first tile issued
+            if constexpr (kPair) umma_commit_2cta_mc(tfull_bar(acc), 3);   // accumulator halves complete in both CTAs
+            else umma_commit(tfull_bar(acc));                     // accumulator complete -> epilogue
           }
         }
-        // frees the smem slot once these MMAs have read it - in every CTA of the cluster (peers multicast into it)
-        if constexpr (kPair) umma_commit_2cta_mc(empty_bar(s), 3);
-        else if (p.cluster > 1) umma_commit_mc(empty_bar(s), static_cast<uint16_t>((1u << p.cluster) - 1u));
-        else umma_commit(empty_bar(s));
+        __syncwarp();
         if (++s == p.stages) {
           s = 0;
           phase ^= 1u;
         }
       }
-      if (tile == first_work) UP_STAMP(4);                 // all MMAs of the first tile issued
-      if constexpr (kPair) umma_commit_2cta_mc(tfull_bar(acc), 3);   // accumulator halves complete in both CTAs
-      else umma_commit(tfull_bar(acc));                     // accumulator complete -> epilogue
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -394,12 +497,17 @@ __global__ void __launch_bounds__(kThreads, 1)
         t = decode_tile(p, tile, crank);
         c = t.nt * p.block_n + (q % groups) * 64;
       };
-      // Two staging buffers, one group of look-ahead: while the epilogue warps fill buffer q%2, this thread waits for
-      // the TMA store of group q-1 to finish READING the other buffer and hands it out for group q+1.
+      // nbuf staging buffers, one group of look-ahead: while the epilogue warps fill buffer q % nbuf, this thread
+      // waits until the TMA store of group q+1-nbuf has finished READING its buffer (at most nbuf-2 younger stores
+      // still pending) and hands that buffer out for group q+1.
       mbar_arrive(avail_bar(0));
       for (int q = 0; q < total_q; ++q) {
         if (q + 1 < total_q) {
-          if (q >= 1) tma_store_wait_read<0>();
+          if (q + 1 >= p.nbuf) {
+            if (p.nbuf == 2) tma_store_wait_read<0>();
+            else if (p.nbuf == 3) tma_store_wait_read<1>();
+            else tma_store_wait_read<2>();
+          }
           mbar_arrive(avail_bar((q + 1) % p.nbuf));
         }
         const int b = q % p.nbuf;
@@ -430,6 +538,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
     for (int tile = first_work; tile < total_tiles; tile += work_step) {
       const TileCoord t = decode_tile(p, tile, crank);
+      if (!nchw && lane < 2 * (p.block_n / 64)) {
+        // pull this warp's scale / shift lines (128 B per 32 columns) into L1 while the MMAs of the tile still run
+        const float* line = ((lane & 1) ? p.shift : p.scale) + t.nt * p.block_n + (lane >> 1) * 64 + half * 32;
+        float sink;
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(sink) : "l"(line));
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       if (tile == first_work && threadIdx.x == kEpiWarp0 * 32) UP_STAMP(5);   // first accumulator complete
       tcgen05_after_thread_sync();
@@ -458,68 +572,23 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
       } else {
-        const int groups = p.block_n / 64;
-        for (int g = 0; g < groups; ++g, ++q) {
-          const uint32_t b = q % p.nbuf;
-          const uint32_t buf = staging + b * p.buf_bytes;
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr0 + g * 64 + half * 32, r);
-          const int colbase = t.nt * p.block_n + g * 64 + half * 32;
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + colbase) + j4);
-            const float4 h4 = __ldg(reinterpret_cast<const float4*>(p.shift + colbase) + j4);
-            v[4 * j4 + 0] = fmaf(__uint_as_float(r[4 * j4 + 0]), s4.x, h4.x);
-            v[4 * j4 + 1] = fmaf(__uint_as_float(r[4 * j4 + 1]), s4.y, h4.y);
-            v[4 * j4 + 2] = fmaf(__uint_as_float(r[4 * j4 + 2]), s4.z, h4.z);
-            v[4 * j4 + 3] = fmaf(__uint_as_float(r[4 * j4 + 3]), s4.w, h4.w);
-          }
-          // the staging buffer becomes ours (its previous TMA store has drained)
-          mbar_wait(avail_bar(b), (q / p.nbuf) & 1u);
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const uint32_t chunk = static_cast<uint32_t>(half * 4 + c4) ^ (static_cast<uint32_t>(row) & 7u);
-            const uint32_t addr = buf + rowoff + (chunk << 4);
-            if (p.flags & UP_FLAG_RELU) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[8 * c4 + e] = fmaxf(v[8 * c4 + e], 0.f);
-            }
-            uint32_t w0, w1, w2, w3;
-            if (p.split) {
-              uint16_t hi[8], lo[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) split_bf16(v[8 * c4 + e], hi[e], lo[e]);
-              w0 = hi[0] | (static_cast<uint32_t>(hi[1]) << 16);
-              w1 = hi[2] | (static_cast<uint32_t>(hi[3]) << 16);
-              w2 = hi[4] | (static_cast<uint32_t>(hi[5]) << 16);
-              w3 = hi[6] | (static_cast<uint32_t>(hi[7]) << 16);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
-                           : "memory");
-              w0 = lo[0] | (static_cast<uint32_t>(lo[1]) << 16);
-              w1 = lo[2] | (static_cast<uint32_t>(lo[3]) << 16);
-              w2 = lo[4] | (static_cast<uint32_t>(lo[5]) << 16);
-              w3 = lo[6] | (static_cast<uint32_t>(lo[7]) << 16);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + kPlaneBytes), "r"(w0), "r"(w1),
-                           "r"(w2), "r"(w3)
-                           : "memory");
-            } else {
-              w0 = pack2_rt(v[8 * c4 + 0], v[8 * c4 + 1], fmt);
-              w1 = pack2_rt(v[8 * c4 + 2], v[8 * c4 + 3], fmt);
-              w2 = pack2_rt(v[8 * c4 + 4], v[8 * c4 + 5], fmt);
-              w3 = pack2_rt(v[8 * c4 + 6], v[8 * c4 + 7], fmt);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
-                           : "memory");
-            }
-          }
-          fence_proxy_async_smem();   // make the generic-proxy writes visible to the TMA store
-          __syncwarp();
-          if (lane == 0) mbar_arrive(ready_bar(b));  // one arrival per warp (8) -> the DMA thread stores the group
+        const EpiCtx ec{p.scale + t.nt * p.block_n + half * 32, p.shift + t.nt * p.block_n + half * 32,
+                        taddr0 + static_cast<uint32_t>(half * 32), staging + rowoff, p.buf_bytes,
+                        static_cast<uint32_t>(p.nbuf), static_cast<uint32_t>(half * 4),
+                        static_cast<uint32_t>(row) & 7u, bars + 8u * (2 * kMaxStages + 4), lane, p.block_n / 64};
+        const bool relu = (p.flags & UP_FLAG_RELU) != 0;
+        if (p.split) {
+          if (relu) epi_tile<2, true>(ec, q); else epi_tile<2, false>(ec, q);
+        } else if (fmt == 1) {
+          if (relu) epi_tile<1, true>(ec, q); else epi_tile<1, false>(ec, q);
+        } else {
+          if (relu) epi_tile<0, true>(ec, q); else epi_tile<0, false>(ec, q);
         }
       }
       // all TMEM reads of this accumulator are done -> hand it back to the MMA issuer
       if (tile == first_work && threadIdx.x == kEpiWarp0 * 32) UP_STAMP(6);     // first tile's epilogue math done
+      if (tile == first_work + work_step && threadIdx.x == kEpiWarp0 * 32) UP_STAMP(14);      // second tile's
+      if (tile == first_work + 2 * work_step && threadIdx.x == kEpiWarp0 * 32) UP_STAMP(15);  // third tile's
       tcgen05_before_thread_sync();
       __syncwarp();
       if (lane == 0) {
@@ -692,6 +761,8 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   p.buf_bytes = split ? 2 * kPlaneBytes : kPlaneBytes;
   p.nbuf = nchw ? 0 : 2;
   p.res_terms = has_res ? (split ? 2 : 1) : 0;
+  p.res_per_slot = 1;
+  p.bsplit = 1;
   // cluster along the image-group direction: largest of 4 / 2 that divides tiles_n and leaves >= 8 weight rows per CTA
   p.cluster = 1;
   {
@@ -711,6 +782,10 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
     p.pair = (e && e[0] == '1') ? 1 : 0;   // opt-in: measured slower than independent CTAs on most layers (round 1)
   }
   if (!p.pair && !getenv("UP_CLUSTER")) p.cluster = 1;   // plain multicast clusters measured slower than independent CTAs
+  if (const char* e = getenv("UP_DEBUG_BSPLIT")) {
+    const int v = atoi(e);
+    if (p.cluster == 1 && (v == 2 || v == 4) && block_n % (8 * v) == 0) p.bsplit = v;
+  }
   if (p.pair) p.b_bytes = static_cast<uint32_t>(block_n / 2) * ck * 2;   // each CTA of the pair holds half of the weight tile
   p.idesc = make_idesc_f16(static_cast<uint32_t>(fmt), p.pair ? 256u : kTileM, static_cast<uint32_t>(block_n));
   p.idesc_res = make_idesc_f16(static_cast<uint32_t>(fmt), p.pair ? 256u : kTileM, 64u);
@@ -729,6 +804,20 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   }
   UP_CHECK_ARG(stages >= 2, "up_conv2d_fwd: not enough shared memory for 2 pipeline stages");
   p.stages = stages;
+  if (has_res) {
+    // several 16 KB residual tiles ride in one ring slot (fewer slot round trips per tile)
+    p.res_per_slot = static_cast<int>((p.a_bytes + p.b_bytes) / p.a_bytes);
+    if (const char* e = getenv("UP_DEBUG_RES_PER_SLOT")) p.res_per_slot = atoi(e) >= 1 ? std::min(atoi(e), p.res_per_slot) : 1;
+  }
+  size_t fixed_all = fixed;
+  if (!nchw && !getenv("UP_DEBUG_NBUF")) {
+    // shared memory the operand ring cannot use becomes extra staging buffers (more TMA stores in flight)
+    while (p.nbuf < kMaxBufs &&
+           fixed_all + p.buf_bytes + static_cast<size_t>(stages) * (p.a_bytes + p.b_bytes) <= g_max_smem) {
+      fixed_all += p.buf_bytes;
+      ++p.nbuf;
+    }
+  }
   // NOTE: filled again below once the cluster / pair decision is known
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(2 * block_n)) cols *= 2;
@@ -772,7 +861,7 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
     const int taps = d->kh * d->kw;
     const uint64_t dims[2] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(split ? 2 : 1) * taps * d->cout};
     const uint64_t st[1] = {static_cast<uint64_t>(d->cin) * 2};
-    const uint32_t box[2] = {static_cast<uint32_t>(ck), static_cast<uint32_t>(block_n / p.cluster)};
+    const uint32_t box[2] = {static_cast<uint32_t>(ck), static_cast<uint32_t>(block_n / p.cluster / p.bsplit)};
     if (split) {
       UP_CHECK_ARG(d->w_plane_stride == static_cast<int64_t>(taps) * d->cout * d->cin,
                    "up_conv2d_fwd: split weights must have contiguous planes (w_plane_stride = taps*cout*cin)");
@@ -808,7 +897,7 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   }
 
   const long long total_work = static_cast<long long>(m_tiles / p.cluster) * p.n_tiles;
-  const size_t smem = fixed + static_cast<size_t>(stages) * (p.a_bytes + p.b_bytes);
+  const size_t smem = fixed_all + static_cast<size_t>(stages) * (p.a_bytes + p.b_bytes);
   int max_clusters = g_sm_count / p.cluster;
   if (p.cluster > 1) {
     // persistent kernel: never launch more clusters than can be co-resident

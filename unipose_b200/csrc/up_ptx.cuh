@@ -72,6 +72,18 @@ __device__ __forceinline__ void tcgen05_after_thread_sync() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
+// One lane of a converged warp (elect.sync): lets warp-uniform code issue single-thread instructions (TMA, tcgen05.mma)
+// without the compiler treating the surrounding control flow as divergent.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // Named barrier over a subset of the CTA's threads (id 1..15; 0 is __syncthreads).
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
