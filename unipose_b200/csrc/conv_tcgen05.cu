@@ -778,8 +778,11 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   }
   p.pair = 0;
   if (p.cluster == 2 && block_n >= 64) {
-    const char* e = getenv("UP_PAIR");
-    p.pair = (e && e[0] == '1') ? 1 : 0;   // opt-in: measured slower than independent CTAs on most layers (round 1)
+    // CTA pair (tcgen05 cta_group::2, M = 256): each CTA fetches only half of the weight tile -> fewer L2->SM bytes
+    // per FLOP.  Measured faster than independent CTAs on every layer shape of the network except the HBM-bound
+    // 64->256 expansion of layer1 (-1%), so it is the default wherever a pair can form; UP_PAIR=0 / 1 overrides.
+    p.pair = nchw ? 0 : 1;
+    if (const char* e = getenv("UP_PAIR")) p.pair = (e[0] == '1') ? 1 : 0;
   }
   if (!p.pair && !getenv("UP_CLUSTER")) p.cluster = 1;   // plain multicast clusters measured slower than independent CTAs
   if (const char* e = getenv("UP_DEBUG_BSPLIT")) {
