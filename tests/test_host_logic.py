@@ -6,7 +6,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from unipose_b200.model.modules.backbone.resnet import stem_s2d_weight
+from unipose_b200.model.modules.backbone.resnet import stem_s2d_weight, stem_superpixel_weight
 from unipose_b200.model.unipose import unipose
 from unipose_b200.model import uniposeLSTM
 
@@ -65,6 +65,26 @@ def test_stem_space_to_depth_weights_are_equivalent():
     x2 = torch.cat([x2, x2.new_zeros(n, 4, h // 2, wd // 2)], 1)
     w2 = stem_s2d_weight(w)
     got = F.conv2d(F.pad(x2, (2, 1, 2, 1)), w2)
+    assert torch.allclose(got, ref, atol=1e-12)
+
+
+def test_stem_superpixel_weights_are_equivalent():
+    """The 7x7/s2 stem as a plain 4x2 conv over 64-element super pixels (4 s2d pixels x 16 channels) that emits four
+    adjacent output pixels per position - the layout resnet._emit_image feeds to the tcgen05 kernel."""
+    torch.manual_seed(1)
+    co = 8
+    w = torch.randn(co, 3, 7, 7, dtype=torch.float64)
+    x = torch.randn(2, 3, 32, 48, dtype=torch.float64)
+    ref = F.conv2d(x, w, stride=2, padding=3)                         # [2, co, 16, 24]
+    n, c, h, wd = x.shape
+    x2 = x.view(n, c, h // 2, 2, wd // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(n, 12, h // 2, wd // 2)
+    x2 = torch.cat([x2, x2.new_zeros(n, 4, h // 2, wd // 2)], 1)      # [n, 16, h/2, w/2]
+    ws = wd // 8
+    rows = x2.new_zeros(n, h // 2, (ws + 1) * 4, 16)                  # NHWC rows, 2 zero pixels of left padding
+    rows[:, :, 2:2 + wd // 2] = x2.permute(0, 2, 3, 1)
+    sp = rows.reshape(n, h // 2, ws + 1, 64).permute(0, 3, 1, 2)      # super pixels as channels-first [n,64,h/2,ws+1]
+    got = F.conv2d(F.pad(sp, (0, 0, 2, 1)), stem_superpixel_weight(w))   # [n, 4*co, h/2, ws]
+    got = got.view(n, 4, co, h // 2, ws).permute(0, 2, 3, 4, 1).reshape(n, co, h // 2, wd // 2)
     assert torch.allclose(got, ref, atol=1e-12)
 
 

@@ -94,29 +94,31 @@ class Builder:
         shift = torch.zeros(cout, dtype=torch.float32, device=self.device)
         pc = PackedConv(wbuf, scale, shift, kh, kw, cout, cin, co_r, ci_r, self.mode)
 
-        fold_scale = torch.empty(cout, dtype=torch.float32, device=self.device) if bn is not None else None
+        c_bn = bn.num_features if bn is not None else 0
+        fold_scale = torch.empty(c_bn, dtype=torch.float32, device=self.device) if bn is not None else None
+        fold_shift = torch.empty(c_bn, dtype=torch.float32, device=self.device) if bn is not None else None
 
         def fill():
-            w = conv.weight.detach()
-            if weight_fn is not None:
-                w = weight_fn(w)
-            w = w.float()
+            w = conv.weight.detach().float()
             scale.zero_()
             scale[:co_r] = 1.0
+            shift.zero_()
             if bn is not None:
-                # eval-mode BatchNorm: the per-channel scale is folded into the filter (w' = w * gamma/sqrt(var+eps)),
-                # the shift stays in the epilogue.  The residual of a bottleneck is added inside the tensor-core
-                # pipeline BEFORE the epilogue, so the epilogue itself must not scale.
+                # eval-mode BatchNorm: the per-channel scale is folded into the canonical filter
+                # (w' = w * gamma/sqrt(var+eps)), the shift stays in the epilogue.  The residual of a bottleneck is
+                # added inside the tensor-core pipeline BEFORE the epilogue, so the epilogue itself must not scale.
                 ops._lib.call("up_bn_fold", ops._ptr(bn.weight.detach().float().contiguous()),
                               ops._ptr(bn.bias.detach().float().contiguous()),
                               ops._ptr(bn.running_mean.float().contiguous()),
                               ops._ptr(bn.running_var.float().contiguous()), float(bn.eps), ops._ptr(fold_scale),
-                              ops._ptr(shift), co_r, cout, ops._stream())
-                w = w * fold_scale[:co_r].view(-1, 1, 1, 1)
-            else:
-                shift.zero_()
-                if conv.bias is not None:
-                    shift[:co_r] = conv.bias.detach().float()
+                              ops._ptr(fold_shift), c_bn, c_bn, ops._stream())
+                w = w * fold_scale.view(-1, 1, 1, 1)
+                # a weight_fn may replicate the output channels (the stem's 4 pixels per super pixel): tile the shift
+                shift[:co_r] = fold_shift.repeat(co_r // c_bn)
+            elif conv.bias is not None:
+                shift[:co_r] = conv.bias.detach().float().repeat(co_r // conv.bias.numel())
+            if weight_fn is not None:
+                w = weight_fn(w)
             w = w.contiguous()
             ops._lib.call("up_pack_conv_weight", ops._ptr(w), ops._ptr(wbuf), co_r, ci_r, kh, kw, cout, cin, self.mode,
                           kh * kw * cout * cin, ops._stream())

@@ -41,6 +41,25 @@ def stem_window_weight(w):
     return w2.permute(0, 3, 1, 2).reshape(w.shape[0], 64, 4, 1).contiguous()   # cin index = kw' * 16 + ch
 
 
+def stem_superpixel_weight(w):
+    """[co,3,7,7] stride-2 stem filter -> [4*co, 64, 4, 2]: an ORDINARY 4x2 stride-1 convolution that produces four
+    horizontally adjacent output pixels (x = 4s .. 4s+3) at once from the space-to-depth image regrouped into
+    "super pixels" of 4 s2d pixels x 16 channels = 64 contiguous elements (128 aligned bytes).
+
+    Output channel j*co + o is output pixel 4s+j, channel o; input element p*16 + ch of tap (a, kw) is s2d pixel
+    4(s+kw) + p - 2 (the rows carry 2 zero pixels of left padding), i.e. horizontal s2d tap b = 4*kw + p - j."""
+    w2 = stem_s2d_weight(w)                                    # [co, 16, a, b]
+    co = w.shape[0]
+    out = w.new_zeros((4 * co, 64, 4, 2))
+    for j in range(4):
+        for kw in range(2):
+            for pp in range(4):
+                b = 4 * kw + pp - j
+                if 0 <= b < 4:
+                    out[j * co:(j + 1) * co, pp * 16:(pp + 1) * 16, :, kw] = w2[:, :, :, b]
+    return out
+
+
 class Bottleneck(PlanModule):
     expansion = 4
 
@@ -138,13 +157,16 @@ class ResNet(PlanModule):
         n, _, h, w = x_static.shape
         if h % 16 or w % 16:
             raise ValueError('unipose_b200: input height/width must be multiples of 16 (got %dx%d)' % (h, w))
-        # rows padded by 2 zero pixels on the left and 1 on the right: the 4 horizontal taps x 16 channels of an
-        # output pixel are then 64 CONTIGUOUS elements -> one 128-byte K-chunk per filter row (x_window below)
-        x2 = b.act(n, h // 2, w // 2 + 3, 16, zero=True)
+        # Super-pixel stem: the 2x2 space-to-depth image (16 channels, rows padded by 2 zero pixels on the left) is
+        # read as [n, h/2, w/8 + 1, 64] - four s2d pixels per 128-byte "super pixel" - and the 7x7/s2 conv becomes a
+        # plain 4x2 stride-1 conv with 4*64 outputs = four adjacent output pixels (stem_superpixel_weight).  Every
+        # activation row the TMA fetches is 128 aligned bytes and is shared by 4 outputs.
+        ws = w // 8
+        x2 = b.act(n, h // 2, ws + 1, 64, zero=True)
         b.add(lambda x_static=x_static, x2=x2: ops.pack_input_s2d(x_static, x2, wpad_left=2), "pack_input_s2d")
         stem = b.act(n, h // 2, w // 2, 64)
-        pc = b.packed_conv(self.conv1, self.bn1, cin_pad=64, weight_fn=stem_window_weight)
-        b.conv(x2, pc, stem, "stem", pad=(2, 0), relu=True, ho=h // 2, wo=w // 2, x_window=(w // 2, 64))
+        pc = b.packed_conv(self.conv1, self.bn1, cin_pad=64, weight_fn=stem_superpixel_weight)
+        b.conv(x2, pc, stem.reshaped(h // 2, ws, 256), "stem", pad=(2, 0), relu=True, ho=h // 2, wo=ws)
         x = b.act(n, h // 4, w // 4, 64)
         b.add(lambda stem=stem, x=x: ops.maxpool3x3s2(stem, x), "maxpool")
         low = None

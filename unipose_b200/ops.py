@@ -62,6 +62,14 @@ class Act:
     def ptr(self, n_off: int = 0) -> ctypes.c_void_p:
         return ctypes.c_void_p(self.t.data_ptr() + 2 * n_off * self.h * self.w * self.c)
 
+    def reshaped(self, h: int, w: int, c: int) -> "Act":
+        """Alias of the same storage with another (h, w, c) factorisation of an image's elements."""
+        assert h * w * c == self.h * self.w * self.c and c % 8 == 0
+        a = object.__new__(Act)
+        a.n, a.h, a.w, a.c, a.mode = self.n, h, w, c, self.mode
+        a.t = self.t.view(self.t.shape[0], self.n, h, w, c)
+        return a
+
     def to_float(self) -> torch.Tensor:
         """[n, h, w, c] fp32 (hi + lo in split mode) - for tests."""
         f = self.t.float()
@@ -211,10 +219,13 @@ def conv2d(x, pc: PackedConv, y, *, stride: int = 1, dil: int = 1, pad=None, rel
 # bandwidth kernels
 # ---------------------------------------------------------------------------------------------
 def pack_input_s2d(x_nchw: torch.Tensor, y: Act, wpad_left: int = 0) -> None:
-    """fp32 NCHW image -> 2x2 space-to-depth NHWC16; `y` may have padded rows (y.w >= w/2 + wpad_left)."""
+    """fp32 NCHW image -> 2x2 space-to-depth NHWC16; `y` may have padded rows (row pitch >= w/2 + wpad_left s2d
+    pixels) and may group k s2d pixels per buffer pixel (y.c = 16*k, e.g. the stem's 64-element super pixels)."""
     n, c, h, w = x_nchw.shape
-    assert c == 3 and (y.n, y.h, y.c) == (n, h // 2, 16) and y.w >= w // 2 + wpad_left
-    _lib.call("up_pack_input_s2d", _ptr(x_nchw), y.ptr(), n, h, w, y.mode, y.plane_stride, y.w, wpad_left, _stream())
+    assert c == 3 and (y.n, y.h) == (n, h // 2) and y.c % 16 == 0
+    wpitch = y.w * (y.c // 16)
+    assert wpitch >= w // 2 + wpad_left
+    _lib.call("up_pack_input_s2d", _ptr(x_nchw), y.ptr(), n, h, w, y.mode, y.plane_stride, wpitch, wpad_left, _stream())
 
 
 def nchw_to_act(x: torch.Tensor, y, c_real: Optional[int] = None) -> None:
