@@ -234,19 +234,23 @@ typedef struct UpView {
  *   up_bn_finalize  batch mean / biased var -> scale, shift, save_mean, save_invstd; running stats updated with
  *                   momentum and the unbiased variance (torch semantics); running_* may be NULL
  *   up_scale_shift_act  y = [relu](z*scale + shift (+ residual)) (* mask)   (mask = pre-scaled dropout mask) */
-int up_bn_stats(const UpView* z, int64_t npix, int c, int dtype, double* sums, void* stream);
+/* Every BatchNorm reduction works in a caller-owned buffer of up_bn_work_doubles(c) doubles:
+ *   [0, 2c) the two per-channel sums | [2c, 4c) coefficient scratch of the backward | partial rows (one per block). */
+int64_t up_bn_work_doubles(int c);
+int up_bn_stats(const UpView* z, int64_t npix, int c, int dtype, double* work, void* stream);
 int up_bn_finalize(const double* sums, int64_t count, const float* gamma, const float* beta, float* running_mean,
                    float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
                    float* save_invstd, int c_real, int c, void* stream);
 int up_scale_shift_act(const UpView* z, const UpView* y, const UpView* residual, const UpView* mask,
                        const float* scale, const float* shift, int64_t npix, int c, int relu, int dtype,
                        void* stream);
-/* BatchNorm (+ReLU) backward: reduce sum(dy'), sum(dy'*xhat) with dy' = dy*(y>0) -> sums[2*c]; then
- *   dz = gamma*invstd*(dy' - sum_dy/M - xhat*sum_dy_xhat/M), optional dres = dy', dgamma / dbeta (optional). */
+/* BatchNorm (+ReLU) backward: reduce sum(dy'), sum(dy'*xhat) with dy' = dy*(y>0) -> work[0 .. 2*c); then
+ *   dz = gamma*invstd*(dy' - sum_dy/M - xhat*sum_dy_xhat/M), optional dres = dy', dgamma / dbeta (optional).
+ * `work` holds up_bn_work_doubles(c) doubles (see up_bn_stats). */
 int up_bn_bwd_reduce(const UpView* dy, const UpView* y, const UpView* z, const float* save_mean,
-                     const float* save_invstd, int64_t npix, int c, int relu, int dtype, double* sums, void* stream);
+                     const float* save_invstd, int64_t npix, int c, int relu, int dtype, double* work, void* stream);
 int up_bn_bwd_apply(const UpView* dy, const UpView* y, const UpView* z, const UpView* dz, const UpView* dres,
-                    const float* save_mean, const float* save_invstd, const float* gamma, const double* sums,
+                    const float* save_mean, const float* save_invstd, const float* gamma, double* work,
                     int64_t npix, int c_real, int c, int relu, int dtype, float* dgamma, float* dbeta, void* stream);
 /* out (+)= a            (mode_op 0)
  * out (+)= a * m        (mode_op 1, dropout mask)

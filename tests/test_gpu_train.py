@@ -147,3 +147,23 @@ def test_fused_train_step_matches_manual_adam():
         agree = (torch.sign(upd) == torch.sign(ref_upd)).float().mean()
         assert agree > 0.97, (k, float(agree))
     assert torch.equal(after["decoder.conv2.weight"].detach().cpu(), before["decoder.conv2.weight"].cpu())
+
+
+def test_train_step_graph_replay_matches_eager(monkeypatch):
+    """From the third step on forward + loss + backward replay as one CUDA graph: same losses and weights as eager."""
+    from unipose_b200 import train
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("UNIPOSE_B200_TRAIN_GRAPH", flag)
+        m, sd, x, target, masks = _setup(n=2, size=96, seed=4, precision="bf16")
+        for mod in m.modules():     # dropout off: the two runs must see the same network
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        ts = train.TrainStep(m, lr=1e-4)
+        xc, tc = x.cuda(), target.cuda()
+        losses = [float(ts.step(xc, tc)) for _ in range(5)]
+        assert (ts.graph is not None) == (flag == "1")
+        out[flag] = (losses, dict(m.named_parameters())["wasp.conv1.weight"].detach().clone())
+    assert out["0"][0] == out["1"][0], out
+    assert torch.equal(out["0"][1], out["1"][1])
+    assert out["1"][0][-1] < out["1"][0][0]

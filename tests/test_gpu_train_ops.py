@@ -133,7 +133,7 @@ def test_batchnorm_train_forward_backward(prec, c, relu, res):
     zq = za.to_float().permute(0, 3, 1, 2).double().requires_grad_(True)
     rq = ra.to_float().permute(0, 3, 1, 2).double().requires_grad_(True)
     dyq = dya.to_float().permute(0, 3, 1, 2).double()
-    sums = torch.zeros(2 * c, dtype=torch.float64, device=dev)
+    sums = torch.zeros(ops.bn_work_doubles(c), dtype=torch.float64, device=dev)
     scale, shift, mean, invstd = (torch.empty(c, device=dev) for _ in range(4))
     rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
     ops.bn_stats(za, c, sums)

@@ -10,6 +10,7 @@ ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--size", type=int, default=384)
 ap.add_argument("--precision", default="bf16")
 ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--warmup", type=int, default=4)
 a = ap.parse_args()
 with warnings.catch_warnings():
     warnings.simplefilter("ignore")
@@ -19,7 +20,7 @@ m = m.cuda().train()
 x = synth.mpii_like_input(a.batch, a.size, a.size).cuda()
 t = torch.rand(a.batch, 17, a.size // 8, a.size // 8, device="cuda")
 ts = train.TrainStep(m)
-for _ in range(2):
+for _ in range(a.warmup):     # eager warm-up, then the graph capture of forward + loss + backward
     loss = ts.step(x, t)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

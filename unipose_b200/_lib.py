@@ -77,7 +77,8 @@ _SIGNATURES = {
     "up_add_broadcast": [_P, _P, _I, _I, _I, _F, _I, _I, _P],
     "up_zero_insert2x": [_P, _P, _I, _I, _I, _I, _I, _P],
 }
-_RESTYPES = {"up_conv2d_wgrad_scratch_bytes": (c_int64, [POINTER(UpConvDesc)])}
+_RESTYPES = {"up_conv2d_wgrad_scratch_bytes": (c_int64, [POINTER(UpConvDesc)]),
+             "up_bn_work_doubles": (c_int64, [_I])}
 
 
 class UpView(ctypes.Structure):

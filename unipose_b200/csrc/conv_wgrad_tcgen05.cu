@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(256, 1)
   const int a_boxes = 2;                         // 128 cout = 2 x 64
   const int b_boxes = p.block_n / p.ckx;         // cin block = b_boxes x ckx
 
-  if (threadIdx.x == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (converged warp, one elected lane issues) =====================
     int s = 0;
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -156,16 +156,19 @@ __global__ void __launch_bounds__(256, 1)
           mbar_wait(empty_bar(s), phase ^ 1u);
           const uint32_t a_dst = smem_base + s * stage_bytes;
           const uint32_t b_dst = a_dst + p.a_bytes;
-          mbar_arrive_expect_tx(full_bar(s), stage_bytes);
-          const CUtensorMap* mz = (term == 1) ? &tmZ1 : &tmZ0;
-          const CUtensorMap* mx = (term == 2) ? &tmX1 : &tmX0;
-          for (int bx = 0; bx < a_boxes; ++bx) {
-            tma_load_5d(mz, a_dst + bx * p.a_box_bytes, full_bar(s), it.cob * 128 + bx * 64, w0, 0, h0, n0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+            const CUtensorMap* mz = (term == 1) ? &tmZ1 : &tmZ0;
+            const CUtensorMap* mx = (term == 2) ? &tmX1 : &tmX0;
+            for (int bx = 0; bx < a_boxes; ++bx) {
+              tma_load_5d(mz, a_dst + bx * p.a_box_bytes, full_bar(s), it.cob * 128 + bx * 64, w0, 0, h0, n0);
+            }
+            for (int bx = 0; bx < b_boxes; ++bx) {
+              tma_load_5d(mx, b_dst + bx * p.b_box_bytes, full_bar(s), p.x_coff + cc0 + bx * p.ckx + pw * p.x_cs, cw,
+                          ph, ch, n0 + g * p.group_nstride);
+            }
           }
-          for (int bx = 0; bx < b_boxes; ++bx) {
-            tma_load_5d(mx, b_dst + bx * p.b_box_bytes, full_bar(s), p.x_coff + cc0 + bx * p.ckx + pw * p.x_cs, cw, ph,
-                        ch, n0 + g * p.group_nstride);
-          }
+          __syncwarp();
           if (++s == p.stages) {
             s = 0;
             phase ^= 1u;
@@ -173,8 +176,8 @@ __global__ void __launch_bounds__(256, 1)
         }
       }
     }
-  } else if (threadIdx.x == 32) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp, one elected lane issues) =====================
     int s = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -204,12 +207,15 @@ __global__ void __launch_bounds__(256, 1)
           // 16 pixels (two 8-row K atoms) per MMA
           const uint32_t a_step = (2u * 8u * 128u) >> 4;
           const uint32_t b_step = (2u * 8u * swz_b) >> 4;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kWgPix / 16; ++k) {
-            umma_f16(tmem_d, adesc + a_step * k, bdesc + b_step * k, p.idesc, accumulate);
-            accumulate = 1;
+            for (int k = 0; k < kWgPix / 16; ++k) {
+              umma_f16(tmem_d, adesc + a_step * k, bdesc + b_step * k, p.idesc, (accumulate | k) ? 1u : 0u);
+            }
+            umma_commit(empty_bar(s));
           }
-          umma_commit(empty_bar(s));
+          __syncwarp();
+          accumulate = 1;
           if (++s == p.stages) {
             s = 0;
             phase ^= 1u;
@@ -220,7 +226,8 @@ __global__ void __launch_bounds__(256, 1)
         // every pixel tile of this (tap, split) was out of bounds: nothing was accumulated, the
         // epilogue must write zeros -> flag it through the (otherwise unused) top bit of acc slot
       }
-      umma_commit(tfull_bar(acc));
+      if (elect_one()) umma_commit(tfull_bar(acc));
+      __syncwarp();
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;

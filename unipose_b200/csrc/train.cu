@@ -142,9 +142,9 @@ struct TViewW {
 // over pixels; partial sums are combined in shared memory and added to the global double accumulators.
 // kWhat 0: sums of (x, x^2).  kWhat 1: sums of (dy', dy' * xhat) with dy' = dy * (y > 0 if relu).
 template <int kMode, int kWhat>
-__global__ void channel_reduce_kernel(TView a, TView b, TView c, const float* __restrict__ mean,
-                                      const float* __restrict__ invstd, double* __restrict__ sums, long long npix,
-                                      int ch, int relu) {
+__global__ void __launch_bounds__(512)
+    channel_reduce_kernel(TView a, TView b, TView c, const float* __restrict__ mean, const float* __restrict__ invstd,
+                          float* __restrict__ rows, long long npix, int ch, int relu) {
   const int octs = ch / 8;
   const int oct = threadIdx.x % octs;
   const int pstride = blockDim.x / octs;
@@ -163,28 +163,44 @@ __global__ void channel_reduce_kernel(TView a, TView b, TView c, const float* __
   const long long per_block = (npix + gridDim.x - 1) / gridDim.x;
   const long long p0 = blockIdx.x * per_block;
   const long long p1 = min(p0 + per_block, npix);
-  for (long long px = p0 + plane_lane; px < p1; px += pstride) {
-    float va[8];
-    t_load8<kMode>(a.p + px * a.cs + a.coff + oct * 8, a.plane, va);
-    if (kWhat == 0) {
+  constexpr int kUnroll = 4;   // pixels in flight per thread: the loads of one iteration are all issued before any use
+  for (long long px0 = p0 + plane_lane; px0 < p1; px0 += static_cast<long long>(kUnroll) * pstride) {
+    float va[kUnroll][8], vz[kUnroll][8], vy[kUnroll][8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        s0[e] += va[e];
-        s1[e] = fmaf(va[e], va[e], s1[e]);
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long px = px0 + static_cast<long long>(u) * pstride;
+      if (px < p1) {
+        t_load8<kMode>(a.p + px * a.cs + a.coff + oct * 8, a.plane, va[u]);
+        if (kWhat == 1) {
+          t_load8<kMode>(c.p + px * c.cs + c.coff + oct * 8, c.plane, vz[u]);
+          if (relu) t_load8<kMode>(b.p + px * b.cs + b.coff + oct * 8, b.plane, vy[u]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          va[u][e] = 0.f;
+          vz[u][e] = 0.f;
+          vy[u][e] = 1.f;
+        }
       }
-    } else {
-      float vz[8];
-      t_load8<kMode>(c.p + px * c.cs + c.coff + oct * 8, c.plane, vz);
-      if (relu) {
-        float vy[8];
-        t_load8<kMode>(b.p + px * b.cs + b.coff + oct * 8, b.plane, vy);
+    }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) va[e] = vy[e] > 0.f ? va[e] : 0.f;
-      }
+    for (int u = 0; u < kUnroll; ++u) {
+      if (kWhat == 0) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        s0[e] += va[e];
-        s1[e] = fmaf(va[e], (vz[e] - mu[e]) * is[e], s1[e]);
+        for (int e = 0; e < 8; ++e) {
+          s0[e] += va[u][e];
+          s1[e] = fmaf(va[u][e], va[u][e], s1[e]);
+        }
+      } else {
+        const bool live = px0 + static_cast<long long>(u) * pstride < p1;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float d = va[u][e];
+          if (relu) d = vy[u][e] > 0.f ? d : 0.f;
+          s0[e] += d;
+          s1[e] = fmaf(d, live ? (vz[u][e] - mu[e]) * is[e] : 0.f, s1[e]);
+        }
       }
     }
   }
@@ -195,13 +211,22 @@ __global__ void channel_reduce_kernel(TView a, TView b, TView c, const float* __
     red[threadIdx.x * 16 + 8 + e] = s1[e];
   }
   __syncthreads();
+  // every block owns one row of partial sums (no atomics, deterministic); reduce_rows_kernel adds the rows up
   for (int idx = threadIdx.x; idx < octs * 16; idx += blockDim.x) {
     const int o = idx / 16, e = idx % 16;
     double s = 0.0;
     for (int q = 0; q < pstride; ++q) s += red[(q * octs + o) * 16 + e];
     const int chn = o * 8 + (e & 7);
-    atomicAdd(sums + (e < 8 ? 0 : ch) + chn, s);
+    rows[static_cast<long long>(blockIdx.x) * 2 * ch + (e < 8 ? 0 : ch) + chn] = static_cast<float>(s);
   }
+}
+
+__global__ void reduce_rows_kernel(const float* __restrict__ rows, int nrows, int c2, double* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c2) return;
+  double s = 0.0;
+  for (int r = 0; r < nrows; ++r) s += rows[static_cast<long long>(r) * c2 + i];
+  sums[i] = s;
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
@@ -268,11 +293,10 @@ __global__ void scale_shift_act_kernel(TView z, TViewW y, TView res, TView mask,
 }
 
 // dz = gamma*invstd * ( dy' - sum_dy/M - xhat * sum_dy_xhat/M ),  dy' = dy * (y > 0 if relu);  optional dres = dy'
+// The per-channel part is folded once (bn_bwd_coef_kernel, double arithmetic) into dz = k1*dy' + k2*z + k3.
 template <int kMode>
-__global__ void bn_bwd_apply_kernel(TView dy, TView y, TView z, TViewW dz, TViewW dres, const float* __restrict__ mean,
-                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                    const double* __restrict__ sums, double count, long long npix, int ch, int c_real,
-                                    int relu, int has_dres) {
+__global__ void bn_bwd_apply_kernel(TView dy, TView y, TView z, TViewW dz, TViewW dres, const float* __restrict__ coef,
+                                    long long npix, int ch, int relu, int has_dres) {
   const int c8 = ch / 8;
   const long long total = npix * c8;
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -288,20 +312,38 @@ __global__ void bn_bwd_apply_kernel(TView dy, TView y, TView z, TViewW dz, TView
 #pragma unroll
     for (int e = 0; e < 8; ++e) vd[e] = vy[e] > 0.f ? vd[e] : 0.f;
   }
+  const float4* k1 = reinterpret_cast<const float4*>(coef + g * 8);
+  const float4* k2 = reinterpret_cast<const float4*>(coef + ch + g * 8);
+  const float4* k3 = reinterpret_cast<const float4*>(coef + 2 * ch + g * 8);
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = g * 8 + e;
-    if (c < c_real) {
-      const float xhat = (vz[e] - mean[c]) * invstd[c];
-      const float m0 = static_cast<float>(sums[c] / count);
-      const float m1 = static_cast<float>(sums[ch + c] / count);
-      o[e] = gamma[c] * invstd[c] * (vd[e] - m0 - xhat * m1);
-    } else {
-      o[e] = 0.f;
-    }
+  for (int q = 0; q < 2; ++q) {
+    const float4 a = __ldg(k1 + q), b = __ldg(k2 + q), c = __ldg(k3 + q);
+    o[4 * q + 0] = fmaf(a.x, vd[4 * q + 0], fmaf(b.x, vz[4 * q + 0], c.x));
+    o[4 * q + 1] = fmaf(a.y, vd[4 * q + 1], fmaf(b.y, vz[4 * q + 1], c.y));
+    o[4 * q + 2] = fmaf(a.z, vd[4 * q + 2], fmaf(b.z, vz[4 * q + 2], c.z));
+    o[4 * q + 3] = fmaf(a.w, vd[4 * q + 3], fmaf(b.w, vz[4 * q + 3], c.w));
   }
   t_store8<kMode>(dz.p + px * dz.cs + dz.coff + g * 8, dz.plane, o);
   if (has_dres) t_store8<kMode>(dres.p + px * dres.cs + dres.coff + g * 8, dres.plane, vd);
+}
+
+// k1 = gamma*invstd, k2 = -k1*invstd*m1, k3 = -k1*m0 - k2*mean with m0 = sum_dy/M, m1 = sum_dy_xhat/M; padded
+// channels get zeros.  coef = [k1 | k2 | k3], c floats each.
+__global__ void bn_bwd_coef_kernel(const double* __restrict__ sums, double count, const float* __restrict__ mean,
+                                   const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                   float* __restrict__ coef, int c_real, int c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  double k1 = 0.0, k2 = 0.0, k3 = 0.0;
+  if (i < c_real) {
+    const double m0 = sums[i] / count, m1 = sums[c + i] / count;
+    k1 = static_cast<double>(gamma[i]) * invstd[i];
+    k2 = -k1 * invstd[i] * m1;
+    k3 = -k1 * m0 - k2 * mean[i];
+  }
+  coef[i] = static_cast<float>(k1);
+  coef[c + i] = static_cast<float>(k2);
+  coef[2 * c + i] = static_cast<float>(k3);
 }
 
 __global__ void bn_bwd_params_kernel(const double* __restrict__ sums, float* __restrict__ dgamma,
@@ -545,6 +587,17 @@ static int check_view(const char* who, const UpView* v, int c) {
   return 0;
 }
 static inline int blocks_for(long long total) { return static_cast<int>((total + 255) / 256); }
+// Per-channel reductions: blocks of 512 threads, ~16 pixel-octets per thread (4 iterations of 4 loads in flight), at
+// most kBnRows = 296 blocks (2 per SM).  Block b writes its partial sums to row b of the work buffer.
+constexpr int kBnRows = 296;
+static inline int reduce_grid(long long npix, int octs) {
+  long long g = (npix * octs + 512LL * 16 - 1) / (512LL * 16);
+  if (g > kBnRows) g = kBnRows;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+// work buffer layout (doubles): [0, 2c) sums | [2c, 4c) coefficient scratch | [4c, 4c + kBnRows*c) partial rows
+extern "C" int64_t up_bn_work_doubles(int c) { return static_cast<int64_t>(4 + kBnRows) * c; }
 
 extern "C" int up_bn_stats(const UpView* x, int64_t npix, int c, int dtype, double* sums, void* stream) {
   int rc = check_view("up_bn_stats", x, c);
@@ -553,13 +606,13 @@ extern "C" int up_bn_stats(const UpView* x, int64_t npix, int c, int dtype, doub
   const int octs = c / 8;
   UP_CHECK_ARG(octs <= 256 && (octs & (octs - 1)) == 0, "up_bn_stats: c/8 must be a power of two <= 256 (c = %d)", c);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = up::check_cuda(cudaMemsetAsync(sums, 0, 2 * c * sizeof(double), st), "cudaMemsetAsync(bn sums)");
-  if (rc) return rc;
-  long long grid = (npix + 255) / 256;
-  if (grid > 1184) grid = 1184;
-  UP_T_DISPATCH(dtype, (up::channel_reduce_kernel<kMode, 0><<<static_cast<int>(grid), 256, 256 * 16 * sizeof(float), st>>>(
-                           tv(x), up::TView{}, up::TView{}, nullptr, nullptr, sums, npix, c, 0)));
+  const int grid = reduce_grid(npix, octs);
+  float* rows = reinterpret_cast<float*>(sums + 4 * c);
+  UP_T_DISPATCH(dtype, (up::channel_reduce_kernel<kMode, 0><<<grid, 512, 512 * 16 * sizeof(float), st>>>(
+                           tv(x), up::TView{}, up::TView{}, nullptr, nullptr, rows, npix, c, 0)));
   UP_CHECK_LAUNCH("channel_reduce_kernel<stats>");
+  up::reduce_rows_kernel<<<(2 * c + 127) / 128, 128, 0, st>>>(rows, grid, 2 * c, sums);
+  UP_CHECK_LAUNCH("reduce_rows_kernel");
   return 0;
 }
 
@@ -604,19 +657,19 @@ extern "C" int up_bn_bwd_reduce(const UpView* dy, const UpView* y, const UpView*
   UP_CHECK_ARG(octs <= 256 && (octs & (octs - 1)) == 0, "up_bn_bwd_reduce: c/8 must be a power of two <= 256");
   UP_CHECK_ARG(save_mean && save_invstd && sums && npix > 0, "up_bn_bwd_reduce: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = up::check_cuda(cudaMemsetAsync(sums, 0, 2 * c * sizeof(double), st), "cudaMemsetAsync(bn bwd sums)");
-  if (rc) return rc;
-  long long grid = (npix + 255) / 256;
-  if (grid > 1184) grid = 1184;
-  UP_T_DISPATCH(dtype, (up::channel_reduce_kernel<kMode, 1><<<static_cast<int>(grid), 256, 256 * 16 * sizeof(float), st>>>(
-                           tv(dy), tv(y), tv(z), save_mean, save_invstd, sums, npix, c, relu)));
+  const int grid = reduce_grid(npix, octs);
+  float* rows = reinterpret_cast<float*>(sums + 4 * c);
+  UP_T_DISPATCH(dtype, (up::channel_reduce_kernel<kMode, 1><<<grid, 512, 512 * 16 * sizeof(float), st>>>(
+                           tv(dy), tv(y), tv(z), save_mean, save_invstd, rows, npix, c, relu)));
   UP_CHECK_LAUNCH("channel_reduce_kernel<bn bwd>");
+  up::reduce_rows_kernel<<<(2 * c + 127) / 128, 128, 0, st>>>(rows, grid, 2 * c, sums);
+  UP_CHECK_LAUNCH("reduce_rows_kernel");
   return 0;
 }
 
 extern "C" int up_bn_bwd_apply(const UpView* dy, const UpView* y, const UpView* z, const UpView* dz,
                                const UpView* dres, const float* save_mean, const float* save_invstd,
-                               const float* gamma, const double* sums, int64_t npix, int c_real, int c, int relu,
+                               const float* gamma, double* sums, int64_t npix, int c_real, int c, int relu,
                                int dtype, float* dgamma, float* dbeta, void* stream) {
   int rc = check_view("up_bn_bwd_apply(dy)", dy, c);
   if (rc) return rc;
@@ -628,9 +681,13 @@ extern "C" int up_bn_bwd_apply(const UpView* dy, const UpView* y, const UpView* 
   if (dres && (rc = check_view("up_bn_bwd_apply(dres)", dres, c))) return rc;
   UP_CHECK_ARG(save_mean && save_invstd && gamma && sums && npix > 0 && c_real <= c, "up_bn_bwd_apply: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // per-channel coefficients: 3*c floats right behind the 2*c reduction doubles (the work buffer holds 4*c doubles)
+  float* coef = reinterpret_cast<float*>(sums + 2 * c);
+  up::bn_bwd_coef_kernel<<<(c + 127) / 128, 128, 0, st>>>(sums, static_cast<double>(npix), save_mean, save_invstd, gamma,
+                                                           coef, c_real, c);
+  UP_CHECK_LAUNCH("bn_bwd_coef_kernel");
   UP_T_DISPATCH(dtype, (up::bn_bwd_apply_kernel<kMode><<<blocks_for(npix*(c / 8)), 256, 0, st>>>(
-                           tv(dy), tv(y), tv(z), tvw(dz), tvw(dres), save_mean, save_invstd, gamma, sums,
-                           static_cast<double>(npix), npix, c, c_real, relu, dres != nullptr)));
+                           tv(dy), tv(y), tv(z), tvw(dz), tvw(dres), coef, npix, c, relu, dres != nullptr)));
   UP_CHECK_LAUNCH("bn_bwd_apply_kernel");
   if (dgamma && dbeta) {
     up::bn_bwd_params_kernel<<<(c_real + 127) / 128, 128, 0, st>>>(sums, dgamma, dbeta, c_real, c);

@@ -338,8 +338,14 @@ def conv2d_wgrad(d: UpConvDesc, x, dz, dw: torch.Tensor, scratch: torch.Tensor, 
               _ptr(scratch), scratch.numel() * scratch.element_size(), 1 if accumulate else 0, _stream())
 
 
+def bn_work_doubles(c: int) -> int:
+    """Size (in doubles) of the work buffer every BatchNorm reduction of `c` channels needs (sums, scratch, rows)."""
+    return int(_lib.load().up_bn_work_doubles(int(c)))
+
+
 def bn_stats(z, c: int, sums: torch.Tensor) -> None:
     zv = as_view(z)
+    assert sums.numel() >= bn_work_doubles(c), "bn_stats: work buffer smaller than ops.bn_work_doubles(c)"
     _lib.call("up_bn_stats", _vref(zv), zv.n * zv.h * zv.w, c, zv.act.mode, _ptr(sums), _stream())
 
 
@@ -360,6 +366,7 @@ def scale_shift_act(z, y, scale, shift, *, relu: bool, residual=None, mask=None)
 def bn_bwd(dy, y, z, dz, dres, save_mean, save_invstd, gamma, sums, c_real: int, relu: bool, dgamma, dbeta) -> None:
     dv = as_view(dy)
     npix = dv.n * dv.h * dv.w
+    assert sums.numel() >= bn_work_doubles(dv.c), "bn_bwd: work buffer smaller than ops.bn_work_doubles(c)"
     _lib.call("up_bn_bwd_reduce", _vref(dv), _vref(y) if relu else None, _vref(z), _ptr(save_mean), _ptr(save_invstd),
               npix, dv.c, 1 if relu else 0, dv.act.mode, _ptr(sums), _stream())
     _lib.call("up_bn_bwd_apply", _vref(dv), _vref(y) if relu else None, _vref(z), _vref(dz), _vref(dres),

@@ -16,6 +16,8 @@ flat gradient buffer, up_adam_step.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -177,7 +179,7 @@ class TrainPlan:
                 raise NotImplementedError("conv without BatchNorm only supports a plain (bias) epilogue in training")
         else:
             c = cout
-            sums = self.tensor((2 * c,), dtype=torch.float64)
+            sums = self.tensor((ops.bn_work_doubles(c),), dtype=torch.float64)   # sums + scratch + partial rows
             scale, shift, mean, invstd = (self.tensor((c,)) for _ in range(4))
             y = out if out is not None else self.act(n, ho, wo, cout)
             count = n * ho * wo
@@ -199,7 +201,7 @@ class TrainPlan:
             dheat = self.dheat
             self.bwd.append(lambda: ops.nchw_to_act(dheat, dz))
             if conv.bias is not None:
-                bsums = self.tensor((2 * cout,), dtype=torch.float64)
+                bsums = self.tensor((ops.bn_work_doubles(cout),), dtype=torch.float64)
                 gb = self.param_grad(conv.bias)
                 self.bwd.append(lambda: ops.bn_stats(dz, cout, bsums))
                 self.bwd.append(lambda: gb.copy_(bsums[:r["co_r"]]))
@@ -542,17 +544,40 @@ class TrainStep:
         self.loss = torch.zeros(1, dtype=torch.float32, device=x.device)
         self.loss_scratch = torch.zeros(1, dtype=torch.float64, device=x.device)
 
-    def step(self, x: torch.Tensor, target: torch.Tensor, lr: Optional[float] = None) -> torch.Tensor:
-        from . import parallel
-        if self.plan is None:
-            self._setup(x)
+    def _fwd_loss_bwd(self, target: torch.Tensor, world: int) -> None:
         p = self.plan
-        heat = p.run_forward(x)
-        world = parallel.world()[1]
+        heat = p.run_forward(p.input)
         ops._lib.call("up_mse_fwd_bwd", ops._ptr(heat), ops._ptr(target), ops._ptr(self.loss), ops._ptr(p.dheat),
                       ops._ptr(self.loss_scratch), heat.numel(), 1.0 / world, ops._stream())
         for op in p.bwd:
             op()
+
+    def step(self, x: torch.Tensor, target: torch.Tensor, lr: Optional[float] = None) -> torch.Tensor:
+        from . import parallel
+        if self.plan is None:
+            self._setup(x)
+            self.target_buf = torch.empty_like(target, dtype=torch.float32)
+            self.graph = None
+            self.steps_done = 0
+            # forward + loss + backward (~2000 launches) replay as ONE CUDA graph from the third step on; the
+            # all-reduce and Adam (step-dependent bias correction) stay eager.  UNIPOSE_B200_TRAIN_GRAPH=0 disables.
+            self.use_graph = (os.environ.get("UNIPOSE_B200_TRAIN_GRAPH", "1") != "0" and
+                              self.plan.mode != ops.UP_SPLIT)
+        p = self.plan
+        world = parallel.world()[1]
+        p.input.copy_(x)
+        self.target_buf.copy_(target)
+        if self.use_graph and self.graph is None and self.steps_done >= 2:
+            torch.cuda.synchronize(p.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._fwd_loss_bwd(self.target_buf, world)
+            self.graph = g          # capturing does not execute: fall through to the replay below
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._fwd_loss_bwd(self.target_buf, world)
+        self.steps_done += 1
         parallel.allreduce_sum_(self.flat_g)   # gradients were pre-scaled by 1/world in the MSE kernel
         self.t += 1
         ops._lib.call("up_adam_step", ops._ptr(self.flat_p), ops._ptr(self.flat_g), ops._ptr(self.exp_avg),
