@@ -258,8 +258,10 @@ int up_bn_bwd_apply(const UpView* dy, const UpView* y, const UpView* z, const Up
 int up_ew_mul(const UpView* a, const UpView* m, const UpView* out, int64_t npix, int c, int mode_op, int accumulate,
               int dtype, void* stream);
 /* adjoints of the bandwidth kernels */
+/* idx_scratch: optional n*ho*wo*c bytes (8-byte aligned) -> two-pass form (arg-max map, then gather); NULL -> one
+ * pass that re-scans every window (slower). */
 int up_maxpool3x3s2_bwd(const UpView* x, const UpView* dy, const UpView* dx, int n, int h, int w, int c,
-                        int accumulate, int dtype, void* stream);
+                        int accumulate, int dtype, void* idx_scratch, void* stream);
 int up_upsample_bilinear_ac_bwd(const UpView* dy, const UpView* dx, int n, int h, int w, int ho, int wo, int c,
                                 int accumulate, int dtype, void* stream);
 /* dx[n,h,w,:] (+)= g[n,:] * mult  (adjoint of the global average pool with mult = 1/(h*w)) */

@@ -197,6 +197,19 @@ def test_pool_upsample_gap_adjoints():
     assert (got - ref).abs().max() < 1e-4
     ops.maxpool3x3s2_bwd(xa, dya, dxa, accumulate=True)
     assert (dxa.to_float().permute(0, 3, 1, 2).double() - 2 * ref).abs().max() < 2e-4
+    # two-pass form (arg-max map in caller scratch), incl. ties: quantised input has many equal neighbours
+    for tie in (False, True):
+        xt = (x * 2).round() / 2 if tie else x
+        xb = ops.Act(n, h, w, c, mode, dev)
+        ops.nchw_to_act(xt, xb)
+        xqt = xb.to_float().permute(0, 3, 1, 2).double().requires_grad_(True)
+        (reft,) = torch.autograd.grad(F.max_pool2d(xqt, 3, 2, 1), xqt, dy)
+        idx = torch.empty(n * dya.h * dya.w * c, dtype=torch.uint8, device=dev)
+        dxb = ops.Act(n, h, w, c, mode, dev)
+        ops.maxpool3x3s2_bwd(xb, dya, dxb, idx=idx)
+        assert (dxb.to_float().permute(0, 3, 1, 2).double() - reft).abs().max() < 1e-4
+        ops.maxpool3x3s2_bwd(xb, dya, dxb, accumulate=True, idx=idx)
+        assert (dxb.to_float().permute(0, 3, 1, 2).double() - 2 * reft).abs().max() < 2e-4
     # bilinear align_corners
     y = F.interpolate(xq, size=(48, 41), mode="bilinear", align_corners=True)
     dy = torch.randn_like(y)

@@ -72,7 +72,7 @@ _SIGNATURES = {
     "up_bn_bwd_reduce": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _P, _P],
     "up_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P, _P, _P],
     "up_ew_mul": [_P, _P, _P, _L, _I, _I, _I, _I, _P],
-    "up_maxpool3x3s2_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "up_maxpool3x3s2_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "up_upsample_bilinear_ac_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "up_add_broadcast": [_P, _P, _I, _I, _I, _F, _I, _I, _P],
     "up_zero_insert2x": [_P, _P, _I, _I, _I, _I, _I, _P],

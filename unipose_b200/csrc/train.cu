@@ -383,6 +383,97 @@ __global__ void ew_mul_kernel(TView a, TView m, TViewW out, long long npix, int 
   t_store8<kMode>(op, out.plane, v);
 }
 
+// Two-pass max-pool backward (used when the caller provides `idx` scratch, n*ho*wo*c bytes):
+//   pass 1: every output window records the position (0..8, row-major) of its FIRST maximum per channel;
+//   pass 2: every input pixel sums dy of the (at most 4) windows that point at it.
+template <int kMode>
+__global__ void maxpool3x3s2_argmax_kernel(TView x, uint8_t* __restrict__ idx, int n, int h, int w, int ho, int wo,
+                                           int ch) {
+  const int c8 = ch / 8;
+  const long long total = static_cast<long long>(n) * ho * wo * c8;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % c8);
+  const long long opix = i / c8;
+  const int ox = static_cast<int>(opix % wo);
+  long long t = opix / wo;
+  const int oy = static_cast<int>(t % ho);
+  const int b = static_cast<int>(t / ho);
+  float best[8];
+  uint32_t pos[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    best[e] = -INFINITY;
+    pos[e] = 4;   // the centre is always inside the image
+  }
+#pragma unroll
+  for (int d = 0; d < 9; ++d) {
+    const int yy = 2 * oy - 1 + d / 3, xx = 2 * ox - 1 + d % 3;
+    if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+    float v[8];
+    t_load8<kMode>(x.p + ((static_cast<long long>(b) * h + yy) * w + xx) * x.cs + x.coff + g * 8, x.plane, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (v[e] > best[e]) {   // strict: the first maximum in scan order wins, like ATen
+        best[e] = v[e];
+        pos[e] = d;
+      }
+    }
+  }
+  uint2 o;
+  o.x = pos[0] | (pos[1] << 8) | (pos[2] << 16) | (pos[3] << 24);
+  o.y = pos[4] | (pos[5] << 8) | (pos[6] << 16) | (pos[7] << 24);
+  *reinterpret_cast<uint2*>(idx + opix * ch + g * 8) = o;
+}
+
+template <int kMode>
+__global__ void maxpool3x3s2_bwd_idx_kernel(const uint8_t* __restrict__ idx, TView dy, TViewW dx, int n, int h, int w,
+                                            int ho, int wo, int ch, int accumulate) {
+  const int c8 = ch / 8;
+  const long long total = static_cast<long long>(n) * h * w * c8;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % c8);
+  const long long ipix = i / c8;
+  const int ix = static_cast<int>(ipix % w);
+  long long t = ipix / w;
+  const int iy = static_cast<int>(t % h);
+  const int b = static_cast<int>(t / h);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  // windows covering (iy, ix): oy = iy/2 (+1 when iy is odd), same for ox
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int oy = iy / 2 + a;
+    if ((a == 1 && (iy & 1) == 0) || oy >= ho) continue;
+    const int py = iy - (2 * oy - 1);
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb) {
+      const int ox = ix / 2 + bb;
+      if ((bb == 1 && (ix & 1) == 0) || ox >= wo) continue;
+      const uint32_t code = static_cast<uint32_t>(py * 3 + (ix - (2 * ox - 1)));
+      const long long opix = (static_cast<long long>(b) * ho + oy) * wo + ox;
+      const uint2 k = __ldg(reinterpret_cast<const uint2*>(idx + opix * ch + g * 8));
+      float d[8];
+      t_load8<kMode>(dy.p + opix * dy.cs + dy.coff + g * 8, dy.plane, d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t ke = ((e < 4 ? k.x : k.y) >> (8 * (e & 3))) & 0xFFu;
+        acc[e] += ke == code ? d[e] : 0.f;
+      }
+    }
+  }
+  uint16_t* op = dx.p + ipix * dx.cs + dx.coff + g * 8;
+  if (accumulate) {
+    float o[8];
+    t_load8<kMode>(op, dx.plane, o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += o[e];
+  }
+  t_store8<kMode>(op, dx.plane, acc);
+}
+
 // max-pool 3/2/1 backward (gather form): an input pixel receives dy of every window whose FIRST maximum
 // (row-major scan, like ATen) it is.
 template <int kMode>
@@ -711,7 +802,7 @@ extern "C" int up_ew_mul(const UpView* a, const UpView* m, const UpView* out, in
 }
 
 extern "C" int up_maxpool3x3s2_bwd(const UpView* x, const UpView* dy, const UpView* dx, int n, int h, int w, int c,
-                                   int accumulate, int dtype, void* stream) {
+                                   int accumulate, int dtype, void* idx_scratch, void* stream) {
   int rc = check_view("up_maxpool3x3s2_bwd(x)", x, c);
   if (rc) return rc;
   rc = check_view("up_maxpool3x3s2_bwd(dy)", dy, c);
@@ -719,6 +810,19 @@ extern "C" int up_maxpool3x3s2_bwd(const UpView* x, const UpView* dy, const UpVi
   rc = check_view("up_maxpool3x3s2_bwd(dx)", dx, c);
   if (rc) return rc;
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  if (idx_scratch) {
+    UP_CHECK_ARG((reinterpret_cast<uintptr_t>(idx_scratch) & 7) == 0, "up_maxpool3x3s2_bwd: idx_scratch alignment");
+    uint8_t* idx = static_cast<uint8_t*>(idx_scratch);
+    UP_T_DISPATCH(dtype, (up::maxpool3x3s2_argmax_kernel<kMode><<<blocks_for((long long)n * ho * wo * (c / 8)), 256, 0,
+                                                                  (cudaStream_t)stream>>>(tv(x), idx, n, h, w, ho, wo,
+                                                                                          c)));
+    UP_CHECK_LAUNCH("maxpool3x3s2_argmax_kernel");
+    UP_T_DISPATCH(dtype, (up::maxpool3x3s2_bwd_idx_kernel<kMode><<<blocks_for((long long)n * h * w * (c / 8)), 256, 0,
+                                                                   (cudaStream_t)stream>>>(idx, tv(dy), tvw(dx), n, h,
+                                                                                           w, ho, wo, c, accumulate)));
+    UP_CHECK_LAUNCH("maxpool3x3s2_bwd_idx_kernel");
+    return 0;
+  }
   UP_T_DISPATCH(dtype, (up::maxpool3x3s2_bwd_kernel<kMode><<<blocks_for((long long)n * h * w * (c / 8)), 256, 0,
                                                              (cudaStream_t)stream>>>(tv(x), tv(dy), tvw(dx), n, h, w, ho,
                                                                                      wo, c, accumulate)));

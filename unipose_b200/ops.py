@@ -381,10 +381,14 @@ def ew(a, out, *, m=None, op: int = 0, accumulate: bool = False) -> None:
               av.act.mode, _stream())
 
 
-def maxpool3x3s2_bwd(x, dy, dx, accumulate: bool = False) -> None:
+def maxpool3x3s2_bwd(x, dy, dx, accumulate: bool = False, idx: Optional[torch.Tensor] = None) -> None:
+    """`idx`: optional uint8 scratch of n*ho*wo*c elements -> two-pass (arg-max map + gather) form."""
     xv = as_view(x)
+    if idx is not None:
+        ho, wo = (xv.h - 1) // 2 + 1, (xv.w - 1) // 2 + 1
+        assert idx.dtype == torch.uint8 and idx.numel() >= xv.n * ho * wo * xv.c
     _lib.call("up_maxpool3x3s2_bwd", _vref(xv), _vref(dy), _vref(dx), xv.n, xv.h, xv.w, xv.c, 1 if accumulate else 0,
-              xv.act.mode, _stream())
+              xv.act.mode, _ptr(idx), _stream())
 
 
 def upsample_bilinear_ac_bwd(dy, dx, accumulate: bool = False) -> None:

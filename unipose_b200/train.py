@@ -290,7 +290,8 @@ class TrainPlan:
             dy, dx = self.grad_view(yv), self.grad_view(xv)
             acc = self.is_written(dx)
             self.mark_written(dx)
-            self.bwd.append(lambda: ops.maxpool3x3s2_bwd(xv, dy, dx, accumulate=acc))
+            idx = self.tensor((xv.n * ((xv.h - 1) // 2 + 1) * ((xv.w - 1) // 2 + 1) * xv.c,), dtype=torch.uint8)
+            self.bwd.append(lambda: ops.maxpool3x3s2_bwd(xv, dy, dx, accumulate=acc, idx=idx))
         self.tape.append(bwd)
 
     def upsample(self, x, y) -> None:
