@@ -7,15 +7,23 @@
 //             N = output channels (tile = block_n in {32,64,128,256}),
 //             K = taps x input channels (k-block = one tap x `ck` channels, ck in {16,64}).
 //
-// Persistent, warp-specialised CTA (384 threads, 1 CTA / SM):
-//   warp 0 (32 lanes) : TMA producer - the lanes compute the coordinates of 32 consecutive k-blocks in parallel (the
-//                       scalar address arithmetic of a single producer thread was the bottleneck of small-K layers);
-//                       lane 0 then issues them in order (mbarrier wait, expect_tx, two TMA loads per k-block)
-//   warp 1 lane 0     : tcgen05.mma issuer   (smem ring: full/empty mbarriers; TMEM double buffer: tfull/tempty)
-//   warp 2            : TMEM alloc/dealloc; lane 0 = epilogue DMA thread: TMA-prefetches the residual tile of each
-//                       64-channel group into a staging buffer and TMA-stores the finished group (avail/ready mbarriers)
-//   warps 4..11       : epilogue math: TMEM -> regs, scale/shift (+ residual from smem) (+ ReLU), pack, write the
-//                       staging buffer in place.  Two warps per TMEM lane quarter, each takes 32 of the 64 columns.
+// Persistent, warp-specialised CTA (384 threads, 1 CTA / SM).  By default two CTAs form a cluster and issue ONE
+// tcgen05.mma.cta_group::2 of M = 256 per k-step (kPair): each CTA loads its own 128 activation rows and HALF of the
+// weight tile, i.e. 2/3 of the L2->SM bytes per FLOP of two independent CTAs.
+//   warps 0 and 3     : TMA producers (even / odd k-blocks).  Each warp walks the (tap, channel chunk, term) loop nest
+//                       CONVERGED with warp-uniform values - increments only, no divisions - and one elect.sync lane
+//                       issues the mbarrier expect_tx + the TMA loads.  Residual tiles ride in the same ring, up to
+//                       (a_bytes + b_bytes) / 16 KB of them per slot.
+//   warp 1            : tcgen05.mma issuer, converged as well (descriptors stay in uniform registers, the four MMAs
+//                       of a k-block issue back to back); smem ring: full/empty mbarriers, TMEM double buffer:
+//                       tfull/tempty.  The residual is added as D += R x I (identity B tile) inside the same pipe.
+//   warp 2            : TMEM alloc/dealloc; lane 0 = epilogue DMA thread: TMA-stores each finished 64-channel group
+//                       from its staging buffer (2..4 buffers, avail/ready mbarriers, one group of look-ahead)
+//   warps 4..11       : epilogue math, templated on the storage format: tcgen05.ld of group g+1 is in flight while
+//                       group g gets shift (+scale), cvt.rn[.relu].{f16,bf16}x2 and the swizzled st.shared.
+//                       Two warps per TMEM lane quarter, each takes 32 of a group's 64 columns.
+// Measured (profiles/conv_phase_timeline_r1_*.txt): a k-block costs ~0.28 us of unique activation bytes (16 KB at
+// ~57 KB/us/SM from L2) + weight bytes at ~200 KB/us/SM (all SMs read the same tile); the tensor pipe needs 0.26 us.
 //
 // Filter taps whose whole input box lies outside the image contribute exact zeros and are skipped by producer and
 // issuer alike (large-dilation WASP convs on small maps: wasp.py:47-49); the in-bounds taps of a tile always form a
