@@ -221,12 +221,23 @@ __global__ void __launch_bounds__(512)
   }
 }
 
+// blockDim = (32, 16): 32 consecutive sums per block, the rows split 16 ways, combined in shared memory in a fixed
+// order (deterministic).
 __global__ void reduce_rows_kernel(const float* __restrict__ rows, int nrows, int c2, double* __restrict__ sums) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c2) return;
+  __shared__ double part[16][33];
+  const int i = blockIdx.x * 32 + threadIdx.x;
   double s = 0.0;
-  for (int r = 0; r < nrows; ++r) s += rows[static_cast<long long>(r) * c2 + i];
-  sums[i] = s;
+  if (i < c2) {
+    for (int r = threadIdx.y; r < nrows; r += 16) s += rows[static_cast<long long>(r) * c2 + i];
+  }
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < c2) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) t += part[q][threadIdx.x];
+    sums[i] = t;
+  }
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
@@ -702,7 +713,7 @@ extern "C" int up_bn_stats(const UpView* x, int64_t npix, int c, int dtype, doub
   UP_T_DISPATCH(dtype, (up::channel_reduce_kernel<kMode, 0><<<grid, 512, 512 * 16 * sizeof(float), st>>>(
                            tv(x), up::TView{}, up::TView{}, nullptr, nullptr, rows, npix, c, 0)));
   UP_CHECK_LAUNCH("channel_reduce_kernel<stats>");
-  up::reduce_rows_kernel<<<(2 * c + 127) / 128, 128, 0, st>>>(rows, grid, 2 * c, sums);
+  up::reduce_rows_kernel<<<(2 * c + 31) / 32, dim3(32, 16), 0, st>>>(rows, grid, 2 * c, sums);
   UP_CHECK_LAUNCH("reduce_rows_kernel");
   return 0;
 }
@@ -753,7 +764,7 @@ extern "C" int up_bn_bwd_reduce(const UpView* dy, const UpView* y, const UpView*
   UP_T_DISPATCH(dtype, (up::channel_reduce_kernel<kMode, 1><<<grid, 512, 512 * 16 * sizeof(float), st>>>(
                            tv(dy), tv(y), tv(z), save_mean, save_invstd, rows, npix, c, relu)));
   UP_CHECK_LAUNCH("channel_reduce_kernel<bn bwd>");
-  up::reduce_rows_kernel<<<(2 * c + 127) / 128, 128, 0, st>>>(rows, grid, 2 * c, sums);
+  up::reduce_rows_kernel<<<(2 * c + 31) / 32, dim3(32, 16), 0, st>>>(rows, grid, 2 * c, sums);
   UP_CHECK_LAUNCH("reduce_rows_kernel");
   return 0;
 }
