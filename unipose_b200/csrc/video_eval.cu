@@ -35,20 +35,40 @@ __global__ void avgpool9s8p1_kernel(const float* __restrict__ x, float* __restri
 
 // ------------------------------------------------------------------------------------------
 // ConvLSTM cells: all gate convolutions (3x3, pad 1, with bias) + gate non-linearities + state update
-// in one kernel.  One thread per output pixel holds the kGates x kC accumulators; the input tile
-// (+halo) is staged in shared memory, weights are warp-uniform broadcast loads.
+// in one kernel.  A block owns a 16x16 pixel tile of one image and a group of kLstmCoG output channels (all gates
+// of those channels, so the point-wise update stays local): batch 8 x 9 tiles x 3 channel groups = 216 blocks.
+// One thread per pixel keeps kGates x kLstmCoG accumulators IN REGISTERS (compile-time trip counts); the input tile
+// (+halo) and the block's slice of the filters are staged in shared memory (broadcast reads).
+// Accumulation order per output = (input channel, tap), the same as a direct fp32 convolution loop.
 // ------------------------------------------------------------------------------------------
 constexpr int kLstmTile = 16;
 constexpr int kLstmCMax = 16;
+constexpr int kLstmCoG = 5;
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
 
+// wsm: [kGates][kLstmCoG][cin][9] slice of wts [kGates][c][cin][3][3] for channels co0 .. co0+kLstmCoG-1 (zeros beyond c)
 template <int kGates>
-__device__ __forceinline__ void lstm_accumulate(const float* __restrict__ src, int cin, int c, int h, int w,
-                                                const float* __restrict__ wts, float (&acc)[kGates][kLstmCMax],
-                                                float* tile, int ty0, int tx0) {
-  // src: [cin, h, w] of one image;  wts: [kGates][c][cin][3][3]
-  const int tw = kLstmTile + 2;
+__device__ __forceinline__ void lstm_stage_weights(const float* __restrict__ wts, float* wsm, int cin, int c, int co0) {
+  const int total = kGates * kLstmCoG * cin * 9;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int t = e % 9;
+    int r = e / 9;
+    const int ci = r % cin;
+    r /= cin;
+    const int j = r % kLstmCoG, g = r / kLstmCoG;
+    const int co = co0 + j;
+    wsm[e] = co < c ? wts[((static_cast<long long>(g) * c + co) * cin + ci) * 9 + t] : 0.f;
+  }
+}
+
+template <int kGates>
+__device__ __forceinline__ void lstm_accumulate(const float* __restrict__ src, int cin, int h, int w,
+                                                const float* wsm, float (&acc)[kGates][kLstmCoG], float* tile, int ty0,
+                                                int tx0) {
+  // src: [cin, h, w] of one image
+  constexpr int tw = kLstmTile + 2;
+  const int ly = threadIdx.x / kLstmTile, lx = threadIdx.x % kLstmTile;
   for (int ci = 0; ci < cin; ++ci) {
     __syncthreads();
     for (int e = threadIdx.x; e < tw * tw; e += blockDim.x) {
@@ -56,18 +76,18 @@ __device__ __forceinline__ void lstm_accumulate(const float* __restrict__ src, i
       tile[e] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? src[(static_cast<long long>(ci) * h + yy) * w + xx] : 0.f;
     }
     __syncthreads();
-    const int ly = threadIdx.x / kLstmTile, lx = threadIdx.x % kLstmTile;
     float v[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) v[t] = tile[(ly + t / 3) * tw + lx + t % 3];
 #pragma unroll
     for (int g = 0; g < kGates; ++g) {
-      for (int co = 0; co < c; ++co) {
-        const float* wp = wts + ((static_cast<long long>(g) * c + co) * cin + ci) * 9;
-        float a = acc[g][co];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) a = fmaf(__ldg(wp + t), v[t], a);
-        acc[g][co] = a;
+      for (int j = 0; j < kLstmCoG; ++j) {
+        const float* wp = wsm + ((g * kLstmCoG + j) * cin + ci) * 9;
+        float a = acc[g][j];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) a = fmaf(wp[t], v[t], a);
+        acc[g][j] = a;
       }
     }
   }
@@ -76,21 +96,27 @@ __device__ __forceinline__ void lstm_accumulate(const float* __restrict__ src, i
 // LSTM_0: gates g,i,o from x only.
 __global__ void __launch_bounds__(kLstmTile * kLstmTile)
     convlstm_cell0_kernel(const float* __restrict__ x, const float* __restrict__ w3, const float* __restrict__ b3,
-                          float* __restrict__ cell, float* __restrict__ hide, int cin, int c, int h, int w) {
+                          float* __restrict__ cell, float* __restrict__ hide, int cin, int c, int h, int w, int ngroups) {
   __shared__ float tile[(kLstmTile + 2) * (kLstmTile + 2)];
-  const int b = blockIdx.z;
+  extern __shared__ float wsm[];
+  const int b = blockIdx.z / ngroups, co0 = (blockIdx.z % ngroups) * kLstmCoG;
   const int ty0 = blockIdx.y * kLstmTile, tx0 = blockIdx.x * kLstmTile;
-  float acc[3][kLstmCMax];
+  lstm_stage_weights<3>(w3, wsm, cin, c, co0);
+  float acc[3][kLstmCoG];
 #pragma unroll
   for (int g = 0; g < 3; ++g)
-    for (int co = 0; co < kLstmCMax; ++co) acc[g][co] = 0.f;
-  lstm_accumulate<3>(x + static_cast<long long>(b) * cin * h * w, cin, c, h, w, w3, acc, tile, ty0, tx0);
+#pragma unroll
+    for (int j = 0; j < kLstmCoG; ++j) acc[g][j] = 0.f;
+  lstm_accumulate<3>(x + static_cast<long long>(b) * cin * h * w, cin, h, w, wsm, acc, tile, ty0, tx0);
   const int oy = ty0 + threadIdx.x / kLstmTile, ox = tx0 + threadIdx.x % kLstmTile;
   if (oy >= h || ox >= w) return;
-  for (int co = 0; co < c; ++co) {
-    const float g = tanhf(acc[0][co] + b3[0 * c + co]);
-    const float i = sigmoidf_(acc[1][co] + b3[1 * c + co]);
-    const float o = sigmoidf_(acc[2][co] + b3[2 * c + co]);
+#pragma unroll
+  for (int j = 0; j < kLstmCoG; ++j) {
+    const int co = co0 + j;
+    if (co >= c) break;
+    const float g = tanhf(acc[0][j] + b3[0 * c + co]);
+    const float i = sigmoidf_(acc[1][j] + b3[1 * c + co]);
+    const float o = sigmoidf_(acc[2][j] + b3[2 * c + co]);
     const float cl = tanhf(g * i);
     const long long idx = ((static_cast<long long>(b) * c + co) * h + oy) * w + ox;
     cell[idx] = cl;
@@ -103,28 +129,32 @@ __global__ void __launch_bounds__(kLstmTile * kLstmTile)
     convlstm_cell_kernel(const float* __restrict__ x, const float* __restrict__ hp, const float* __restrict__ cp,
                          const float* __restrict__ wx, const float* __restrict__ bx, const float* __restrict__ wh,
                          const float* __restrict__ bh, float* __restrict__ cell, float* __restrict__ hide, int cin,
-                         int c, int h, int w) {
+                         int c, int h, int w, int ngroups) {
   __shared__ float tile[(kLstmTile + 2) * (kLstmTile + 2)];
-  const int b = blockIdx.z;
+  extern __shared__ float wsm[];   // [x filters | h filters]
+  const int b = blockIdx.z / ngroups, co0 = (blockIdx.z % ngroups) * kLstmCoG;
   const int ty0 = blockIdx.y * kLstmTile, tx0 = blockIdx.x * kLstmTile;
-  float acc[4][kLstmCMax];
+  float* wsm_h = wsm + 4 * kLstmCoG * cin * 9;
+  lstm_stage_weights<4>(wx, wsm, cin, c, co0);
+  lstm_stage_weights<4>(wh, wsm_h, c, c, co0);
+  float acc[4][kLstmCoG], acch[4][kLstmCoG];
 #pragma unroll
   for (int g = 0; g < 4; ++g)
-    for (int co = 0; co < kLstmCMax; ++co) acc[g][co] = 0.f;
-  float acch[4][kLstmCMax];
 #pragma unroll
-  for (int g = 0; g < 4; ++g)
-    for (int co = 0; co < kLstmCMax; ++co) acch[g][co] = 0.f;
-  lstm_accumulate<4>(x + static_cast<long long>(b) * cin * h * w, cin, c, h, w, wx, acc, tile, ty0, tx0);
-  lstm_accumulate<4>(hp + static_cast<long long>(b) * c * h * w, c, c, h, w, wh, acch, tile, ty0, tx0);
+    for (int j = 0; j < kLstmCoG; ++j) acc[g][j] = acch[g][j] = 0.f;
+  lstm_accumulate<4>(x + static_cast<long long>(b) * cin * h * w, cin, h, w, wsm, acc, tile, ty0, tx0);
+  lstm_accumulate<4>(hp + static_cast<long long>(b) * c * h * w, c, h, w, wsm_h, acch, tile, ty0, tx0);
   const int oy = ty0 + threadIdx.x / kLstmTile, ox = tx0 + threadIdx.x % kLstmTile;
   if (oy >= h || ox >= w) return;
-  for (int co = 0; co < c; ++co) {
+#pragma unroll
+  for (int j = 0; j < kLstmCoG; ++j) {
+    const int co = co0 + j;
+    if (co >= c) break;
     // same association as the reference: (conv_x + bias_x) + (conv_h + bias_h)
-    const float gs = (acc[0][co] + bx[0 * c + co]) + (acch[0][co] + bh[0 * c + co]);
-    const float is = (acc[1][co] + bx[1 * c + co]) + (acch[1][co] + bh[1 * c + co]);
-    const float os = (acc[2][co] + bx[2 * c + co]) + (acch[2][co] + bh[2 * c + co]);
-    const float fs = (acc[3][co] + bx[3 * c + co]) + (acch[3][co] + bh[3 * c + co]);
+    const float gs = (acc[0][j] + bx[0 * c + co]) + (acch[0][j] + bh[0 * c + co]);
+    const float is = (acc[1][j] + bx[1 * c + co]) + (acch[1][j] + bh[1 * c + co]);
+    const float os = (acc[2][j] + bx[2 * c + co]) + (acch[2][j] + bh[2 * c + co]);
+    const float fs = (acc[3][j] + bx[3 * c + co]) + (acch[3][j] + bh[3 * c + co]);
     const long long idx = ((static_cast<long long>(b) * c + co) * h + oy) * w + ox;
     const float cl = sigmoidf_(fs) * cp[idx] + sigmoidf_(is) * tanhf(gs);
     cell[idx] = cl;
@@ -247,8 +277,12 @@ extern "C" int up_convlstm_cell0_fwd(const float* x, const float* w3, const floa
                                      int b, int cin, int c, int h, int w, void* stream) {
   UP_CHECK_ARG(x && w3 && b3 && cell && hide, "up_convlstm_cell0_fwd: null argument");
   UP_CHECK_ARG(b > 0 && cin > 0 && c > 0 && c <= kLstmCMax, "up_convlstm_cell0_fwd: c must be <= %d", kLstmCMax);
-  dim3 grid((w + kLstmTile - 1) / kLstmTile, (h + kLstmTile - 1) / kLstmTile, b);
-  convlstm_cell0_kernel<<<grid, kLstmTile * kLstmTile, 0, (cudaStream_t)stream>>>(x, w3, b3, cell, hide, cin, c, h, w);
+  const int ngroups = (c + kLstmCoG - 1) / kLstmCoG;
+  UP_CHECK_ARG(cin <= 64, "up_convlstm_cell0_fwd: cin must be <= 64");
+  dim3 grid((w + kLstmTile - 1) / kLstmTile, (h + kLstmTile - 1) / kLstmTile, b * ngroups);
+  const size_t wbytes = static_cast<size_t>(3) * kLstmCoG * cin * 9 * sizeof(float);
+  convlstm_cell0_kernel<<<grid, kLstmTile * kLstmTile, wbytes, (cudaStream_t)stream>>>(x, w3, b3, cell, hide, cin, c, h,
+                                                                                      w, ngroups);
   UP_CHECK_LAUNCH("convlstm_cell0_kernel");
   return 0;
 }
@@ -258,9 +292,12 @@ extern "C" int up_convlstm_cell_fwd(const float* x, const float* h_prev, const f
                                     int cin, int c, int h, int w, void* stream) {
   UP_CHECK_ARG(x && h_prev && c_prev && wx && bx && wh && bh && cell && hide, "up_convlstm_cell_fwd: null argument");
   UP_CHECK_ARG(b > 0 && cin > 0 && c > 0 && c <= kLstmCMax, "up_convlstm_cell_fwd: c must be <= %d", kLstmCMax);
-  dim3 grid((w + kLstmTile - 1) / kLstmTile, (h + kLstmTile - 1) / kLstmTile, b);
-  convlstm_cell_kernel<<<grid, kLstmTile * kLstmTile, 0, (cudaStream_t)stream>>>(x, h_prev, c_prev, wx, bx, wh, bh,
-                                                                                 cell, hide, cin, c, h, w);
+  const int ngroups = (c + kLstmCoG - 1) / kLstmCoG;
+  UP_CHECK_ARG(cin <= 32, "up_convlstm_cell_fwd: cin must be <= 32 (filters are staged in 48 KB of shared memory)");
+  dim3 grid((w + kLstmTile - 1) / kLstmTile, (h + kLstmTile - 1) / kLstmTile, b * ngroups);
+  const size_t wbytes = static_cast<size_t>(4) * kLstmCoG * (cin + c) * 9 * sizeof(float);
+  convlstm_cell_kernel<<<grid, kLstmTile * kLstmTile, wbytes, (cudaStream_t)stream>>>(x, h_prev, c_prev, wx, bx, wh, bh,
+                                                                                     cell, hide, cin, c, h, w, ngroups);
   UP_CHECK_LAUNCH("convlstm_cell_kernel");
   return 0;
 }
