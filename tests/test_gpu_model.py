@@ -107,7 +107,9 @@ def test_mpii_384_vs_oracle_and_batch_consistency():
     _argmax_checked(h4, ref, 1e-3 * np.abs(ref).max())
     h32 = m(x.cuda()).cpu().numpy()
     assert h32.shape == (32, 17, 48, 48)
-    assert _rel(h32[:4], h4) < 1e-5
+    # same samples at another batch size: the tile configuration (N tile, CTA pairs, filter-row reuse) and with it the
+    # fp32 accumulation order depend on the launch shape, so the match is to rounding, not bitwise
+    assert _rel(h32[:4], h4) < 5e-5
     # the bf16 throughput mode on the full config-2 batch: PCKh@0.5 on its own heat-maps vs the fp32 ones
     mb = _model(16, 4, "bf16")
     hb = mb(x.cuda()).cpu().numpy()

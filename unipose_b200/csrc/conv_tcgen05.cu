@@ -75,6 +75,10 @@ struct ConvKParams {
   int res_terms;   // residual tiles (128 px x 64 ch, 16 KB) per 64-channel group (0 = none, 1, or 2 in split mode)
   int res_per_slot;  // how many of them share one ring slot (the slot is a_bytes + b_bytes wide)
   int bsplit;        // experiment (UP_DEBUG_BSPLIT): fetch the weight tile with this many TMA instructions
+  int tall;          // 3x3 stride-1 convs on single-image tiles: ONE activation box of bh + 2*dil rows per (kw, chunk)
+                     // serves the three filter rows through row-offset descriptors (a_bytes = tall box, b_bytes = 3 taps)
+  uint32_t tall_a_step;   // dil * bw * 128 bytes >> 4: descriptor step between filter rows
+  uint32_t tall_b_bytes;  // bytes of ONE tap's weight tile in the slot (this CTA's half in pair mode)
   uint32_t idesc_res;
   uint32_t a_bytes, b_bytes, buf_bytes;
   uint32_t idesc;
@@ -328,6 +332,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       tap_range(p, p.taps_h, p.pad_h, t.h0, p.bh, p.Hq, kh_lo, kh_hi);
       tap_range(p, p.taps_w, p.pad_w, t.w0, p.bw, p.Wq, kw_lo, kw_hi);
       const int brow_nt = t.nt * p.block_n;
+      if (p.tall) {   // the tall activation box starts at filter row 0 and covers all three rows
+        kh_lo = 0;
+        kh_hi = 0;
+      }
       for (int kh = kh_lo; kh <= kh_hi; ++kh) {
         int oh, ph;
         tap_offset(p, kh, p.pad_h, oh, ph);
@@ -354,8 +362,14 @@ __global__ void __launch_bounds__(kThreads, 1)
                   if (crank == 0) mbar_arrive_expect_tx(full_bar(s), 2u * mine);
                   else mbar_arrive_remote(full_bar(s), 0u);
                   tma_load_5d_2cta(amap, dst, full_bar(s), c, t.w0 + ow, ph, t.h0 + oh, n);
-                  tma_load_2d_2cta(&tmB, dst + p.a_bytes, full_bar(s), chunk * p.ck,
-                                   brow + static_cast<int>(crank) * (p.block_n >> 1));
+                  if (p.tall) {
+                    for (int r = 0; r < 3; ++r)
+                      tma_load_2d_2cta(&tmB, dst + p.a_bytes + r * p.tall_b_bytes, full_bar(s), chunk * p.ck,
+                                       brow + r * p.taps_w * p.cout + static_cast<int>(crank) * (p.block_n >> 1));
+                  } else {
+                    tma_load_2d_2cta(&tmB, dst + p.a_bytes, full_bar(s), chunk * p.ck,
+                                     brow + static_cast<int>(crank) * (p.block_n >> 1));
+                  }
                 } else {
                   mbar_arrive_expect_tx(full_bar(s), stage_bytes);
                   tma_load_5d(amap, dst, full_bar(s), c, t.w0 + ow, ph, t.h0 + oh, n);
@@ -365,6 +379,10 @@ __global__ void __launch_bounds__(kThreads, 1)
                     tma_load_2d_mc(&tmB, dst + p.a_bytes + crank * sub_rows * static_cast<uint32_t>(p.ck) * 2u,
                                    full_bar(s), chunk * p.ck, brow + static_cast<int>(crank * sub_rows),
                                    static_cast<uint16_t>((1u << p.cluster) - 1u));
+                  } else if (p.tall) {
+                    for (int r = 0; r < 3; ++r)
+                      tma_load_2d(&tmB, dst + p.a_bytes + r * p.tall_b_bytes, full_bar(s), chunk * p.ck,
+                                  brow + r * p.taps_w * p.cout);
                   } else {
                     const uint32_t part_rows = static_cast<uint32_t>(p.block_n / p.bsplit);
                     for (int j = 0; j < p.bsplit; ++j)
@@ -437,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       int kh_lo, kh_hi, kw_lo, kw_hi;
       tap_range(p, p.taps_h, p.pad_h, t.h0, p.bh, p.Hq, kh_lo, kh_hi);
       tap_range(p, p.taps_w, p.pad_w, t.w0, p.bw, p.Wq, kw_lo, kw_hi);
-      const int nkb_conv = (kh_hi - kh_lo + 1) * (kw_hi - kw_lo + 1) * p.chunks * p.nterms;
+      const int nkb_conv = (p.tall ? 1 : (kh_hi - kh_lo + 1)) * (kw_hi - kw_lo + 1) * p.chunks * p.nterms;
       const int res_units = (p.block_n >> 6) * p.res_terms;
       const int nkb = nkb_conv + (p.res_terms ? (res_units + p.res_per_slot - 1) / p.res_per_slot : 0);
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -461,6 +479,18 @@ __global__ void __launch_bounds__(kThreads, 1)
               for (int k = 0; k < 4; ++k) {
                 if constexpr (kPair) umma_f16_2cta(tmem_d + rg * 64, rdesc + 2u * k, identdesc + 2u * k, p.idesc_res, 1u);
                 else umma_f16(tmem_d + rg * 64, rdesc + 2u * k, identdesc + 2u * k, p.idesc_res, 1u);
+              }
+            }
+          } else if (p.tall) {
+            // three filter rows from ONE activation box: row r reads it dil*bw pixel rows further down (a multiple
+            // of the 1024-byte swizzle atom) against its own weight tile
+            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage_step * s);
+            for (int r = 0; r < 3; ++r) {
+              const uint64_t ar = adesc + static_cast<uint64_t>(p.tall_a_step * r);
+              const uint64_t br = bdesc + static_cast<uint64_t>((p.tall_b_bytes >> 4) * r);
+              for (int k = 0; k < kk; ++k) {
+                if constexpr (kPair) umma_f16_2cta(tmem_d, ar + 2u * k, br + 2u * k, p.idesc, (kb | r | k) ? 1u : 0u);
+                else umma_f16(tmem_d, ar + 2u * k, br + 2u * k, p.idesc, (kb | r | k) ? 1u : 0u);
               }
             }
           } else {
@@ -798,6 +828,27 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
     if (p.cluster == 1 && (v == 2 || v == 4) && block_n % (8 * v) == 0) p.bsplit = v;
   }
   if (p.pair) p.b_bytes = static_cast<uint32_t>(block_n / 2) * ck * 2;   // each CTA of the pair holds half of the weight tile
+  // Filter-row reuse ("tall" activation box): 3x3, stride 1, same padding, single-image tiles with bw a multiple of 8
+  // (row offsets stay aligned to the 1024-byte swizzle atom), and a slot (tall box + three weight tiles) small
+  // enough for >= 3 pipeline stages.  Cuts the activation bytes of the k-loop by 3*bh / (bh + 2*dil).
+  p.tall = 0;
+  p.tall_a_step = 0;
+  p.tall_b_bytes = 0;
+  {
+    const bool shape_ok = d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad_h == d->dil && ck == 64 && p.bn == 1 &&
+                          p.bw % 8 == 0 && p.cluster * p.bsplit == (p.pair ? 2 : 1) && d->x_cextent == 0 && !has_res;
+    const uint32_t tall_a = static_cast<uint32_t>(p.bh + 2 * d->dil) * p.bw * 128u;
+    const uint32_t slot = tall_a + 3u * p.b_bytes;
+    const char* e = getenv("UP_TALL");
+    const bool want = e ? (e[0] == '1') : true;
+    if (want && shape_ok && p.bh + 2 * d->dil <= 256 && 3u * slot + 2u * p.buf_bytes + 4096u <= g_max_smem) {
+      p.tall = 1;
+      p.tall_a_step = (static_cast<uint32_t>(d->dil) * p.bw * 128u) >> 4;
+      p.tall_b_bytes = p.b_bytes;
+      p.a_bytes = tall_a;
+      p.b_bytes = 3u * p.b_bytes;
+    }
+  }
   p.idesc = make_idesc_f16(static_cast<uint32_t>(fmt), p.pair ? 256u : kTileM, static_cast<uint32_t>(block_n));
   p.idesc_res = make_idesc_f16(static_cast<uint32_t>(fmt), p.pair ? 256u : kTileM, 64u);
   if (has_res) UP_CHECK_ARG(ck == 64, "up_conv2d_fwd: residual needs cin to be a multiple of 64");
@@ -855,8 +906,8 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   // ---- tensor maps ----
   CUtensorMap tmA0, tmA1, tmB, tmY0, tmY1, tmR0, tmR1;
   const int sw = ck * 2;
-  const uint32_t abox[5] = {static_cast<uint32_t>(ck), static_cast<uint32_t>(p.bw), 1u, static_cast<uint32_t>(p.bh),
-                            static_cast<uint32_t>(p.bn)};
+  const uint32_t abox[5] = {static_cast<uint32_t>(ck), static_cast<uint32_t>(p.bw), 1u,
+                            static_cast<uint32_t>(p.tall ? p.bh + 2 * d->dil : p.bh), static_cast<uint32_t>(p.bn)};
   const int n_total = d->n + (groups - 1) * p.group_nstride;
   rc = encode_act_map(&tmA0, fmt, x, n_total, d->h, d->w, d->x_cstride, d->stride, abox, sw, "x", d->x_cextent,
                       d->x_wpitch);
