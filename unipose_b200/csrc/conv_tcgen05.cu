@@ -841,7 +841,9 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
     const uint32_t slot = tall_a + 3u * p.b_bytes;
     const char* e = getenv("UP_TALL");
     const bool want = e ? (e[0] == '1') : true;
-    if (want && shape_ok && p.bh + 2 * d->dil <= 256 && 3u * slot + 2u * p.buf_bytes + 4096u <= g_max_smem) {
+    uint32_t min_stages = 3;
+    if (const char* ms = getenv("UP_TALL_MIN_STAGES")) min_stages = atoi(ms) == 2 ? 2u : 3u;
+    if (want && shape_ok && p.bh + 2 * d->dil <= 256 && min_stages * slot + 2u * p.buf_bytes + 4096u <= g_max_smem) {
       p.tall = 1;
       p.tall_a_step = (static_cast<uint32_t>(d->dil) * p.bw * 128u) >> 4;
       p.tall_b_bytes = p.b_bytes;
