@@ -49,8 +49,9 @@ enum {
                                 pipeline (identity MMA into the fp32 accumulator): y = act(scale*(conv + res) + shift).
                                 Callers fold a BatchNorm scale into the weights and pass scale = 1. */
   UP_FLAG_OUT_NCHW_F32 = 4,  /* write fp32 NCHW [n, cout_valid, ho, wo] instead of 16-bit NHWC */
-  UP_FLAG_STATS = 8          /* also accumulate per-channel sum / sum-of-squares of the stored output
-                                (train-mode BatchNorm statistics) into stats[2*cout] with atomics */
+  UP_FLAG_STATS = 8          /* RESERVED: per-channel sum / sum-of-squares of the stored output fused into the
+                                epilogue.  Not implemented in this build - up_conv2d_fwd rejects it with an error;
+                                train-mode BatchNorm statistics come from up_bn_stats. */
 };
 
 const char* up_last_error(void);

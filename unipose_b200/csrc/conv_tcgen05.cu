@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 0 || warp == 3) {
     // ===================== TMA producers (two warps: even / odd k-blocks) =====================
     // Each warp walks the whole (tap, channel chunk, term) loop nest with warp-uniform values - pure increments, no
-    // divisions, no cross-lane traffic - and its lane 0 issues the copies of every second k-block.  A k-block's slot
+    // divisions, no cross-lane traffic - and one elected lane issues the copies of every second k-block.  A k-block's slot
     // and barrier parity follow from its sequence number alone, and a producer cannot run more than `stages`
     // k-blocks ahead of the MMA issuer, so the two issue streams need no ordering between them.
     const int which = warp == 3 ? 1 : 0;
