@@ -28,6 +28,9 @@ METRIC = "frames/sec MPII 384x384 bs32 forward (UniPose ResNet-101+WASP+decoder)
 UNIT = "frames/s"
 WASP_FLOPS_PER_IMG = 3.625e9        # 1.8125 GMAC nominal @24x24
 WASP_MIN_BYTES_C2 = 91.4e6          # minimal fused bytes, batch 32, 2 B/elt
+WASP_LAYERWISE_BYTES_C2 = 355.6e6                # layer-by-layer bytes of the block at config 2
+# MMAC/img actually issued at 24x24: aspp1 302.0 + 339.7 * (0.25 + 0.44 + 0.69) + GAP 0.5 + conv1 188.7 (conv2 folded)
+WASP_EXECUTED_FLOPS_PER_IMG_24 = 2.0 * (302.0 + 339.7 * 1.38 + 0.5 + 188.7) * 1e6
 NET_FLOPS_PER_IMG = 68.1e9          # conv-only fwd @384^2
 
 
@@ -325,7 +328,15 @@ def wasp_roofline(model, args, dev, peaks):
             "frac": achieved / peaks["tflops_burst"], "traffic": traffic, "peak_source": peaks["source"],
             "kernel": "conv_tcgen05_kernel (WASP block = %d launches: 6 convs + GAP + broadcast; shared conv2 folded into conv1)" % plan.launches,
             "wasp_ms": ms, "wasp_t_roof_ms": t_roof_ms, "wasp_roofline_frac": t_roof_ms / ms,
-            "flops_convention": "nominal dense (zero taps counted), %.1f GFLOP per launch group" % (flops / 1e9)}
+            "flops_convention": "nominal dense (zero taps counted), %.1f GFLOP per launch group" % (flops / 1e9),
+            # the layer-by-layer variant (every conv reads its input / writes its output: 355.6 MB at
+            # config 2) and, reported separately and NOT used in `frac`, the work actually issued to the tensor
+            # cores: out-of-image taps skipped (25 / 44 / 69 % of the d=18 / 12 / 6 convs survive at 24x24) and the
+            # shared conv2 (8 x 37.7 MMAC/img) folded into conv1's weights
+            "wasp_t_roof_layerwise_ms": (max(flops / (peaks["tflops_burst"] * 1e12),
+                                             WASP_LAYERWISE_BYTES_C2 / (peaks["hbm_gbs"] * 1e9)) * 1e3
+                                         if (B == 32 and hw == 24) else None),
+            "executed_gflop_estimate": (WASP_EXECUTED_FLOPS_PER_IMG_24 * B / 1e9 if hw == 24 else None)}
 
 
 def main() -> int:
