@@ -98,3 +98,24 @@ def test_precision_switch_and_lr_groups():
     n1 = sum(p.numel() for p in m.get_1x_lr_params())
     n10 = sum(p.numel() for p in m.get_10x_lr_params())
     assert n1 == 42500160 and n1 + n10 == 47547313
+
+
+def test_act_reshaped_aliases_storage():
+    """The stem's output is written as [n, h, w/4, 256] and read by the max-pool as [n, h, w, 64]: same bytes."""
+    from unipose_b200 import ops
+    a = ops.Act(2, 4, 8, 64, ops.UP_FP16, torch.device("cpu"))
+    a.t.copy_(torch.arange(a.t.numel(), dtype=torch.float32).view_as(a.t) % 251)
+    b = a.reshaped(4, 2, 256)
+    assert (b.n, b.h, b.w, b.c) == (2, 4, 2, 256) and b.t.data_ptr() == a.t.data_ptr()
+    assert torch.equal(b.t.reshape(-1), a.t.reshape(-1)) and b.plane_stride == a.plane_stride
+    with pytest.raises(AssertionError):
+        a.reshaped(4, 8, 32)
+
+
+def test_kernel_table_tool_reads_the_committed_ncu_capture():
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "kernel_table.py"),
+                          os.path.join(root, "profiles", "wasp_block_ncu_metrics_r1.csv")],
+                         capture_output=True, text=True, check=True).stdout
+    assert "conv_tcgen05_kernel<1>" in out and "global_avgpool_kernel<0>" in out and "total" in out
