@@ -128,6 +128,55 @@ int up_pack_conv_weight(const float* w_oihw, void* w_packed, int cout_real, int 
 int up_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                float* scale, float* shift, int c_real, int c, void* stream);
 
+/* Table-driven weight preparation: one launch for every filter / every epilogue constant of a plan (the per-layer
+ * up_pack_conv_weight + up_bn_fold calls above remain for single layers).  Job tables live in DEVICE memory.
+ *
+ * UpPackJob: OIHW fp32 `w` [cout_real][cin_total][kh][kw] -> 16-bit `out` [plane][kh*kw][rows][cols], zero padded.
+ *   transpose = 0 (forward layout): rows = padded cout, cols = padded cin; element (tap, co, ci) = w[co][ci_off+ci][tap]
+ *   transpose = 1 (dgrad layout, what loss.backward() needs for the input gradient): rows = padded input channels of
+ *     the slice [ci_off, ci_off+cin_slice), cols = padded cout; element (tap, ci, co) = w[co][ci_off+ci][taps-1-tap]
+ *   row_scale (optional): every output channel co is multiplied by row_scale[co % scale_period] (folded eval BatchNorm).
+ *   tile_start: exclusive prefix sum of up_pack_job_tiles() over the table (filled by the caller).
+ * UpEpilogueJob: the fp32 [cout] scale / shift vectors of the conv epilogue from an eval-mode BatchNorm2d
+ *   (torch semantics, resnet.py:26-34) or a conv bias; fold_into_weights = 1 writes gamma/sqrt(var+eps) to fold_scale
+ *   [c_bn] (to be used as UpPackJob.row_scale) and leaves scale = 1. */
+typedef struct UpPackJob {
+  const float* w;
+  void* out;
+  const float* row_scale;
+  int64_t plane_stride;   /* UP_SPLIT: elements between the hi and lo planes of `out` */
+  int64_t tile_start;
+  int32_t kh, kw;
+  int32_t rows, cols;
+  int32_t cout_real;
+  int32_t cin_total, ci_off, cin_slice;
+  int32_t scale_period;
+  int32_t dtype;          /* UpDtype */
+  int32_t transpose;
+  int32_t reserved;
+} UpPackJob;
+
+typedef struct UpEpilogueJob {
+  const float* gamma;     /* BatchNorm weight / bias / running_mean / running_var [c_bn]; unused when c_bn == 0 */
+  const float* beta;
+  const float* mean;
+  const float* var;
+  const float* bias;      /* conv bias [bias_len] when c_bn == 0 (may be NULL) */
+  float* fold_scale;      /* [c_bn] or NULL */
+  float* scale;           /* [cout] */
+  float* shift;           /* [cout] */
+  float eps;
+  int32_t c_bn, bias_len;
+  int32_t cout_real, cout;   /* channels >= cout_real get scale = shift = 0; the BN / bias vectors repeat with period
+                                c_bn / bias_len (the stem's four-pixels-per-super-pixel output) */
+  int32_t fold_into_weights;
+  int32_t reserved[2];
+} UpEpilogueJob;
+
+int64_t up_pack_job_tiles(const UpPackJob* h_job);   /* HOST pointer: thread blocks this job needs */
+int up_pack_conv_weights(const UpPackJob* d_jobs, int njobs, int64_t total_tiles, void* stream);
+int up_epilogue_consts(const UpEpilogueJob* d_jobs, int njobs, int max_channels, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Bandwidth kernels (NHWC 16-bit unless noted)
  * ------------------------------------------------------------------------------------------ */
@@ -242,12 +291,20 @@ int up_bn_stats(const UpView* z, int64_t npix, int c, int dtype, double* work, v
 int up_bn_finalize(const double* sums, int64_t count, const float* gamma, const float* beta, float* running_mean,
                    float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
                    float* save_invstd, int c_real, int c, void* stream);
+/* Frozen (eval-mode) BatchNorm inside a training step - the reference's freeze_bn=True / model.freeze_bn()
+ * (model/unipose.py:24-25,40-43): scale/shift from the RUNNING statistics, plus save_mean = running_mean and
+ * save_invstd = 1/sqrt(running_var + eps) for the backward (up_bn_bwd_reduce / up_bn_bwd_apply with relu | 2). */
+int up_bn_eval_prepare(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                       float eps, float* scale, float* shift, float* save_mean, float* save_invstd, int c_real, int c,
+                       void* stream);
 int up_scale_shift_act(const UpView* z, const UpView* y, const UpView* residual, const UpView* mask,
                        const float* scale, const float* shift, int64_t npix, int c, int relu, int dtype,
                        void* stream);
 /* BatchNorm (+ReLU) backward: reduce sum(dy'), sum(dy'*xhat) with dy' = dy*(y>0) -> work[0 .. 2*c); then
  *   dz = gamma*invstd*(dy' - sum_dy/M - xhat*sum_dy_xhat/M), optional dres = dy', dgamma / dbeta (optional).
- * `work` holds up_bn_work_doubles(c) doubles (see up_bn_stats). */
+ * `work` holds up_bn_work_doubles(c) doubles (see up_bn_stats).
+ * `relu` is a bit mask: 1 = gate by the forward output (y > 0); 2 (up_bn_bwd_apply only) = frozen BatchNorm, whose
+ * statistics are constants: dz = gamma*invstd*dy' (dgamma / dbeta unchanged). */
 int up_bn_bwd_reduce(const UpView* dy, const UpView* y, const UpView* z, const float* save_mean,
                      const float* save_invstd, int64_t npix, int c, int relu, int dtype, double* work, void* stream);
 int up_bn_bwd_apply(const UpView* dy, const UpView* y, const UpView* z, const UpView* dz, const UpView* dres,

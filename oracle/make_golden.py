@@ -50,7 +50,31 @@ def check_specs(model, num_classes, video):
     return {k: list(s) for k, s, _ in specs}
 
 
+def round2_fixtures():
+    """Fixtures added in round 2 (the round-1 files are left untouched): BASELINE.json configs[4] geometry
+    (512x512, 17 joints -> 32x32 WASP map, 64x64 heat-maps) and the output_stride=8 variant (layer3/4 dilated,
+    WASP dilations 48/36/24/12: wasp.py:41-42, resnet.py:54-56)."""
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_grad_enabled(False)
+    RefUnipose, _ref_lstm, _ref_eval = import_reference()
+    m5 = RefUnipose(dataset="COCO", num_classes=17).eval()
+    m5.load_state_dict(O.synth_state_dict(17, seed=5), strict=True)
+    x5 = O.synth_input(1, 512, 512, seed=5)
+    np.savez_compressed(os.path.join(OUT, "image_c5_512.npz"), heat=m5(x5).numpy())
+    m8 = RefUnipose(dataset="MPII", num_classes=16, output_stride=8).eval()
+    sd8 = O.synth_state_dict(16, seed=8, output_stride=8)
+    assert list(sd8.keys()) == list(m8.state_dict().keys())
+    m8.load_state_dict(sd8, strict=True)
+    x8 = O.synth_input(2, 128, 128, seed=8)
+    f8, l8 = m8.backbone(x8)
+    np.savez_compressed(os.path.join(OUT, "image_os8_128.npz"), heat=m8(x8).numpy(), feat_s=f8[:, ::16].numpy())
+    for fn in ("image_c5_512.npz", "image_os8_128.npz"):
+        print("%-32s %8.1f KB" % (fn, os.path.getsize(os.path.join(OUT, fn)) / 1024))
+
+
 def main():
+    if "--round2" in sys.argv:
+        return round2_fixtures()
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_grad_enabled(False)

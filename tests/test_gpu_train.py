@@ -101,6 +101,34 @@ def test_train_step_matches_oracle_autograd():
     assert int(bufs["backbone.bn1.num_batches_tracked"]) == 1
 
 
+def test_train_step_config3_geometry_384_bs4():
+    """BASELINE.json configs[2] geometry (384x384 -> 24x24 maps: image-pair tiles, CTA pairs and tap skipping in the
+    dgrad / wgrad kernels, 48x48 decoder maps) at batch 4: loss, heat-maps and gradients from the stem to the head
+    against torch autograd over the CPU oracle (fp32 = the reference's arithmetic, fp64 = ground truth)."""
+    m, sd, x, target, masks = _setup(n=4, size=384, seed=3)
+    from unipose_b200 import train
+    heat = train.forward_train(m, x.cuda(), dropout_masks=[t.cuda() for t in masks])
+    assert heat.shape == (4, 17, 48, 48)
+    loss = F.mse_loss(heat, target.cuda())
+    loss.backward()
+    ref_heat, ref_loss, ref_sd = _oracle_step(sd, x, target, masks)
+    h64, l64, sd64 = _oracle_step(sd, x, target, masks, dtype=torch.float64)
+    assert _rel_l2(heat, h64) < 1e-3
+    assert abs(float(loss.detach()) - float(l64)) < 2e-3 * float(l64)
+    params = dict(m.named_parameters())
+    report = {}
+    for k in CHECK:
+        ours = _rel_l2(params[k].grad, sd64[k].grad)
+        floor = _rel_l2(ref_sd[k].grad, sd64[k].grad)
+        report[k] = (ours, floor, _cos(params[k].grad, sd64[k].grad))
+    print("384^2 bs4 grad rel-L2 (ours vs fp64, reference-fp32 vs fp64, cosine):",
+          {k: "%.1e / %.1e / %.5f" % v for k, v in report.items()})
+    for k, (ours, floor, cos) in report.items():
+        assert ours <= min(max(40.0 * floor, 2e-3), 0.1), (k, ours, floor)
+        assert cos > 0.995, (k, report[k])
+    assert report["decoder.last_conv.8.weight"][0] < 1e-3
+
+
 def test_reference_training_loop_runs_unchanged():
     """optimizer.zero_grad(); heat = model(x); loss = MSELoss(heat, target); loss.backward(); optimizer.step()."""
     m, sd, x, target, masks = _setup(n=2, size=96, seed=1, precision="bf16")

@@ -62,6 +62,38 @@ def test_oracle_lsp_config1_vs_golden():
     _close(heat.numpy(), _load("image_lsp_256.npz")["heat"])
 
 
+def test_oracle_config5_512_and_output_stride8_vs_golden():
+    """Round-2 fixtures from the real reference: BASELINE.json configs[4] geometry (512x512, 17 joints) and the
+    output_stride=8 variant (WASP dilations 48/36/24/12, layer3/4 dilated)."""
+    with torch.no_grad():
+        h5 = O.unipose_forward(O.synth_input(1, 512, 512, seed=5), O.synth_state_dict(17, seed=5))
+        assert h5.shape == (1, 18, 64, 64)
+        _close(h5.numpy(), _load("image_c5_512.npz")["heat"])
+        sd8 = O.synth_state_dict(16, seed=8, output_stride=8)
+        x8 = O.synth_input(2, 128, 128, seed=8)
+        g8 = _load("image_os8_128.npz")
+        f8, _ = O.resnet101_forward(x8, sd8, output_stride=8)
+        _close(f8[:, ::16].numpy(), g8["feat_s"])
+        _close(O.unipose_forward(x8, sd8, output_stride=8).numpy(), g8["heat"])
+
+
+def test_compiled_reference_matches_oracle_when_present():
+    """oracle/_ref (the reference's own modules as byte-code, what bench.py's CPU arm times) == the oracle port."""
+    from oracle import build_ref
+    if not build_ref.have_ref():
+        pytest.skip("oracle/_ref not built (python oracle/build_ref.py needs /root/reference)")
+    RefUnipose, _, ref_eval = build_ref.import_reference()
+    m = RefUnipose(dataset="MPII", num_classes=16).eval()
+    sd = O.synth_state_dict(16, seed=6)
+    m.load_state_dict(sd, strict=True)
+    x = O.synth_input(1, 64, 64, seed=6)
+    with torch.no_grad():
+        _close(O.unipose_forward(x, sd).numpy(), m(x).numpy(), rtol=1e-5, atol=1e-6)
+    gt, pred = E.synth_eval_inputs(4, 16, 48, seed=22)
+    for u, v in zip(ref_eval.accuracy(pred, gt, 0.2, 0.5, "MPII"), E.accuracy(pred, gt, 0.2, 0.5, "MPII")):
+        np.testing.assert_allclose(np.asarray(u, dtype=np.float64), np.asarray(v, dtype=np.float64), rtol=0, atol=1e-12)
+
+
 def test_oracle_video_vs_golden():
     g = _load("video_penn_368.npz")
     sd = O.synth_state_dict(13, video=True, seed=2)

@@ -34,6 +34,21 @@ class UpConvDesc(ctypes.Structure):
     ]
 
 
+class UpPackJob(ctypes.Structure):
+    _fields_ = [("w", c_void_p), ("out", c_void_p), ("row_scale", c_void_p),
+                ("plane_stride", c_int64), ("tile_start", c_int64),
+                ("kh", c_int32), ("kw", c_int32), ("rows", c_int32), ("cols", c_int32),
+                ("cout_real", c_int32), ("cin_total", c_int32), ("ci_off", c_int32), ("cin_slice", c_int32),
+                ("scale_period", c_int32), ("dtype", c_int32), ("transpose", c_int32), ("reserved", c_int32)]
+
+
+class UpEpilogueJob(ctypes.Structure):
+    _fields_ = [("gamma", c_void_p), ("beta", c_void_p), ("mean", c_void_p), ("var", c_void_p), ("bias", c_void_p),
+                ("fold_scale", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
+                ("eps", c_float), ("c_bn", c_int32), ("bias_len", c_int32), ("cout_real", c_int32), ("cout", c_int32),
+                ("fold_into_weights", c_int32), ("reserved", c_int32 * 2)]
+
+
 _P = c_void_p
 _I = c_int
 _L = c_int64
@@ -68,6 +83,7 @@ _SIGNATURES = {
     "up_conv2d_wgrad": [POINTER(UpConvDesc), _P, _P, _P, _I, _I, _P, _L, _I, _P],
     "up_bn_stats": [_P, _L, _I, _I, _P, _P],
     "up_bn_finalize": [_P, _L, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _I, _I, _P],
+    "up_bn_eval_prepare": [_P, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _P],
     "up_scale_shift_act": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
     "up_bn_bwd_reduce": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _P, _P],
     "up_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P, _P, _P],
@@ -76,9 +92,12 @@ _SIGNATURES = {
     "up_upsample_bilinear_ac_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "up_add_broadcast": [_P, _P, _I, _I, _I, _F, _I, _I, _P],
     "up_zero_insert2x": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "up_pack_conv_weights": [_P, _I, _L, _P],
+    "up_epilogue_consts": [_P, _I, _I, _P],
 }
 _RESTYPES = {"up_conv2d_wgrad_scratch_bytes": (c_int64, [POINTER(UpConvDesc)]),
-             "up_bn_work_doubles": (c_int64, [_I])}
+             "up_bn_work_doubles": (c_int64, [_I]),
+             "up_pack_job_tiles": (c_int64, [POINTER(UpPackJob)])}
 
 
 class UpView(ctypes.Structure):

@@ -20,6 +20,28 @@ int check_cuda(cudaError_t e, const char* what) {
   return fail(UP_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
 }
 
+DeviceInfo* device_info() {
+  static DeviceInfo infos[64];
+  int dev = 0;
+  if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return nullptr;
+  if (dev < 0 || dev >= 64) {
+    fail(UP_ERR_UNSUPPORTED, "device index %d out of range", dev);
+    return nullptr;
+  }
+  DeviceInfo& di = infos[dev];
+  if (di.sm_count == 0) {
+    cudaDeviceProp prop;
+    if (check_cuda(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties")) return nullptr;
+    if (prop.major != 10) {
+      fail(UP_ERR_UNSUPPORTED, "unipose_b200 needs an sm_100 class GPU (found sm_%d%d)", prop.major, prop.minor);
+      return nullptr;
+    }
+    di.max_smem = prop.sharedMemPerBlockOptin;
+    di.sm_count = prop.multiProcessorCount;
+  }
+  return &di;
+}
+
 }  // namespace up
 
 extern "C" const char* up_last_error(void) { return up::g_err; }

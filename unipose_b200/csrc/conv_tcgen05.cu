@@ -659,35 +659,21 @@ __global__ void __launch_bounds__(kThreads, 1)
 #include "up_conv_host.h"  // tensor-map encoding + tile picking helpers (shared with the wgrad kernel)
 namespace up {
 
-static int g_sm_count = 0;
 static unsigned long long* g_dbg_last = nullptr;
-static size_t g_max_smem = 0;
-static bool g_attr_set = false;
 
-static int ensure_device() {
-  if (g_sm_count == 0) {
-    int dev = 0;
-    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
-    if (rc) return rc;
-    cudaDeviceProp prop;
-    rc = check_cuda(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
-    if (rc) return rc;
-    if (prop.major != 10) {
-      return fail(UP_ERR_UNSUPPORTED, "unipose_b200 needs an sm_100 class GPU (found sm_%d%d)", prop.major, prop.minor);
-    }
-    g_sm_count = prop.multiProcessorCount;
-    g_max_smem = prop.sharedMemPerBlockOptin;
-  }
-  if (!g_attr_set) {
+static int ensure_device(DeviceInfo*& di) {
+  di = device_info();
+  if (!di) return UP_ERR_CUDA;
+  if (!di->conv_attr) {
     int rc = check_cuda(cudaFuncSetAttribute(conv_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(g_max_smem)),
+                                             static_cast<int>(di->max_smem)),
                         "cudaFuncSetAttribute(max dynamic smem)");
     if (rc) return rc;
     rc = check_cuda(cudaFuncSetAttribute(conv_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(g_max_smem)),
+                                         static_cast<int>(di->max_smem)),
                     "cudaFuncSetAttribute(max dynamic smem, pair)");
     if (rc) return rc;
-    g_attr_set = true;
+    di->conv_attr = true;
   }
   return 0;
 }
@@ -754,8 +740,11 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   UP_CHECK_ARG(d->pad_h <= (d->kh - 1) * d->dil && d->pad_w <= (d->kw - 1) * d->dil,
                "up_conv2d_fwd: padding larger than the filter extent");
 
-  int rc = ensure_device();
+  DeviceInfo* di = nullptr;
+  int rc = ensure_device(di);
   if (rc) return rc;
+  const int g_sm_count = di->sm_count;
+  const size_t g_max_smem = di->max_smem;
 
   const int fmt = fmt_of_dtype(d->dtype);
   ConvKParams p{};
@@ -965,7 +954,7 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   int max_clusters = g_sm_count / p.cluster;
   if (p.cluster > 1) {
     // persistent kernel: never launch more clusters than can be co-resident
-    static int cached[5] = {0, 0, 0, 0, 0};
+    int* cached = di->max_clusters;
     if (cached[p.cluster] == 0) {
       cudaLaunchConfig_t occ{};
       occ.gridDim = dim3(g_sm_count / p.cluster * p.cluster);

@@ -317,28 +317,15 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ scratch, float* __
   *o = accumulate ? (*o + s) : s;
 }
 
-static bool g_wg_attr_set = false;
-static int g_wg_sm_count = 0;
-static size_t g_wg_max_smem = 0;
-
-static int wg_ensure_device() {
-  if (g_wg_sm_count == 0) {
-    int dev = 0;
-    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
-    if (rc) return rc;
-    cudaDeviceProp prop;
-    rc = check_cuda(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
-    if (rc) return rc;
-    if (prop.major != 10) return fail(UP_ERR_UNSUPPORTED, "unipose_b200 needs an sm_100 class GPU");
-    g_wg_sm_count = prop.multiProcessorCount;
-    g_wg_max_smem = prop.sharedMemPerBlockOptin;
-  }
-  if (!g_wg_attr_set) {
+static int wg_ensure_device(DeviceInfo*& di) {
+  di = device_info();
+  if (!di) return UP_ERR_CUDA;
+  if (!di->wgrad_attr) {
     int rc = check_cuda(cudaFuncSetAttribute(conv_wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(g_wg_max_smem)),
+                                             static_cast<int>(di->max_smem)),
                         "cudaFuncSetAttribute(wgrad smem)");
     if (rc) return rc;
-    g_wg_attr_set = true;
+    di->wgrad_attr = true;
   }
   return 0;
 }
@@ -378,7 +365,8 @@ using namespace up;
 extern "C" int64_t up_conv2d_wgrad_scratch_bytes(const UpConvDesc* d) {
   if (!d || d->cin <= 0 || d->cout <= 0) return -1;
   WgradKParams p{};
-  int sm = g_wg_sm_count > 0 ? g_wg_sm_count : 148;
+  DeviceInfo* di = device_info();   // no device (CPU-only host): size for a 148-SM part
+  int sm = di ? di->sm_count : 148;
   if (wgrad_plan(d, p, sm) != 0) return -1;
   // upper bound independent of the SM count actually found later: splits <= 148-ish; be generous
   const int64_t per_split = static_cast<int64_t>(d->kh) * d->kw * d->cout * d->cin * 4;
@@ -398,8 +386,11 @@ extern "C" int up_conv2d_wgrad(const UpConvDesc* d, const void* x, const void* d
   UP_CHECK_ARG(d->y_cstride == d->cout && d->y_coff == 0, "up_conv2d_wgrad: dz must be a dense [n,ho,wo,cout] tensor");
   const int groups = d->x_groups > 0 ? d->x_groups : 1;
   UP_CHECK_ARG(d->cin % groups == 0, "up_conv2d_wgrad: cin not divisible by x_groups");
-  int rc = wg_ensure_device();
+  DeviceInfo* di = nullptr;
+  int rc = wg_ensure_device(di);
   if (rc) return rc;
+  const int g_wg_sm_count = di->sm_count;
+  const size_t g_wg_max_smem = di->max_smem;
 
   const bool split = d->dtype == UP_SPLIT;
   const int fmt = fmt_of_dtype(d->dtype);

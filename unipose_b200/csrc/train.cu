@@ -340,17 +340,20 @@ __global__ void bn_bwd_apply_kernel(TView dy, TView y, TView z, TViewW dz, TView
 
 // k1 = gamma*invstd, k2 = -k1*invstd*m1, k3 = -k1*m0 - k2*mean with m0 = sum_dy/M, m1 = sum_dy_xhat/M; padded
 // channels get zeros.  coef = [k1 | k2 | k3], c floats each.
+// frozen (eval-mode BatchNorm inside a training step: the statistics are constants): dz = gamma*invstd*dy'.
 __global__ void bn_bwd_coef_kernel(const double* __restrict__ sums, double count, const float* __restrict__ mean,
                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                   float* __restrict__ coef, int c_real, int c) {
+                                   float* __restrict__ coef, int c_real, int c, int frozen) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c) return;
   double k1 = 0.0, k2 = 0.0, k3 = 0.0;
   if (i < c_real) {
     const double m0 = sums[i] / count, m1 = sums[c + i] / count;
     k1 = static_cast<double>(gamma[i]) * invstd[i];
-    k2 = -k1 * invstd[i] * m1;
-    k3 = -k1 * m0 - k2 * mean[i];
+    if (!frozen) {
+      k2 = -k1 * invstd[i] * m1;
+      k3 = -k1 * m0 - k2 * mean[i];
+    }
   }
   coef[i] = static_cast<float>(k1);
   coef[c + i] = static_cast<float>(k2);
@@ -730,6 +733,39 @@ extern "C" int up_bn_finalize(const double* sums, int64_t count, const float* ga
   return 0;
 }
 
+namespace up {
+__global__ void bn_eval_prepare_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       const float* __restrict__ rmean, const float* __restrict__ rvar, float eps,
+                                       float* __restrict__ scale, float* __restrict__ shift,
+                                       float* __restrict__ save_mean, float* __restrict__ save_invstd, int c_real, int c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  float sc = 0.f, sh = 0.f, m = 0.f, is = 0.f;
+  if (i < c_real) {
+    is = 1.0f / sqrtf(rvar[i] + eps);     // ATen's inference order: invstd, then gamma * invstd
+    m = rmean[i];
+    sc = gamma[i] * is;
+    sh = beta[i] - m * sc;
+  }
+  scale[i] = sc;
+  shift[i] = sh;
+  save_mean[i] = m;
+  save_invstd[i] = is;
+}
+}  // namespace up
+
+extern "C" int up_bn_eval_prepare(const float* gamma, const float* beta, const float* running_mean,
+                                  const float* running_var, float eps, float* scale, float* shift, float* save_mean,
+                                  float* save_invstd, int c_real, int c, void* stream) {
+  UP_CHECK_ARG(gamma && beta && running_mean && running_var && scale && shift && save_mean && save_invstd,
+               "up_bn_eval_prepare: null argument");
+  UP_CHECK_ARG(c_real > 0 && c >= c_real, "up_bn_eval_prepare: bad channel counts");
+  up::bn_eval_prepare_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      gamma, beta, running_mean, running_var, eps, scale, shift, save_mean, save_invstd, c_real, c);
+  UP_CHECK_LAUNCH("bn_eval_prepare_kernel");
+  return 0;
+}
+
 extern "C" int up_scale_shift_act(const UpView* z, const UpView* y, const UpView* residual, const UpView* mask,
                                   const float* scale, const float* shift, int64_t npix, int c, int relu, int dtype,
                                   void* stream) {
@@ -779,14 +815,16 @@ extern "C" int up_bn_bwd_apply(const UpView* dy, const UpView* y, const UpView* 
   if (rc) return rc;
   rc = check_view("up_bn_bwd_apply(dz)", dz, c);
   if (rc) return rc;
-  if (relu && (rc = check_view("up_bn_bwd_apply(y)", y, c))) return rc;
+  if ((relu & 1) && (rc = check_view("up_bn_bwd_apply(y)", y, c))) return rc;
   if (dres && (rc = check_view("up_bn_bwd_apply(dres)", dres, c))) return rc;
   UP_CHECK_ARG(save_mean && save_invstd && gamma && sums && npix > 0 && c_real <= c, "up_bn_bwd_apply: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // per-channel coefficients: 3*c floats right behind the 2*c reduction doubles (the work buffer holds 4*c doubles)
   float* coef = reinterpret_cast<float*>(sums + 2 * c);
+  const int frozen = (relu & 2) ? 1 : 0;
+  relu &= 1;
   up::bn_bwd_coef_kernel<<<(c + 127) / 128, 128, 0, st>>>(sums, static_cast<double>(npix), save_mean, save_invstd, gamma,
-                                                           coef, c_real, c);
+                                                           coef, c_real, c, frozen);
   UP_CHECK_LAUNCH("bn_bwd_coef_kernel");
   UP_T_DISPATCH(dtype, (up::bn_bwd_apply_kernel<kMode><<<blocks_for(npix*(c / 8)), 256, 0, st>>>(
                            tv(dy), tv(y), tv(z), tvw(dz), tvw(dres), coef, npix, c, relu, dres != nullptr)));

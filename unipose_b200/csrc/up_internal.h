@@ -15,6 +15,19 @@ namespace up {
 int fail(int code, const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 
+// Per-device facts and one-time kernel attributes (cudaFuncSetAttribute is per device): indexed by cudaGetDevice(), so
+// a process that drives several GPUs - or a model on cuda:1 - gets the right SM count / shared-memory opt-in.
+struct DeviceInfo {
+  int sm_count = 0;
+  size_t max_smem = 0;
+  bool conv_attr = false;    // conv_tcgen05_kernel<*> MaxDynamicSharedMemorySize set on this device
+  bool wgrad_attr = false;   // conv_wgrad_tcgen05_kernel
+  bool chain_attr = false;   // wasp_chain_kernel
+  int max_clusters[5] = {0, 0, 0, 0, 0};   // cached cudaOccupancyMaxActiveClusters by cluster size
+};
+// Info of the CURRENT device (validated to be sm_100 class); nullptr + error message on failure.
+DeviceInfo* device_info();
+
 #define UP_CHECK_ARG(cond, ...)                                \
   do {                                                         \
     if (!(cond)) return ::up::fail(UP_ERR_INVALID, __VA_ARGS__); \

@@ -39,8 +39,9 @@ def _max_preds_device(heat: torch.Tensor):
     idx = torch.empty((n, k), dtype=torch.int32, device=heat.device)
     preds = torch.empty((n, k, 2), dtype=torch.float32, device=heat.device)
     maxvals = torch.empty((n, k), dtype=torch.float32, device=heat.device)
-    _lib.call("up_argmax2d", ops._ptr(heat), ops._ptr(idx), ops._ptr(preds), ops._ptr(maxvals), n, k, h, w,
-              ops._stream())
+    with torch.cuda.device(heat.device):     # launches go to the current device's stream
+        _lib.call("up_argmax2d", ops._ptr(heat), ops._ptr(idx), ops._ptr(preds), ops._ptr(maxvals), n, k, h, w,
+                  ops._stream())
     return idx, preds, maxvals
 
 
@@ -59,8 +60,9 @@ def argmax_indices(batch_heatmaps) -> torch.Tensor:
 def _calc_dists_device(preds: torch.Tensor, target: torch.Tensor, norm_xy):
     n, k, _ = preds.shape
     dists = torch.empty((k, n), dtype=torch.float64, device=preds.device)
-    _lib.call("up_calc_dists", ops._ptr(preds), ops._ptr(target), ops._ptr(dists), n, k,
-              ctypes.c_double(norm_xy[0]), ctypes.c_double(norm_xy[1]), ops._stream())
+    with torch.cuda.device(preds.device):
+        _lib.call("up_calc_dists", ops._ptr(preds), ops._ptr(target), ops._ptr(dists), n, k,
+                  ctypes.c_double(norm_xy[0]), ctypes.c_double(norm_xy[1]), ops._stream())
     return dists
 
 
@@ -74,7 +76,8 @@ def calc_dists(preds, target, normalize):
 def _dist_acc_device(dists: torch.Tensor, threshold: float) -> torch.Tensor:
     k, n = dists.shape
     acc = torch.empty((k,), dtype=torch.float64, device=dists.device)
-    _lib.call("up_dist_acc", ops._ptr(dists), ops._ptr(acc), n, k, ctypes.c_double(threshold), ops._stream())
+    with torch.cuda.device(dists.device):
+        _lib.call("up_dist_acc", ops._ptr(dists), ops._ptr(acc), n, k, ctypes.c_double(threshold), ops._stream())
     return acc
 
 

@@ -55,9 +55,12 @@ class unipose(PlanModule):
 
     def forward(self, input):
         self._check_inputs([input])
-        if self.training and any(m.training for m in self.modules() if isinstance(m, nn.BatchNorm2d)):
+        if self.training:
+            # train mode = the autograd-carrying training plan (dropout live); BatchNorm layers that were put in eval
+            # mode - freeze_bn=True / model.freeze_bn(), model/unipose.py:24-25,40-43 - use their running statistics
             from .. import train
             return train.forward_train(self, input)
+        self._bn_eval_only()
         plan = self.plan_for(input)
         src = input.detach()
         if src.dtype != torch.float32:

@@ -38,10 +38,18 @@ class LSTM_0(PlanModule):
     def _gates(self):
         return (self.conv_g_lstm, self.conv_i_lstm, self.conv_o_lstm)
 
-    def launch(self, x, cell, hide):
-        """x fp32 NCHW (contiguous, CUDA) -> cell, hide written in place."""
-        w3 = torch.stack([c.weight.detach().float() for c in self._gates()]).contiguous()
-        b3 = torch.stack([c.bias.detach().float() for c in self._gates()]).contiguous()
+    def stacked(self):
+        """(weights [3, c, cin, 3, 3], biases [3, c]) in gate order g, i, o - what up_convlstm_cell0_fwd reads."""
+        return (torch.stack([c.weight.detach().float() for c in self._gates()]).contiguous(),
+                torch.stack([c.bias.detach().float() for c in self._gates()]).contiguous())
+
+    def sources(self):
+        return [p for c in self._gates() for p in (c.weight, c.bias)]
+
+    def launch(self, x, cell, hide, stacked=None):
+        """x fp32 NCHW (contiguous, CUDA) -> cell, hide written in place.  `stacked`: pre-stacked gate weights (plans
+        keep them in static buffers refreshed by a pack job, so a captured graph never bakes a temporary's address)."""
+        w3, b3 = stacked if stacked is not None else self.stacked()
         b, cin, h, w = x.shape
         ops._lib.call("up_convlstm_cell0_fwd", ops._ptr(x), ops._ptr(w3), ops._ptr(b3), ops._ptr(cell), ops._ptr(hide),
                       b, cin, w3.shape[1], h, w, ops._stream())
@@ -52,7 +60,8 @@ class LSTM_0(PlanModule):
         planes = self.conv_g_lstm.out_channels
         cell = torch.empty((x.shape[0], planes, x.shape[2], x.shape[3]), device=x.device)
         hide = torch.empty_like(cell)
-        self.launch(x, cell, hide)
+        with torch.cuda.device(x.device):
+            self.launch(x, cell, hide)
         return cell, hide
 
 
@@ -70,9 +79,15 @@ class LSTM(PlanModule):
         return (torch.stack([c.weight.detach().float() for c in convs]).contiguous(),
                 torch.stack([c.bias.detach().float() for c in convs]).contiguous())
 
-    def launch(self, x, h_prev, c_prev, cell, hide):
-        wx, bx = self._stacked('x')
-        wh, bh = self._stacked('h')
+    def stacked(self):
+        return self._stacked('x') + self._stacked('h')
+
+    def sources(self):
+        return [p for sfx in 'xh' for g in 'giof' for p in (getattr(self, 'conv_%s%s_lstm' % (g, sfx)).weight,
+                                                            getattr(self, 'conv_%s%s_lstm' % (g, sfx)).bias)]
+
+    def launch(self, x, h_prev, c_prev, cell, hide, stacked=None):
+        wx, bx, wh, bh = stacked if stacked is not None else self.stacked()
         b, cin, h, w = x.shape
         ops._lib.call("up_convlstm_cell_fwd", ops._ptr(x), ops._ptr(h_prev), ops._ptr(c_prev), ops._ptr(wx),
                       ops._ptr(bx), ops._ptr(wh), ops._ptr(bh), ops._ptr(cell), ops._ptr(hide), b, cin, wx.shape[1],
@@ -87,7 +102,8 @@ class LSTM(PlanModule):
         cp = _nchw_state(prevCell, b, planes, h, w, 'prevCell')
         cell = torch.empty_like(hp)
         hide = torch.empty_like(hp)
-        self.launch(x, hp, cp, cell, hide)
+        with torch.cuda.device(x.device):
+            self.launch(x, hp, cp, cell, hide)
         return cell, hide
 
 
@@ -131,12 +147,19 @@ class unipose(PlanModule):
         planes = self.lstm_0.conv_g_lstm.out_channels
         cell = b.tensor((b_, planes, hs, ws))
         hide = b.tensor((b_, planes, hs, ws))
+        cell_mod = self.lstm_0 if first else self.lstm
+        gate_w = [torch.empty_like(t) for t in cell_mod.stacked()]      # static: refreshed in place by a pack job
+
+        def restack():
+            for dst, src in zip(gate_w, cell_mod.stacked()):
+                dst.copy_(src)
+        plan.pack_jobs.append(engine._PackJob(cell_mod.sources(), restack))
         if first:
-            b.add(lambda: self.lstm_0.launch(cat, cell, hide), "lstm_0")
+            b.add(lambda: self.lstm_0.launch(cat, cell, hide, stacked=gate_w), "lstm_0")
         else:
             hp = plan.static_input((b_, planes, hs, ws))
             cp = plan.static_input((b_, planes, hs, ws))
-            b.add(lambda: self.lstm.launch(cat, hp, cp, cell, hide), "lstm")
+            b.add(lambda: self.lstm.launch(cat, hp, cp, cell, hide, stacked=gate_w), "lstm")
         hin = b.act(b_, hs, ws, 16, zero=True)
         b.add(lambda: ops.nchw_to_act(hide, hin), "hide_to_nhwc")
         a1 = b.act(b_, hs, ws, 128)

@@ -363,15 +363,23 @@ def scale_shift_act(z, y, scale, shift, *, relu: bool, residual=None, mask=None)
               zv.n * zv.h * zv.w, zv.c, 1 if relu else 0, zv.act.mode, _stream())
 
 
-def bn_bwd(dy, y, z, dz, dres, save_mean, save_invstd, gamma, sums, c_real: int, relu: bool, dgamma, dbeta) -> None:
+def bn_eval_prepare(bn, scale, shift, save_mean, save_invstd, c_real: int, c: int) -> None:
+    """Frozen (eval-mode) BatchNorm of a training step: epilogue constants + backward statistics from running stats."""
+    _lib.call("up_bn_eval_prepare", _ptr(bn.weight.detach()), _ptr(bn.bias.detach()), _ptr(bn.running_mean),
+              _ptr(bn.running_var), float(bn.eps), _ptr(scale), _ptr(shift), _ptr(save_mean), _ptr(save_invstd), c_real, c,
+              _stream())
+
+
+def bn_bwd(dy, y, z, dz, dres, save_mean, save_invstd, gamma, sums, c_real: int, relu: bool, dgamma, dbeta,
+           frozen: bool = False) -> None:
     dv = as_view(dy)
     npix = dv.n * dv.h * dv.w
     assert sums.numel() >= bn_work_doubles(dv.c), "bn_bwd: work buffer smaller than ops.bn_work_doubles(c)"
     _lib.call("up_bn_bwd_reduce", _vref(dv), _vref(y) if relu else None, _vref(z), _ptr(save_mean), _ptr(save_invstd),
               npix, dv.c, 1 if relu else 0, dv.act.mode, _ptr(sums), _stream())
     _lib.call("up_bn_bwd_apply", _vref(dv), _vref(y) if relu else None, _vref(z), _vref(dz), _vref(dres),
-              _ptr(save_mean), _ptr(save_invstd), _ptr(gamma), _ptr(sums), npix, c_real, dv.c, 1 if relu else 0,
-              dv.act.mode, _ptr(dgamma), _ptr(dbeta), _stream())
+              _ptr(save_mean), _ptr(save_invstd), _ptr(gamma), _ptr(sums), npix, c_real, dv.c,
+              (1 if relu else 0) | (2 if frozen else 0), dv.act.mode, _ptr(dgamma), _ptr(dbeta), _stream())
 
 
 def ew(a, out, *, m=None, op: int = 0, accumulate: bool = False) -> None:

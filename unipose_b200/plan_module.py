@@ -43,13 +43,9 @@ class PlanModule(nn.Module):
     def _plan_cache(self) -> Dict:
         return self._plans
 
-    def train(self, mode: bool = True):
-        # plans bake the train/eval decision of every BatchNorm -> drop them when it changes
-        if mode != self.training:
-            for m in self.modules():
-                if isinstance(m, PlanModule):
-                    m._plans.clear()
-        return super().train(mode)
+    # Plans survive .train() / .eval() flips: inference plans are only used when every BatchNorm is in eval mode (their
+    # packed weights follow the parameters through engine.WeightTable), training plans are keyed by the set of frozen
+    # BatchNorm layers - so an epoch loop that alternates training and validation rebuilds nothing.
 
     def _check_inputs(self, tensors: Sequence[torch.Tensor]) -> None:
         for t in tensors:
@@ -61,8 +57,12 @@ class PlanModule(nn.Module):
             break
 
     def _bn_eval_only(self) -> None:
-        for m in self.modules():
-            if isinstance(m, nn.BatchNorm2d) and m.training:
+        bns = self.__dict__.get("_bn_list")
+        if bns is None:
+            bns = [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)]
+            object.__setattr__(self, "_bn_list", bns)
+        for m in bns:
+            if m.training:
                 raise NotImplementedError(
                     "unipose_b200: train-mode BatchNorm (batch statistics) is only supported through the training "
                     "step API (unipose_b200.train); call .eval() or freeze_bn() for inference")

@@ -43,7 +43,8 @@ class TrainPlan:
         self.bwd: List = []
         self.tape: List = []
         self.buffers: List = []
-        self.pack_jobs: List = []          # refilled every step (weights change every step)
+        self.weights = engine.WeightTable(self.device, self.mode, always=True)   # refilled every step
+        self.fwd_counter = 0
         self.grads: Dict[int, Act] = {}    # id(forward Act) -> gradient Act
         self.written: List[Tuple] = []     # gradient regions that already hold a value
         self.pgrad: Dict[int, torch.Tensor] = {}
@@ -108,25 +109,25 @@ class TrainPlan:
         return g
 
     # ---- weights ---------------------------------------------------------------------------------
-    def packed(self, weight_src, cout: int, cin: int, bias=None) -> PackedConv:
-        """Packed weights refreshed every step from `weight_src()` (an OIHW fp32 tensor); scale 1, shift = bias."""
-        w0 = weight_src()
+    def packed(self, conv: nn.Conv2d, cout: int, cin: int, *, weight_fn=None, transpose: bool = False, ci_off: int = 0,
+               cin_slice: Optional[int] = None, use_bias: bool = False) -> PackedConv:
+        """Packed filter of `conv`, refilled every step by the plan's weight table (ONE launch for all filters).
+        transpose=True is the dgrad layout of the input-channel slice [ci_off, ci_off+cin_slice): rows = those input
+        channels (padded to `cout`), cols = the conv's output channels (padded to `cin`), taps flipped."""
+        w0 = conv.weight.detach() if weight_fn is None else weight_fn(conv.weight.detach())
         co_r, ci_r, kh, kw = w0.shape
         planes = 2 if self.mode == ops.UP_SPLIT else 1
         dt = torch.float16 if self.mode == ops.UP_FP16 else torch.bfloat16
         wbuf = torch.empty((planes, kh * kw, cout, cin), dtype=dt, device=self.device)
-        scale = torch.zeros(cout, dtype=torch.float32, device=self.device)
-        scale[:co_r] = 1.0
-        shift = torch.zeros(cout, dtype=torch.float32, device=self.device)
-        pc = PackedConv(wbuf, scale, shift, kh, kw, cout, cin, co_r, ci_r, self.mode)
-
-        def fill():
-            w = weight_src().float().contiguous()
-            ops._lib.call("up_pack_conv_weight", ops._ptr(w), ops._ptr(wbuf), co_r, ci_r, kh, kw, cout, cin, self.mode,
-                          kh * kw * cout * cin, ops._stream())
-            if bias is not None:
-                shift[:co_r] = bias.detach().float()
-        self.pack_jobs.append(fill)
+        scale = torch.empty(cout, dtype=torch.float32, device=self.device)
+        shift = torch.empty(cout, dtype=torch.float32, device=self.device)
+        rows_real = (cin_slice if cin_slice is not None else ci_r - ci_off) if transpose else co_r
+        cols_real = co_r if transpose else ci_r
+        pc = PackedConv(wbuf, scale, shift, kh, kw, cout, cin, rows_real, cols_real, self.mode)
+        bias = (lambda: conv.bias) if (use_bias and conv.bias is not None) else None
+        self.weights.add_epilogue(scale, shift, rows_real, bias=bias)
+        self.weights.add_pack(lambda: conv.weight, wbuf, cout, cin, transpose=transpose, ci_off=ci_off,
+                              cin_slice=cin_slice, weight_fn=weight_fn)
         return pc
 
     # ---- ops with adjoints --------------------------------------------------------------------------
@@ -150,7 +151,7 @@ class TrainPlan:
         if x_window is not None:
             ho, wo = h_in, w_in          # the stem: explicit output size, asymmetric padding
         n = xv.n
-        pc = self.packed(w_src, cout, cin, bias=None if bn is not None else conv.bias)
+        pc = self.packed(conv, cout, cin, weight_fn=weight_fn, use_bias=bn is None)
         kw_conv = dict(stride=stride, dil=dil, pad=pad, ho=ho, wo=wo, x_groups=x_groups,
                        x_group_nstride=x_group_nstride, x_window=x_window)
         z = out if (bn is None and out is not None) else self.act(n, ho, wo, cout)
@@ -183,11 +184,15 @@ class TrainPlan:
             scale, shift, mean, invstd = (self.tensor((c,)) for _ in range(4))
             y = out if out is not None else self.act(n, ho, wo, cout)
             count = n * ho * wo
-            self.bn_modules.append(bn)
-            self.fwd.append(lambda: ops.bn_stats(z, c, sums))
-            self.fwd.append(lambda: ops.bn_finalize(sums, count, bn, scale, shift, mean, invstd, co_r, c))
+            frozen = not bn.training      # freeze_bn(): running statistics, no update (model/unipose.py:40-43)
+            if frozen:
+                self.fwd.append(lambda: ops.bn_eval_prepare(bn, scale, shift, mean, invstd, co_r, c))
+            else:
+                self.bn_modules.append(bn)
+                self.fwd.append(lambda: ops.bn_stats(z, c, sums))
+                self.fwd.append(lambda: ops.bn_finalize(sums, count, bn, scale, shift, mean, invstd, co_r, c))
             self.fwd.append(lambda: ops.scale_shift_act(z, y, scale, shift, relu=relu, residual=residual, mask=mask))
-            rec.update(sums=sums, mean=mean, invstd=invstd)
+            rec.update(sums=sums, mean=mean, invstd=invstd, frozen=frozen)
         rec["y"] = y
         self.tape.append(lambda: self._conv_unit_bwd(rec))
         return y
@@ -230,8 +235,9 @@ class TrainPlan:
                         self.mark_written(rv)
                 dgamma, dbeta = self.param_grad(bn.weight), self.param_grad(bn.bias)
                 sums, mean, invstd, relu, co_r = r["sums"], r["mean"], r["invstd"], r["relu"], r["co_r"]
+                frozen = r["frozen"]
                 self.bwd.append(lambda: ops.bn_bwd(dy, y, z, dz, dres, mean, invstd, bn.weight.detach(), sums, co_r,
-                                                   relu, dgamma, dbeta))
+                                                   relu, dgamma, dbeta, frozen=frozen))
                 if dres_tmp is not None:
                     self.bwd.append(lambda: ops.ew(dres_tmp, rv, accumulate=True))
         dzv = as_view(dz)
@@ -267,13 +273,8 @@ class TrainPlan:
         cg_pad = r["cin"] // groups
         wfn = r["weight_fn"]
         for g in range(groups):
-            def w_t(g=g):
-                w = conv.weight.detach()
-                if wfn is not None:
-                    w = wfn(w)
-                w = w[:, g * cg_real:(g + 1) * cg_real]
-                return w.flip(2, 3).transpose(0, 1)
-            pct = self.packed(w_t, cout=cg_pad if groups > 1 else xv.c, cin=cout)
+            pct = self.packed(conv, cout=cg_pad if groups > 1 else xv.c, cin=cout, weight_fn=wfn, transpose=True,
+                              ci_off=g * cg_real, cin_slice=cg_real)
             xg = View(self.grad_act(xv.act), coff=xv.coff, c=xv.c, n_off=xv.n_off + g * r["x_group_nstride"], n=xv.n)
             res = xg if self.is_written(xg) else None
             self.mark_written(xg)
@@ -350,21 +351,27 @@ class TrainPlan:
         self.scratch = torch.empty(max(self.scratch_bytes // 4, 1), dtype=torch.float32, device=self.device)
 
     def run_forward(self, x: torch.Tensor, masks: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+        with torch.cuda.device(self.device):     # C-ABI launches use the current device's stream
+            return self._run_forward(x, masks)
+
+    def _run_forward(self, x, masks):
         self.input.copy_(x)
-        for job in self.pack_jobs:
-            job()
+        self.weights.refresh()
         self._fill_masks(masks)
+        self.fwd_counter += 1
         for op in self.fwd:
             op()
         for bn in self.bn_modules:
             if bn.num_batches_tracked is not None:
                 bn.num_batches_tracked.add_(1)
+        engine.note_raw_parameter_update()      # running statistics changed behind torch's version counters
         return self.heat
 
     def run_backward(self, dheat: torch.Tensor) -> None:
-        self.dheat.copy_(dheat)
-        for op in self.bwd:
-            op()
+        with torch.cuda.device(self.device):
+            self.dheat.copy_(dheat)
+            for op in self.bwd:
+                op()
 
     def _fill_masks(self, given) -> None:
         for i, (act, p) in enumerate(self.masks):
@@ -412,9 +419,6 @@ def build_image_train_plan(model, shape, device, precision: str, flat: bool = Fa
     tp = TrainPlan(device, precision)
     tp.input = torch.zeros(shape, dtype=torch.float32, device=device)
     bb, wasp, dec = model.backbone, model.wasp, model.decoder
-    for m in model.modules():
-        if isinstance(m, nn.BatchNorm2d) and not m.training:
-            raise NotImplementedError("unipose_b200: training with frozen (eval-mode) BatchNorm layers is not supported yet")
 
     # ---- backbone ----
     x2 = tp.act(n, h // 2, w // 2 + 3, 16, zero=True)
@@ -488,11 +492,16 @@ class _TrainFn(torch.autograd.Function):
     def forward(ctx, plan: TrainPlan, masks, x, *params):
         ctx.plan = plan
         heat = plan.run_forward(x.detach().float(), masks)
+        ctx.counter = plan.fwd_counter
         return heat.clone()
 
     @staticmethod
     def backward(ctx, dheat):
         plan: TrainPlan = ctx.plan
+        if plan.fwd_counter != ctx.counter:
+            # the plan keeps ONE set of saved activations per input shape: a second forward overwrote them
+            raise RuntimeError("unipose_b200: backward() after another forward() of the same shape - the training plan "
+                               "keeps one set of activations (call backward before the next forward)")
         plan.run_backward(dheat.detach().float().contiguous())
         grads = tuple(plan.pgrad[id(p)].clone() for p in plan.params)
         return (None, None, None) + grads
@@ -503,7 +512,8 @@ def forward_train(model, input: torch.Tensor, dropout_masks=None) -> torch.Tenso
     `dropout_masks`: optional three pre-scaled fp32 NCHW masks (wasp, decoder 0.5, decoder 0.1) for parity tests."""
     if getattr(model, "stride", 8) != 8:
         raise NotImplementedError("unipose_b200: training supports stride=8 outputs (the reference's training setting)")
-    key = ("train", tuple(input.shape), model._precision(), input.device.index)
+    frozen_sig = tuple(m.training for m in model.modules() if isinstance(m, nn.BatchNorm2d))
+    key = ("train", tuple(input.shape), model._precision(), input.device.index, frozen_sig)
     plan = model._plans.get(key)
     if plan is None:
         plan = build_image_train_plan(model, tuple(input.shape), input.device, model._precision())
@@ -579,6 +589,7 @@ class TrainStep:
         else:
             self._fwd_loss_bwd(self.target_buf, world)
         self.steps_done += 1
+        engine.note_raw_parameter_update()     # Adam / BatchNorm statistics move behind torch's version counters
         parallel.allreduce_sum_(self.flat_g)   # gradients were pre-scaled by 1/world in the MSE kernel
         self.t += 1
         ops._lib.call("up_adam_step", ops._ptr(self.flat_p), ops._ptr(self.flat_g), ops._ptr(self.exp_avg),
