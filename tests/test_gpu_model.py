@@ -137,7 +137,7 @@ def test_config5_512_17joints_vs_golden_and_oracle():
     r16 = _rel(h16, ref)
     print("config 5 (512x512, K=17): fp32-grade max-rel %.3g (bs1 vs reference) / %.3g (bs4 vs oracle); fp16 %.3g"
           % (r1, r4, r16))
-    assert r16 < 2e-2, r16
+    assert r16 < 5e-3, r16      # measured 1.4e-3
 
 
 def test_output_stride8_vs_golden_and_oracle():
@@ -166,7 +166,7 @@ def test_output_stride8_vs_golden_and_oracle():
 
 # Stated bounds of the single-pass throughput modes at BASELINE.json configs[1] (max|err| / max|ref| vs the fp32
 # oracle): fp16 keeps 11 mantissa bits per stored activation, bf16 8.
-THROUGHPUT_BOUND_C2 = {"fp16": 1e-2, "bf16": 6e-2}
+THROUGHPUT_BOUND_C2 = {"fp16": 5e-3, "bf16": 3e-2}      # measured on B200: 1.7e-3 / 1.6e-2
 
 
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
