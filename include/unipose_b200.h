@@ -113,6 +113,41 @@ typedef struct UpConvDesc {
 int up_conv2d_fwd(const UpConvDesc* desc, const void* x, const void* w_packed, const float* scale,
                   const float* shift, const void* residual, void* y, float* stats, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * The whole WASP block as ONE persistent kernel (eval mode, fp16 / bf16): wasp.forward, model/modules/wasp.py:66-90
+ * (waspVideo.py:67-91 with shift_gap = 0).  aspp1 -> aspp2 -> aspp3 -> aspp4 cascade with per-image dependencies (no
+ * grid barrier), conv1 accumulated stage by stage from the on-chip tiles, pooling branch folded into a per-image bias.
+ * Filters are the packed / folded ones the layer-wise plan uses (BatchNorm scales folded in, conv2 o conv2 folded into
+ * conv1); `gap_t` and `conv1_pool_t` are TRANSPOSED packings (UpPackJob.transpose = 1).
+ *   x [n,h,w,cin] dense NHWC 16-bit;  s_stack [4n,h,w,256]: receives x1..x4 (stage s at images [s*n, (s+1)*n));
+ *   out [n,h,w,256];  workspace: up_wasp_chain_workspace_bytes() bytes, 256-byte aligned, ZEROED ONCE by the caller
+ *   (the kernel re-arms its counters itself).  up_wasp_chain_supported() == 0 when the shape can take this path
+ *   (otherwise callers run the layer-wise convolutions).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct UpWaspChainDesc {
+  int32_t n, h, w, cin;
+  int32_t dil[3];        /* dilation (= padding) of aspp2 / aspp3 / aspp4 */
+  int32_t dtype;         /* UP_FP16 or UP_BF16 */
+  int32_t conv1_cin;     /* K of the packed conv1' filter: 5 groups of 256 */
+} UpWaspChainDesc;
+
+typedef struct UpWaspChainWeights {
+  const void* aspp[4];        /* packed [taps][256][cin_s] */
+  const float* shift[4];      /* [256] BatchNorm shifts */
+  const void* conv1;          /* packed [1][256][conv1_cin] */
+  const float* shift1;        /* bn1 shift [256] */
+  const void* gap_t;          /* pooling-branch 1x1, transposed packing [1][cin][256] */
+  const float* shift_gap;     /* [256] */
+  const void* conv1_pool_t;   /* conv1' group 5 (pooling branch), transposed packing [1][256][256] */
+} UpWaspChainWeights;
+
+int up_wasp_chain_supported(const UpWaspChainDesc* desc);
+int64_t up_wasp_chain_workspace_bytes(const UpWaspChainDesc* desc);
+int up_wasp_chain_fwd(const UpWaspChainDesc* desc, const UpWaspChainWeights* weights, const void* x, void* s_stack,
+                      void* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Debug aid (UP_DEBUG_TIMING=1): per-CTA phase timestamps (ns) of the last up_wasp_chain_fwd launch, 160 CTAs x 32 slots. */
+int up_debug_chain_timing(unsigned long long* h_out);
 /* Debug aid (UP_DEBUG_TIMING=1 in the environment): per-CTA phase timestamps (ns) of the last up_conv2d_fwd launch,
  * 160 CTAs x 16 slots, copied to host memory (synchronising). */
 int up_debug_conv_timing(unsigned long long* h_out);

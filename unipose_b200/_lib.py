@@ -49,6 +49,16 @@ class UpEpilogueJob(ctypes.Structure):
                 ("fold_into_weights", c_int32), ("reserved", c_int32 * 2)]
 
 
+class UpWaspChainDesc(ctypes.Structure):
+    _fields_ = [("n", c_int32), ("h", c_int32), ("w", c_int32), ("cin", c_int32), ("dil", c_int32 * 3),
+                ("dtype", c_int32), ("conv1_cin", c_int32)]
+
+
+class UpWaspChainWeights(ctypes.Structure):
+    _fields_ = [("aspp", c_void_p * 4), ("shift", c_void_p * 4), ("conv1", c_void_p), ("shift1", c_void_p),
+                ("gap_t", c_void_p), ("shift_gap", c_void_p), ("conv1_pool_t", c_void_p)]
+
+
 _P = c_void_p
 _I = c_int
 _L = c_int64
@@ -80,6 +90,7 @@ _SIGNATURES = {
     "up_mse_fwd_bwd": [_P, _P, _P, _P, _P, _L, _F, _P],
     "up_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P],
     "up_debug_conv_timing": [_P],
+    "up_debug_chain_timing": [_P],
     "up_conv2d_wgrad": [POINTER(UpConvDesc), _P, _P, _P, _I, _I, _P, _L, _I, _P],
     "up_bn_stats": [_P, _L, _I, _I, _P, _P],
     "up_bn_finalize": [_P, _L, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _I, _I, _P],
@@ -93,11 +104,14 @@ _SIGNATURES = {
     "up_add_broadcast": [_P, _P, _I, _I, _I, _F, _I, _I, _P],
     "up_zero_insert2x": [_P, _P, _I, _I, _I, _I, _I, _P],
     "up_pack_conv_weights": [_P, _I, _L, _P],
+    "up_wasp_chain_supported": [POINTER(UpWaspChainDesc)],
+    "up_wasp_chain_fwd": [POINTER(UpWaspChainDesc), POINTER(UpWaspChainWeights), _P, _P, _P, _P, _L, _P],
     "up_epilogue_consts": [_P, _I, _I, _P],
 }
 _RESTYPES = {"up_conv2d_wgrad_scratch_bytes": (c_int64, [POINTER(UpConvDesc)]),
              "up_bn_work_doubles": (c_int64, [_I]),
-             "up_pack_job_tiles": (c_int64, [POINTER(UpPackJob)])}
+             "up_pack_job_tiles": (c_int64, [POINTER(UpPackJob)]),
+             "up_wasp_chain_workspace_bytes": (c_int64, [POINTER(UpWaspChainDesc)])}
 
 
 class UpView(ctypes.Structure):

@@ -254,15 +254,40 @@ class Builder:
         wbuf = torch.empty((planes, kh * kw, cout, cin), dtype=dt, device=self.device)
         scale = torch.empty(cout, dtype=torch.float32, device=self.device)
         shift = torch.empty(cout, dtype=torch.float32, device=self.device)
-        pc = PackedConv(wbuf, scale, shift, kh, kw, cout, cin, co_r, ci_r, self.mode)
         wt = self.plan.weights
         fold = torch.empty(bn.num_features, dtype=torch.float32, device=self.device) if bn is not None else None
+        pc = PackedConv(wbuf, scale, shift, kh, kw, cout, cin, co_r, ci_r, self.mode, fold)
         bias = (lambda: conv.bias) if (bn is None and conv.bias is not None) else None
         wt.add_epilogue(scale, shift, co_r, bn=bn, bias=bias, fold_scale=fold)
         wt.add_pack(lambda: conv.weight, wbuf, cout, cin, row_scale=fold,
                     scale_period=bn.num_features if bn is not None else 1, weight_fn=weight_fn,
                     watch=list(extra_sources))
         return pc
+
+    def packed_transposed(self, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d] = None, *, ci_off: int = 0,
+                          cin_slice: Optional[int] = None, weight_fn=None, fold: Optional[torch.Tensor] = None,
+                          fold_period: int = 1, extra_sources: Sequence[torch.Tensor] = ()):
+        """TRANSPOSED packing [planes, taps, cin_slice_pad, cout_pad] of (a slice of) `conv`'s filter, optionally scaled
+        per output channel by an eval BatchNorm (`bn`: its own fold, or `fold`: one computed elsewhere in the plan).
+        Returns (packed, shift) - shift is the fp32 [cout_pad] BatchNorm shift (zeros without `bn`)."""
+        w0 = conv.weight if weight_fn is None else weight_fn(conv.weight.detach())
+        co_r, ci_t, kh, kw = w0.shape
+        ci_r = (ci_t - ci_off) if cin_slice is None else cin_slice
+        rows, cols = round_up(ci_r, 16), round_up(co_r, 64)
+        planes = 2 if self.mode == ops.UP_SPLIT else 1
+        dt = torch.float16 if self.mode == ops.UP_FP16 else torch.bfloat16
+        wbuf = torch.empty((planes, kh * kw, rows, cols), dtype=dt, device=self.device)
+        scale = torch.empty(cols, dtype=torch.float32, device=self.device)
+        shift = torch.empty(cols, dtype=torch.float32, device=self.device)
+        wt = self.plan.weights
+        period = fold_period
+        if bn is not None:
+            fold = torch.empty(bn.num_features, dtype=torch.float32, device=self.device)
+            period = bn.num_features
+        wt.add_epilogue(scale, shift, co_r, bn=bn, fold_scale=fold if bn is not None else None)
+        wt.add_pack(lambda: conv.weight, wbuf, rows, cols, transpose=True, ci_off=ci_off, cin_slice=ci_r, row_scale=fold,
+                    scale_period=period, weight_fn=weight_fn, watch=list(extra_sources))
+        return wbuf, shift
 
     def conv(self, x, pc: PackedConv, y, name: str = "conv", side: bool = False, **kw) -> None:
         self.add(lambda: ops.conv2d(x, pc, y, **kw), name, side=side)

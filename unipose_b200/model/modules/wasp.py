@@ -86,7 +86,57 @@ class wasp(PlanModule):
         parts = [w1m[:, i * 256:(i + 1) * 256] @ w22 for i in range(4)] + [w1m[:, 1024:]]
         return torch.cat(parts, dim=1)[:, :, None, None].contiguous()
 
+    # ---- the whole block as one persistent kernel (fp16 / bf16 inference) ------------------------------------
+    def _chain_desc(self, b, x):
+        import ctypes
+        import os
+        from ... import _lib
+        if os.environ.get("UNIPOSE_B200_WASP_CHAIN", "1") == "0" or b.mode == ops.UP_SPLIT:
+            return None
+        d = _lib.UpWaspChainDesc()
+        d.n, d.h, d.w, d.cin = x.n, x.h, x.w, x.c
+        for i, a in enumerate((self.aspp2, self.aspp3, self.aspp4)):
+            d.dil[i] = a.atrous_conv.dilation[0]
+        d.dtype = b.mode
+        d.conv1_cin = 1280
+        if _lib.load().up_wasp_chain_supported(ctypes.byref(d)) != 0:
+            return None          # e.g. odd batch, tiny maps: the layer-wise plan below handles every shape
+        return d
+
+    def _emit_chain(self, b, x, d):
+        """aspp1..4, the folded conv1 and the pooling branch as ONE launch of up_wasp_chain_fwd (csrc/wasp_chain.cu)."""
+        import ctypes
+        from ... import _lib
+        n, h, w = x.n, x.h, x.w
+        S = b.act(4 * n, h, w, 256)          # x1..x4: halo sources of the cascade
+        out = b.act(n, h, w, 256)
+        pcs = [b.packed_conv(a.atrous_conv, a.bn) for a in (self.aspp1, self.aspp2, self.aspp3, self.aspp4)]
+        pc1 = b.packed_conv(self.conv1, self.bn1, weight_fn=self._folded_conv1_weight, extra_sources=[self.conv2.weight])
+        gap_bn = self.global_avg_pool[2] if self._gap_has_bn else None
+        gap_t, shift_gap = b.packed_transposed(self.global_avg_pool[1], gap_bn)
+        pool_t, _ = b.packed_transposed(self.conv1, None, ci_off=1024, cin_slice=256, weight_fn=self._folded_conv1_weight,
+                                        fold=pc1.fold, fold_period=256, extra_sources=[self.conv2.weight])
+        ws_bytes = int(_lib.load().up_wasp_chain_workspace_bytes(ctypes.byref(d)))
+        ws = b.tensor((ws_bytes,), dtype=torch.uint8, zero=True)      # counters start at zero; the kernel re-arms them
+        wts = _lib.UpWaspChainWeights()
+        for i, pc in enumerate(pcs):
+            wts.aspp[i] = pc.w.data_ptr()
+            wts.shift[i] = pc.shift.data_ptr()
+        wts.conv1, wts.shift1 = pc1.w.data_ptr(), pc1.shift.data_ptr()
+        wts.gap_t, wts.shift_gap = gap_t.data_ptr(), shift_gap.data_ptr()
+        wts.conv1_pool_t = pool_t.data_ptr()
+        keep = (pcs, pc1, gap_t, shift_gap, pool_t, ws)
+
+        def launch(keep=keep):
+            _lib.call("up_wasp_chain_fwd", ctypes.byref(d), ctypes.byref(wts), x.ptr(), S.ptr(), out.ptr(), ops._ptr(ws),
+                      ws_bytes, ops._stream())
+        b.add(launch, "wasp.chain")
+        return out
+
     def _emit(self, b, x):
+        d = self._chain_desc(b, x) if isinstance(x, ops.Act) else None
+        if d is not None:
+            return self._emit_chain(b, x, d)
         n, h, w = x.n, x.h, x.w
         S = b.act(5 * n, h, w, 256)      # the four cascade outputs + the broadcast pooling branch, stacked along n
         branch = [View(S, n_off=i * n, n=n) for i in range(5)]

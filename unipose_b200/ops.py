@@ -120,6 +120,7 @@ class PackedConv:
     cout_real: int
     cin_real: int
     mode: int
+    fold: Optional[torch.Tensor] = None    # eval BatchNorm scale folded into the filter rows (fp32 [bn.num_features])
 
     @property
     def plane_stride(self) -> int:
