@@ -305,10 +305,8 @@ def train_record(args, dev, rank, world):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.train_steps
-    stats = ts.comm_stats() if hasattr(ts, "comm_stats") else {}
-    vals = torch.tensor([ms, stats.get("allreduce_ms", 0.0), stats.get("exposed_ms", 0.0)], dtype=torch.float64, device=dev)
+    stats = ts.comm_stats()
     if world > 1:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         chk = ts.flat_p.double().sum().reshape(1)
         lo, hi = chk.clone(), chk.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
@@ -316,13 +314,33 @@ def train_record(args, dev, rank, world):
         same = bool(float(hi - lo) == 0.0)
     else:
         same = True
-    ms, ar_ms, exposed = float(vals[0]), float(vals[1]), float(vals[2])
+    # what the collective costs: (a) all buckets back to back on an otherwise idle GPU, (b) the same steps with the
+    # all-reduce switched off (ranks diverge from here on: measured last) -> exposed = full - compute_only
+    ar_alone = ts.time_allreduce_alone()
+    ts.comm_enabled = False
+    for _ in range(2):
+        ts.step(x, t)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    for _ in range(args.train_steps):
+        ts.step(x, t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_nocomm = e0.elapsed_time(e1) / args.train_steps
+    vals = torch.tensor([ms, ar_alone, ms_nocomm], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms, ar_alone, ms_nocomm = float(vals[0]), float(vals[1]), float(vals[2])
+    exposed = max(0.0, ms - ms_nocomm)
     rec = {"workload": "MPII %dx%d training step, batch %d per GPU, bf16 compute / fp32 master (BASELINE.json configs[2])" % (S, S, B),
            "ms_per_step": ms, "frames_s": B * world / (ms * 1e-3), "n_gpus": world, "steps": args.train_steps,
            "loss": float(loss), "params_identical_across_ranks": same,
            "allreduce": {"bytes": int(ts.flat_g.numel() * 4), "buckets": stats.get("buckets"),
-                         "ms_sum_of_buckets": ar_ms, "exposed_ms": exposed,
-                         "hidden_frac": (None if not ar_ms else max(0.0, 1.0 - exposed / ar_ms))},
+                         "bucket_mb": stats.get("bucket_mb"), "ms_alone": ar_alone,
+                         "ms_per_step_without_allreduce": ms_nocomm, "exposed_ms": exposed,
+                         "hidden_frac": (None if world == 1 or ar_alone <= 0 else max(0.0, min(1.0, 1.0 - exposed / ar_alone)))},
            "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
     del ts, m
     torch.cuda.empty_cache()

@@ -37,6 +37,11 @@ def _worker(rank, world, port, out):
         w2 = w.detach().clone().requires_grad_(True)
         ((x @ w2 - y) ** 2).mean().backward()
         ok_grad = torch.allclose(flat, w2.grad.reshape(-1), atol=1e-6)
+        # the bucketed form (what TrainStep overlaps with the backward) gives the same sum
+        buckets = parallel.make_buckets([(0, 5, 3), (5, 7, 9), (12, 6, 4)], bucket_bytes=40, n_ops=11)
+        flat_b = w.grad.detach().reshape(-1).clone()
+        parallel.allreduce_buckets_(flat_b, buckets)
+        ok_grad = ok_grad and torch.equal(flat_b, flat) and buckets[-1][1] == 18
         tmax = parallel.max_over_ranks([1.0 + rank, 5.0 - rank], "cpu")
         out.put((rank, ok_grad, tmax, (start, count)))
     finally:
@@ -68,3 +73,15 @@ def test_two_rank_gradient_allreduce_and_timing():
         assert ok_grad, rank
         assert tmax == [2.0, 5.0]
     assert sorted(r[3] for r in res) == [(0, 5), (5, 5)]
+
+
+def test_make_buckets_covers_buffer_in_backward_order():
+    items = [(0, 1000, 5), (1000, 3000, 9), (4000, 10, 7), (4010, 5000, 20), (9010, 20, 18)]
+    b = parallel.make_buckets(items, bucket_bytes=12000, n_ops=25)
+    assert b[0][0] == 0 and b[-1][1] == 9030
+    assert all(x[1] == y[0] for x, y in zip(b, b[1:]))                # contiguous, no gaps
+    assert all(x[2] <= y[2] for x, y in zip(b, b[1:])) and b[-1][2] == 25
+    # a bucket is never released before the last gradient inside it is final
+    for lo, hi, ready in b[:-1]:
+        assert ready >= max(r for off, n, r in items if lo <= off < hi)
+    assert parallel.make_buckets([(0, 10, 1)], bucket_bytes=1 << 30, n_ops=4) == [(0, 10, 4)]

@@ -32,6 +32,38 @@ def allreduce_sum_(flat: torch.Tensor) -> torch.Tensor:
     return flat
 
 
+def make_buckets(items: Sequence[Tuple[int, int, int]], bucket_bytes: int, n_ops: int, elem_bytes: int = 4):
+    """Cut a flat gradient buffer into contiguous all-reduce buckets.
+
+    `items`: (offset, numel, ready) per parameter in LAYOUT order - `ready` = index into the backward op list after
+    which that gradient is final.  Returns [(lo, hi, ready)]: elements [lo, hi) may be reduced once `ready` backward
+    ops have run; `ready` is non-decreasing over the buckets and the last one equals n_ops (whole backward done)."""
+    buckets, cur_start, cur_ready, cur_bytes, end = [], 0, 0, 0, 0
+    for off, numel, ready in items:
+        cur_ready = max(cur_ready, ready)
+        cur_bytes += numel * elem_bytes
+        end = off + numel
+        if cur_bytes >= bucket_bytes:
+            buckets.append([cur_start, end, cur_ready])
+            cur_start, cur_bytes = end, 0
+    if cur_bytes > 0 or not buckets:
+        buckets.append([cur_start, end, cur_ready])
+    run = 0
+    for b in buckets:       # the layout only approximates the completion order: make the segment ends monotonic
+        run = max(run, b[2])
+        b[2] = run
+    buckets[-1][2] = n_ops
+    return [tuple(b) for b in buckets]
+
+
+def allreduce_buckets_(flat: torch.Tensor, buckets) -> torch.Tensor:
+    """Bucket-by-bucket in-place sum (what TrainStep overlaps with the backward); == allreduce_sum_(flat)."""
+    if world()[1] > 1:
+        for lo, hi, _ready in buckets:
+            dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM)
+    return flat
+
+
 def max_over_ranks(values: Sequence[float], device) -> Sequence[float]:
     t = torch.tensor(list(values), dtype=torch.float64, device=device)
     if world()[1] > 1:

@@ -45,6 +45,7 @@ class TrainPlan:
         self.buffers: List = []
         self.weights = engine.WeightTable(self.device, self.mode, always=True)   # refilled every step
         self.fwd_counter = 0
+        self.grad_ready: Dict[int, int] = {}   # id(param) -> index into self.bwd after which its gradient is final
         self.grads: Dict[int, Act] = {}    # id(forward Act) -> gradient Act
         self.written: List[Tuple] = []     # gradient regions that already hold a value
         self.pgrad: Dict[int, torch.Tensor] = {}
@@ -99,6 +100,10 @@ class TrainPlan:
         if g is None:
             return False
         return self.is_written(View(g, coff=v.coff, c=v.c, n_off=v.n_off, n=v.n))
+
+    def _grad_final(self, p: nn.Parameter) -> None:
+        """The op just appended to self.bwd is (so far) the last writer of p's gradient."""
+        self.grad_ready[id(p)] = len(self.bwd)
 
     def param_grad(self, p: nn.Parameter) -> torch.Tensor:
         g = self.pgrad.get(id(p))
@@ -210,6 +215,7 @@ class TrainPlan:
                 gb = self.param_grad(conv.bias)
                 self.bwd.append(lambda: ops.bn_stats(dz, cout, bsums))
                 self.bwd.append(lambda: gb.copy_(bsums[:r["co_r"]]))
+                self._grad_final(conv.bias)
         else:
             y = r["y"]
             if not self.has_grad(y):
@@ -238,6 +244,8 @@ class TrainPlan:
                 frozen = r["frozen"]
                 self.bwd.append(lambda: ops.bn_bwd(dy, y, z, dz, dres, mean, invstd, bn.weight.detach(), sums, co_r,
                                                    relu, dgamma, dbeta, frozen=frozen))
+                self._grad_final(bn.weight)
+                self._grad_final(bn.bias)
                 if dres_tmp is not None:
                     self.bwd.append(lambda: ops.ew(dres_tmp, rv, accumulate=True))
         dzv = as_view(dz)
@@ -258,6 +266,7 @@ class TrainPlan:
                 self.bwd.append(lambda: gw.add_(inv(gtmp)))
             else:
                 self.bwd.append(lambda: gw.copy_(inv(gtmp)))
+        self._grad_final(conv.weight)
         # ---- input gradient: the forward kernel on the flipped / transposed filter ----
         if not r["x_needs_grad"]:
             return
@@ -339,11 +348,15 @@ class TrainPlan:
         """Emit the backward ops (reverse tape).  flat=True: every live parameter's gradient is a view of ONE flat
         fp32 buffer (self.flat_g) - what the all-reduce and the fused Adam step operate on."""
         if flat:
+            # laid out in REVERSE registration order = the order in which the backward pass finishes the gradients, so
+            # that contiguous buckets of the buffer become final one after the other (bucketed all-reduce, TrainStep)
             total = sum(q.numel() for q in self.live_params)
             self.flat_g = torch.zeros(total, dtype=torch.float32, device=self.device)
             off = 0
-            for q in self.live_params:
+            self.flat_offsets: Dict[int, Tuple[int, int]] = {}
+            for q in reversed(self.live_params):
                 self.pgrad[id(q)] = self.flat_g[off:off + q.numel()].view(q.shape)
+                self.flat_offsets[id(q)] = (off, q.numel())
                 self.params.append(q)
                 off += q.numel()
         for t in reversed(self.tape):
@@ -381,10 +394,11 @@ class TrainPlan:
             keep = (torch.rand((act.n, act.h, act.w, act.c), device=self.device) >= p)
             s = 1.0 / (1.0 - p)
             if self.mode == ops.UP_SPLIT:
-                hi = torch.tensor(s, dtype=torch.bfloat16)
-                lo = torch.tensor(s - float(hi), dtype=torch.bfloat16)
-                act.t[0] = keep.to(act.t.dtype) * hi.to(self.device)
-                act.t[1] = keep.to(act.t.dtype) * lo.to(self.device)
+                # hi / lo planes of the scale as host scalars (no host->device copy: the step is graph-captured)
+                hi = float(torch.tensor(s, dtype=torch.bfloat16))
+                lo = float(torch.tensor(s - hi, dtype=torch.bfloat16))
+                act.t[0] = keep.to(act.t.dtype) * hi
+                act.t[1] = keep.to(act.t.dtype) * lo
             else:
                 act.t[0] = keep.to(act.t.dtype) * s
 
@@ -525,19 +539,30 @@ def forward_train(model, input: torch.Tensor, dropout_masks=None) -> torch.Tenso
 # fused training step: forward, MSE, backward, (all-reduce), Adam  -  unipose.py:107-124
 # ----------------------------------------------------------------------------------------------------
 class TrainStep:
-    """One optimisation step of the reference's training loop on flat fp32 buffers.
+    """One optimisation step of the reference's training loop (unipose.py:107-124) on flat fp32 buffers.
 
-    `step(input, target)` = forward (train-mode BN, dropout) -> nn.MSELoss (up_mse_fwd_bwd) -> backward ->
-    ONE NCCL all-reduce of the flat gradient buffer when torch.distributed is initialised (data parallel over the
-    batch, BatchNorm stays per-GPU as in the reference) -> Adam (up_adam_step) on the flat parameter buffer.
-    Parameters that the reference leaves without gradient (decoder.conv2 / bn2) are never touched."""
+    `step(input, target)` = forward (train-mode BN, dropout) -> nn.MSELoss (up_mse_fwd_bwd) -> backward -> NCCL
+    all-reduce of the gradient (data parallel over the batch; BatchNorm stays per-GPU as in the reference, which has
+    no SyncBN) -> Adam (up_adam_step) on the flat parameter buffer.  Parameters the reference leaves without gradient
+    (decoder.conv2 / bn2) are never touched.
 
-    def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8):
+    The flat gradient buffer is laid out in the order the backward pass completes the gradients and cut into
+    ~25 MB buckets; the backward op list is split where a bucket becomes final, each segment replays
+    as its own CUDA graph, and the bucket's all-reduce is enqueued on a side stream right behind it - the collective
+    of bucket k overlaps the backward of buckets k+1.. (torch.distributed / NCCL over NVLink)."""
+
+    BUCKET_BYTES = 25 << 20
+
+    def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, bucket_bytes: Optional[int] = None):
         self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
         self.plan: Optional[TrainPlan] = None
         self.t = 0
+        self.bucket_bytes = int(bucket_bytes or os.environ.get("UNIPOSE_B200_BUCKET_BYTES", self.BUCKET_BYTES))
+        self.comm_enabled = True          # bench: switch the collective off to measure what it costs
 
+    # ---- setup ------------------------------------------------------------------------------------------------
     def _setup(self, x: torch.Tensor) -> None:
+        from . import parallel
         m = self.model
         self.plan = build_image_train_plan(m, tuple(x.shape), x.device, m._precision(), flat=True)
         p = self.plan
@@ -552,47 +577,123 @@ class TrainStep:
                 self.flat_p[off:off + nq].copy_(q.detach().reshape(-1))
                 q.data = self.flat_p[off:off + nq].view(q.shape)
                 off += nq
+        world = parallel.world()[1]
+        if world > 1:
+            # what DistributedDataParallel does at construction: every rank starts from rank 0's parameters / buffers
+            import torch.distributed as dist
+            dist.broadcast(self.flat_p, 0)
+            for b in m.buffers():
+                if b.is_floating_point() or b.dtype == torch.long:
+                    dist.broadcast(b, 0)
         self.loss = torch.zeros(1, dtype=torch.float32, device=x.device)
         self.loss_scratch = torch.zeros(1, dtype=torch.float64, device=x.device)
+        self._make_buckets()
+        self.comm_stream = torch.cuda.Stream(device=x.device) if world > 1 else None
 
-    def _fwd_loss_bwd(self, target: torch.Tensor, world: int) -> None:
+    def _make_buckets(self) -> None:
+        """Buckets = contiguous ranges of the flat gradient; a bucket is final once backward op `ready` has run."""
+        p = self.plan
+        items = []      # (offset, numel, ready index) in layout order
+        for q in p.params:
+            off, nq = p.flat_offsets[id(q)]
+            items.append((off, nq, p.grad_ready.get(id(q), len(p.bwd))))
+        from . import parallel
+        self.buckets = parallel.make_buckets(items, self.bucket_bytes, len(p.bwd))
+
+    # ---- one step ---------------------------------------------------------------------------------------------
+    def _fwd_loss(self, world: int) -> None:
         p = self.plan
         heat = p.run_forward(p.input)
-        ops._lib.call("up_mse_fwd_bwd", ops._ptr(heat), ops._ptr(target), ops._ptr(self.loss), ops._ptr(p.dheat),
+        ops._lib.call("up_mse_fwd_bwd", ops._ptr(heat), ops._ptr(self.target_buf), ops._ptr(self.loss), ops._ptr(p.dheat),
                       ops._ptr(self.loss_scratch), heat.numel(), 1.0 / world, ops._stream())
-        for op in p.bwd:
+
+    def _bwd_segment(self, k: int) -> None:
+        lo = self.buckets[k - 1][2] if k > 0 else 0
+        for op in self.plan.bwd[lo:self.buckets[k][2]]:
             op()
+
+    def _run_piece(self, k: int, world: int) -> None:
+        """piece 0 = forward + loss + backward segment 0; piece k = backward segment k."""
+        if k == 0:
+            self._fwd_loss(world)
+        self._bwd_segment(k)
 
     def step(self, x: torch.Tensor, target: torch.Tensor, lr: Optional[float] = None) -> torch.Tensor:
         from . import parallel
         if self.plan is None:
             self._setup(x)
             self.target_buf = torch.empty_like(target, dtype=torch.float32)
-            self.graph = None
+            self.graphs: Optional[List[torch.cuda.CUDAGraph]] = None
             self.steps_done = 0
-            # forward + loss + backward (~2000 launches) replay as ONE CUDA graph from the third step on; the
-            # all-reduce and Adam (step-dependent bias correction) stay eager.  UNIPOSE_B200_TRAIN_GRAPH=0 disables.
-            self.use_graph = (os.environ.get("UNIPOSE_B200_TRAIN_GRAPH", "1") != "0" and
-                              self.plan.mode != ops.UP_SPLIT)
+            # the pieces replay as CUDA graphs from the third step on; the all-reduces and Adam (step-dependent bias
+            # correction) stay eager.  UNIPOSE_B200_TRAIN_GRAPH=0 disables.
+            self.use_graph = os.environ.get("UNIPOSE_B200_TRAIN_GRAPH", "1") != "0"
         p = self.plan
         world = parallel.world()[1]
-        p.input.copy_(x)
-        self.target_buf.copy_(target)
-        if self.use_graph and self.graph is None and self.steps_done >= 2:
-            torch.cuda.synchronize(p.device)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._fwd_loss_bwd(self.target_buf, world)
-            self.graph = g          # capturing does not execute: fall through to the replay below
-        if self.graph is not None:
-            self.graph.replay()
-        else:
-            self._fwd_loss_bwd(self.target_buf, world)
-        self.steps_done += 1
-        engine.note_raw_parameter_update()     # Adam / BatchNorm statistics move behind torch's version counters
-        parallel.allreduce_sum_(self.flat_g)   # gradients were pre-scaled by 1/world in the MSE kernel
-        self.t += 1
-        ops._lib.call("up_adam_step", ops._ptr(self.flat_p), ops._ptr(self.flat_g), ops._ptr(self.exp_avg),
-                      ops._ptr(self.exp_avg_sq), self.flat_p.numel(), float(self.lr if lr is None else lr),
-                      float(self.betas[0]), float(self.betas[1]), float(self.eps), self.t, ops._stream())
+        with torch.cuda.device(p.device):
+            p.input.copy_(x)
+            self.target_buf.copy_(target)
+            if self.use_graph and self.graphs is None and self.steps_done >= 2:
+                torch.cuda.synchronize(p.device)
+                graphs, pool = [], None
+                for k in range(len(self.buckets)):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool):
+                        self._run_piece(k, world)
+                    pool = g.pool()
+                    graphs.append(g)
+                self.graphs = graphs          # capturing does not execute: fall through to the replays below
+            main = torch.cuda.current_stream(p.device)
+            works = []
+            for k, (lo, hi, _ready) in enumerate(self.buckets):
+                if self.graphs is not None:
+                    self.graphs[k].replay()
+                else:
+                    self._run_piece(k, world)
+                if world > 1 and self.comm_enabled:
+                    # bucket k is final: its all-reduce runs on the side stream while the next segments compute
+                    import torch.distributed as dist
+                    self.comm_stream.wait_stream(main)
+                    with torch.cuda.stream(self.comm_stream):
+                        works.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+            for w in works:
+                w.wait()                      # the side stream waits for NCCL ...
+            if works:
+                main.wait_stream(self.comm_stream)   # ... and Adam for the side stream
+            self.steps_done += 1
+            engine.note_raw_parameter_update()     # Adam / BatchNorm statistics move behind torch's version counters
+            self.t += 1
+            # gradients were pre-scaled by 1/world in the MSE kernel: the sum is the global-batch mean gradient
+            ops._lib.call("up_adam_step", ops._ptr(self.flat_p), ops._ptr(self.flat_g), ops._ptr(self.exp_avg),
+                          ops._ptr(self.exp_avg_sq), self.flat_p.numel(), float(self.lr if lr is None else lr),
+                          float(self.betas[0]), float(self.betas[1]), float(self.eps), self.t, ops._stream())
         return self.loss
+
+    @property
+    def graph(self):
+        """Truthy once the step replays CUDA graphs (kept for callers of the one-graph version)."""
+        return self.graphs
+
+    def comm_stats(self) -> dict:
+        return {"buckets": len(self.buckets) if self.plan is not None else None,
+                "bucket_mb": [round((hi - lo) * 4 / 2 ** 20, 1) for lo, hi, _ in self.buckets] if self.plan else None}
+
+    def time_allreduce_alone(self, reps: int = 5) -> float:
+        """ms of all bucket all-reduces back to back with nothing else on the GPU (max over ranks is the caller's job)."""
+        from . import parallel
+        if parallel.world()[1] <= 1 or self.plan is None:
+            return 0.0
+        import torch.distributed as dist
+        scratch = torch.zeros_like(self.flat_g)
+        for _ in range(2):
+            for lo, hi, _r in self.buckets:
+                dist.all_reduce(scratch[lo:hi])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            for lo, hi, _r in self.buckets:
+                dist.all_reduce(scratch[lo:hi])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
