@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--no-train", action="store_true", help="skip the training-step sub-record")
     ap.add_argument("--no-parity-mode", action="store_true", help="skip the fp32-grade mode timing")
     ap.add_argument("--train-steps", type=int, default=6)
+    ap.add_argument("--train-only", action="store_true", help="print only the training sub-record (tuning runs)")
     return ap.parse_args()
 
 
@@ -368,6 +369,15 @@ def run_b200(args) -> int:
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.train_only:
+        rec = train_record(args, dev, rank, world)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        if rank == 0:
+            print(json.dumps({"train": rec}))
+        return 0
 
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")

@@ -221,6 +221,18 @@ int up_epilogue_consts(const UpEpilogueJob* d_jobs, int njobs, int max_channels,
  * padding pixels are left untouched (the caller zero-fills them once). */
 int up_pack_input_s2d(const float* x_nchw, void* y, int n, int h, int w, int dtype, int64_t y_plane_stride,
                       int y_wpitch, int y_wpad_left, void* stream);
+/* uint8 HWC images [n,h,w,3] (what cv2.imread / a video decoder delivers) -> (x - mean) / std -> the same space-to-depth
+ * tensor as up_pack_input_s2d: utils/mpii_data.py:184-185 (Mytransforms.to_tensor + normalize with mean 128, std 256)
+ * fused with the stem's input packing; a quarter of the host->device bytes of the fp32 NCHW path, identical bits. */
+int up_pack_input_u8_s2d(const uint8_t* x_nhwc, void* y, int n, int h, int w, int dtype, int64_t y_plane_stride,
+                         int y_wpitch, int y_wpad_left, float mean, float std_, void* stream);
+/* Ground-truth heat-maps on the device (utils/mpii_data.py:62-65,165-181; same code in lsp_lspet_data / bbc_data):
+ * kpts fp32 [n,k,2] (x, y in input-image pixels) -> heat fp32 NCHW [n, k + background, h, w]: channel j+background
+ * = exp(-((x - cx)^2 + (y - cy)^2) / 2 / sigma / sigma) in float64 with cx = int(kx) / stride (truncate_mode 1) or
+ * cx = int(kx / stride) (truncate_mode 2: the centre map, mpii_data.py:178), clipped (> 1 -> 1, < 0.0099 -> 0), stored
+ * as fp32; background != 0 adds channel 0 = 1 - max over the joints. */
+int up_gaussian_labels(const float* kpts, float* heat, int n, int k, int h, int w, float stride, float sigma,
+                       int background, int truncate_mode, void* stream);
 /* Generic fp32 NCHW [n,c_real,h,w] -> NHWC 16-bit view (channels >= c_real zero-filled up to c). */
 int up_nchw_f32_to_nhwc(const float* x, void* y, int n, int c_real, int h, int w, int c, int y_cstride,
                         int y_coff, int dtype, int64_t y_plane_stride, void* stream);

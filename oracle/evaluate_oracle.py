@@ -150,3 +150,45 @@ def synth_eval_inputs(n, k, hw, seed=11, noise=0.25):
     pred[1, 5, 7, 9] = pred[1, 5].max() + 1.0
     pred[1, 5, 20, 2] = pred[1, 5, 7, 9]    # tie: the first occurrence (row-major) must win
     return gt, pred
+
+
+# --------------------------------------------------------------------------------------------
+# ground-truth label synthesis of the datasets (utils/mpii_data.py:62-65,165-181; identical code in
+# lsp_lspet_data.py:65-68, bbc_data.py:17-20)
+# --------------------------------------------------------------------------------------------
+def guassian_kernel(size_w, size_h, center_x, center_y, sigma):
+    """mpii_data.py:62-65 (the reference's spelling)."""
+    gridy, gridx = np.mgrid[0:size_h, 0:size_w]
+    D2 = (gridx - center_x) ** 2 + (gridy - center_y) ** 2
+    return np.exp(-D2 / 2.0 / sigma / sigma)
+
+
+def reference_labels(kpt, center, height, width, stride, sigma):
+    """mpii_data.py:165-181 for ONE sample: kpt [K, 2+] float32 (x, y in input pixels), center [2] float32 ->
+    (heatmap [K+1, h, w] fp32 with the background channel first, centermap [1, h, w] fp32)."""
+    h, w = int(height / stride), int(width / stride)
+    heatmap = np.zeros((h, w, len(kpt) + 1), dtype=np.float32)
+    for i in range(len(kpt)):
+        x = int(kpt[i][0]) * 1.0 / stride
+        y = int(kpt[i][1]) * 1.0 / stride
+        heat_map = guassian_kernel(size_h=h, size_w=w, center_x=x, center_y=y, sigma=sigma)
+        heat_map[heat_map > 1] = 1
+        heat_map[heat_map < 0.0099] = 0
+        heatmap[:, :, i + 1] = heat_map
+    heatmap[:, :, 0] = 1.0 - np.max(heatmap[:, :, 1:], axis=2)
+    cm = guassian_kernel(size_h=h, size_w=w, center_x=int(np.float32(center[0]) / np.float32(stride)),
+                         center_y=int(np.float32(center[1]) / np.float32(stride)), sigma=3)
+    cm[cm > 1] = 1
+    cm[cm < 0.0099] = 0
+    return heatmap.transpose(2, 0, 1).copy(), cm.astype(np.float32)[None]
+
+
+def synth_keypoints(n, k, height, width, seed):
+    """Seeded key-points / centres in input pixels, with a few on the border and fractional coordinates."""
+    rng = np.random.RandomState(seed)
+    kpts = (rng.rand(n, k, 2) * [width - 1, height - 1]).astype(np.float32)
+    kpts[0, 0] = [0.0, 0.0]
+    kpts[0, 1] = [width - 1, height - 1]
+    kpts[1 % n, 2] = [7.99, 8.01]
+    center = (rng.rand(n, 2) * [width - 1, height - 1]).astype(np.float32)
+    return kpts, center

@@ -68,7 +68,38 @@ def round2_fixtures():
     x8 = O.synth_input(2, 128, 128, seed=8)
     f8, l8 = m8.backbone(x8)
     np.savez_compressed(os.path.join(OUT, "image_os8_128.npz"), heat=m8(x8).numpy(), feat_s=f8[:, ::16].numpy())
-    for fn in ("image_c5_512.npz", "image_os8_128.npz"):
+    # ---- label synthesis: the reference's own guassian_kernel (utils/mpii_data.py:62-65) driven through the loop of
+    # mpii.__getitem__ (:165-181).  The module imports utils.Mytransforms (whose package pulls matplotlib): stubbed.
+    import types
+    pkg = types.ModuleType("utils")
+    pkg.__path__ = []
+    sys.modules.setdefault("utils", pkg)
+    sys.modules.setdefault("utils.Mytransforms", types.ModuleType("utils.Mytransforms"))
+    spec = importlib.util.spec_from_file_location("ref_mpii_data", os.path.join(REF, "utils", "mpii_data.py"))
+    ref_data = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_data)
+    kpts, center = E.synth_keypoints(4, 16, 368, 368, seed=40)
+    heat = np.zeros((4, 17, 46, 46), np.float32)
+    cmap = np.zeros((4, 1, 46, 46), np.float32)
+    for b in range(4):
+        hm = np.zeros((46, 46, 17), dtype=np.float32)
+        kp = torch.Tensor(kpts[b])
+        ce = torch.Tensor(center[b])
+        for i in range(len(kp)):                                     # mpii_data.py:166-173
+            x = int(kp[i][0]) * 1.0 / 8
+            y = int(kp[i][1]) * 1.0 / 8
+            g = ref_data.guassian_kernel(size_h=46, size_w=46, center_x=x, center_y=y, sigma=3)
+            g[g > 1] = 1
+            g[g < 0.0099] = 0
+            hm[:, :, i + 1] = g
+        hm[:, :, 0] = 1.0 - np.max(hm[:, :, 1:], axis=2)             # :175
+        c = ref_data.guassian_kernel(size_h=46, size_w=46, center_x=int(ce[0] / 8), center_y=int(ce[1] / 8), sigma=3)
+        c[c > 1] = 1
+        c[c < 0.0099] = 0
+        heat[b] = hm.transpose(2, 0, 1)
+        cmap[b, 0] = c
+    np.savez_compressed(os.path.join(OUT, "labels_mpii.npz"), heat=heat, centermap=cmap)
+    for fn in ("image_c5_512.npz", "image_os8_128.npz", "labels_mpii.npz"):
         print("%-32s %8.1f KB" % (fn, os.path.getsize(os.path.join(OUT, fn)) / 1024))
 
 

@@ -227,6 +227,34 @@ def test_config4_video_batch8_5frames_vs_oracle():
     print("config 4 (B=8 x 5 frames): worst heat-map max-rel over the window %.3g" % worst)
 
 
+def test_video_temporal_batching_matches_per_frame_path(monkeypatch):
+    """the trunk of all T frames as one batch of B*T images + per-frame ConvLSTM / middle-CNN steps
+    must reproduce the per-frame plans (same kernels, other batch size: equal to rounding)."""
+    import warnings
+    from unipose_b200.model import uniposeLSTM
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = uniposeLSTM.unipose(num_classes=13, precision="fp32")
+    m.load_state_dict(O.synth_state_dict(13, video=True, seed=2), strict=True)
+    m = m.cuda().eval()
+    B, T = 2, 3
+    inp = O.synth_input(B * T, 368, 368, seed=31).view(B, T, 3, 368, 368).cuda()
+    cm = torch.from_numpy(E.gaussian_heatmaps(B, T, 368, 368, seed=7, sigma=21.0)[:, 1:T + 1]).reshape(B, T, 1, 368, 368).cuda()
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("UNIPOSE_B200_TEMPORAL_BATCH", flag)
+        heat = hide = cell = None
+        outs = []
+        for it in range(T):
+            heat, cell, hide = m(inp, cm, it, heat, hide, cell)
+            outs.append((heat.cpu().numpy(), cell.cpu().numpy(), hide.cpu().numpy()))
+        res[flag] = outs
+        names = {k[0] for k in m._plans if isinstance(k[0], str)}
+        assert ("trunk" in names) == (flag == "1")
+    for a, b in zip(res["1"], res["0"]):
+        assert _rel(a[0], b[0]) < 1e-4 and np.abs(a[1] - b[1]).max() < 1e-4 and np.abs(a[2] - b[2]).max() < 1e-4
+
+
 def test_video_model_vs_golden_and_batch():
     import warnings
     from unipose_b200.model import uniposeLSTM

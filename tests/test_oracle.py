@@ -128,6 +128,17 @@ def test_evaluate_oracle_vs_golden(name, dataset, k, hw, n):
     assert preds[1, 5].tolist() == [9.0, 7.0]
 
 
+def test_label_oracle_vs_reference_golden():
+    """reference_labels restates utils/mpii_data.py:165-181; the fixture was produced with the reference's own
+    guassian_kernel (oracle/make_golden.py --round2)."""
+    g = _load("labels_mpii.npz")
+    kpts, center = E.synth_keypoints(4, 16, 368, 368, seed=40)
+    for b in range(4):
+        heat, cm = E.reference_labels(kpts[b], center[b], 368, 368, 8, 3)
+        assert np.array_equal(heat, g["heat"][b]) and np.array_equal(cm, g["centermap"][b])
+    assert g["heat"].shape == (4, 17, 46, 46) and float(g["heat"][:, 1:].max()) == 1.0
+
+
 def test_get_kpts_oracle():
     m = np.zeros((1, 3, 46, 46), np.float32)
     m[0, 1, 10, 20] = 1

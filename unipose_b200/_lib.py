@@ -73,6 +73,8 @@ _SIGNATURES = {
     "up_pack_conv_weight": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _L, _P],
     "up_bn_fold": [_P, _P, _P, _P, _F, _P, _P, _I, _I, _P],
     "up_pack_input_s2d": [_P, _P, _I, _I, _I, _I, _L, _I, _I, _P],
+    "up_pack_input_u8_s2d": [_P, _P, _I, _I, _I, _I, _L, _I, _I, _F, _F, _P],
+    "up_gaussian_labels": [_P, _P, _I, _I, _I, _I, _F, _F, _I, _I, _P],
     "up_nchw_f32_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _L, _P],
     "up_nhwc_to_nchw_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _L, _P],
     "up_maxpool3x3s2": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P],

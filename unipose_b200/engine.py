@@ -312,8 +312,8 @@ class Plan:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches = 0
 
-    def static_input(self, shape) -> torch.Tensor:
-        t = torch.zeros(shape, dtype=torch.float32, device=self.device)
+    def static_input(self, shape, dtype=torch.float32) -> torch.Tensor:
+        t = torch.zeros(shape, dtype=dtype, device=self.device)
         self.inputs.append(t)
         return t
 

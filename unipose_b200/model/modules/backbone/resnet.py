@@ -153,8 +153,14 @@ class ResNet(PlanModule):
         return 16
 
     def _emit_image(self, b, x_static):
+        """x_static: fp32 NCHW [n,3,h,w] (the reference's input) or uint8 NHWC [n,h,w,3] (raw images; normalised
+        (x-128)/256 while packing, utils/mpii_data.py:184-185)."""
         from .... import ops
-        n, _, h, w = x_static.shape
+        u8 = x_static.dtype == torch.uint8
+        if u8:
+            n, h, w, _ = x_static.shape
+        else:
+            n, _, h, w = x_static.shape
         if h % 16 or w % 16:
             raise ValueError('unipose_b200: input height/width must be multiples of 16 (got %dx%d)' % (h, w))
         # Super-pixel stem: the 2x2 space-to-depth image (16 channels, rows padded by 2 zero pixels on the left) is
@@ -163,7 +169,10 @@ class ResNet(PlanModule):
         # activation row the TMA fetches is 128 aligned bytes and is shared by 4 outputs.
         ws = w // 8
         x2 = b.act(n, h // 2, ws + 1, 64, zero=True)
-        b.add(lambda x_static=x_static, x2=x2: ops.pack_input_s2d(x_static, x2, wpad_left=2), "pack_input_s2d")
+        if u8:
+            b.add(lambda x_static=x_static, x2=x2: ops.pack_input_u8_s2d(x_static, x2, wpad_left=2), "pack_input_u8_s2d")
+        else:
+            b.add(lambda x_static=x_static, x2=x2: ops.pack_input_s2d(x_static, x2, wpad_left=2), "pack_input_s2d")
         stem = b.act(n, h // 2, w // 2, 64)
         pc = b.packed_conv(self.conv1, self.bn1, cin_pad=64, weight_fn=stem_superpixel_weight)
         b.conv(x2, pc, stem.reshaped(h // 2, ws, 256), "stem", pad=(2, 0), relu=True, ho=h // 2, wo=ws)

@@ -28,10 +28,12 @@ class unipose(PlanModule):
             self.freeze_bn()
 
     # ------------------------------------------------------------------------------------------
-    def _build_plan(self, shape, device):
+    def _build_plan(self, shape, device, u8=False):
         plan = engine.Plan(device, self._precision())
         b = plan.builder
-        st = plan.static_input(shape)
+        st = plan.static_input(shape, dtype=torch.uint8 if u8 else torch.float32)
+        if u8:
+            shape = (shape[0], 3, shape[1], shape[2])
         x, low = self.backbone._emit_image(b, st)
         x = self.wasp._emit(b, x)
         heat = self.decoder._emit(b, x, low)
@@ -46,12 +48,26 @@ class unipose(PlanModule):
 
     def plan_for(self, input):
         """The compiled plan for this input shape (bench / profiling hook)."""
-        key = (tuple(input.shape), self._precision(), input.device.index, self.stride)
+        u8 = input.dtype == torch.uint8
+        key = (tuple(input.shape), self._precision(), input.device.index, self.stride, u8)
         plan = self._plans.get(key)
         if plan is None:
-            plan = self._build_plan(tuple(input.shape), input.device)
+            plan = self._build_plan(tuple(input.shape), input.device, u8=u8)
             self._plans[key] = plan
         return plan
+
+    def forward_uint8(self, images):
+        """Inference on raw uint8 HWC images [N, H, W, 3] (cv2 / decoder layout, BGR or RGB as the weights expect):
+        the reference's `(img - 128) / 256` normalisation (utils/mpii_data.py:184-185) is fused into the stem's input
+        packing, so a batch costs a quarter of the host->device bytes of the fp32 NCHW tensor and produces the same
+        bits as forward(normalised fp32 input)."""
+        self._check_inputs([images])
+        if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[3] != 3:
+            raise ValueError("forward_uint8 expects uint8 [N, H, W, 3]; got %s %s" % (images.dtype, tuple(images.shape)))
+        if self.training:
+            raise NotImplementedError("forward_uint8 is an inference entry point (call .eval())")
+        self._bn_eval_only()
+        return self.plan_for(images).run(images.contiguous())[0].clone()
 
     def forward(self, input):
         self._check_inputs([input])

@@ -229,6 +229,17 @@ def pack_input_s2d(x_nchw: torch.Tensor, y: Act, wpad_left: int = 0) -> None:
     _lib.call("up_pack_input_s2d", _ptr(x_nchw), y.ptr(), n, h, w, y.mode, y.plane_stride, wpitch, wpad_left, _stream())
 
 
+def pack_input_u8_s2d(x_nhwc_u8: torch.Tensor, y: Act, wpad_left: int = 0, mean: float = 128.0, std: float = 256.0) -> None:
+    """uint8 HWC images [n, h, w, 3] -> normalised 2x2 space-to-depth NHWC16 (same layout rules as pack_input_s2d)."""
+    n, h, w, c = x_nhwc_u8.shape
+    assert c == 3 and x_nhwc_u8.dtype == torch.uint8 and x_nhwc_u8.is_contiguous()
+    assert (y.n, y.h) == (n, h // 2) and y.c % 16 == 0
+    wpitch = y.w * (y.c // 16)
+    assert wpitch >= w // 2 + wpad_left
+    _lib.call("up_pack_input_u8_s2d", _ptr(x_nhwc_u8), y.ptr(), n, h, w, y.mode, y.plane_stride, wpitch, wpad_left,
+              float(mean), float(std), _stream())
+
+
 def nchw_to_act(x: torch.Tensor, y, c_real: Optional[int] = None) -> None:
     yv = as_view(y)
     n, c, h, w = x.shape
