@@ -277,12 +277,24 @@ int up_avgpool9s8p1_f32(const float* x, float* y, int n, int c, int h, int w, in
 /* LSTM_0.forward (uniposeLSTM.py:16-24): x fp32 NCHW [b,cin,h,w];  w3 [3][c][cin][3][3] and b3 [3][c]
  * hold conv_{g,i,o}_lstm in that order;  outputs cell, hide fp32 NCHW [b,c,h,w]  (c <= 16). */
 int up_convlstm_cell0_fwd(const float* x, const float* w3, const float* b3, float* cell, float* hide, int b,
-                          int cin, int c, int h, int w, void* stream);
+                          int cin, int c, int h, int w, float* gates, void* stream);
 /* LSTM.forward (uniposeLSTM.py:40-64): gates g,i,o,f each conv_x(x)+conv_h(h_prev) with both biases.
  * wx/bx: [4][c][cin][3][3] / [4][c] in gate order g,i,o,f;  wh/bh: [4][c][c][3][3] / [4][c]. */
 int up_convlstm_cell_fwd(const float* x, const float* h_prev, const float* c_prev, const float* wx,
                          const float* bx, const float* wh, const float* bh, float* cell, float* hide, int b,
-                         int cin, int c, int h, int w, void* stream);
+                         int cin, int c, int h, int w, float* gates, void* stream);
+/* Both forwards: `gates` (optional, training) receives the ACTIVATED gates fp32 [b, G, c, h, w] in the order g, i, o
+ * (G = 3, LSTM_0) / g, i, o, f (G = 4, LSTM) for the backward pass.
+ *
+ * Backward of either cell (loss.backward() through uniposeLSTM.py:16-24 / :40-64 - the video model trains through all
+ * 5 frames with ONE backward, uniposeLSTM.py:116-132): from dcell / dhide (either may be NULL = zero) to
+ *   dx [b,cin,h,w], dwx / dbx ([G,c,cin,3,3] / [G,c], the stacked layouts of the forwards), and for LSTM (wh != NULL)
+ *   dh_prev, dc_prev [b,c,h,w], dwh / dbh.  (The reference adds the x- and h-conv biases, so dbh == dbx.)
+ * dpre: scratch fp32 [b, G, c, h, w].  All reductions are fixed-order (deterministic). */
+int up_convlstm_cell_bwd(const float* x, const float* h_prev, const float* c_prev, const float* gates, const float* cell,
+                         const float* dcell, const float* dhide, const float* wx, const float* wh, float* dx,
+                         float* dh_prev, float* dc_prev, float* dwx, float* dbx, float* dwh, float* dbh, float* dpre,
+                         int b, int cin, int c, int h, int w, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Evaluation (utils/evaluate.py)

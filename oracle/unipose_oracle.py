@@ -179,11 +179,13 @@ def middle_cnn_forward(h, sd: SD):
 
 
 def unipose_lstm_forward(inp, centermap, it: int, prev_heat, prev_hide, prev_cell, sd: SD,
-                         output_stride: int = 16):
+                         output_stride: int = 16, training: bool = False, dropout_masks=None):
     """uniposeLSTM.unipose.forward — model/uniposeLSTM.py:98-147, generalised over the batch dim
-    (the reference hard-codes batch 1 / 46x46 via torch.zeros(1,15,46,46).cuda(), :99-104)."""
+    (the reference hard-codes batch 1 / 46x46 via torch.zeros(1,15,46,46).cuda(), :99-104).
+    training=True: BatchNorm on batch statistics, dropout masks supplied by the test (uniposeLSTM.py:102 .train())."""
     frame = inp[:, it]
-    heat = unipose_forward(frame, sd, output_stride, stride=8, video=True)
+    heat = unipose_forward(frame, sd, output_stride, stride=8, video=True, training=training,
+                           dropout_masks=dropout_masks)
     cm = F.avg_pool2d(centermap[:, it], kernel_size=9, stride=8, padding=1)
     cat = torch.cat((heat, cm), dim=1)
     if it == 0:

@@ -1,0 +1,137 @@
+"""Training path of the video model (BASELINE north star: "forward and backward are both implemented" for the
+ConvLSTM kernel path): the reference's clip loop - one model(...) call per frame in train mode, summed MSE, ONE
+backward through all frames (uniposeLSTM.py:116-132) - against torch autograd over the CPU oracle."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import evaluate_oracle as E
+from oracle import unipose_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_l2(a, b):
+    a = a.detach().double().cpu().flatten()
+    b = b.detach().double().cpu().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _cos(a, b):
+    a = a.detach().double().cpu().flatten()
+    b = b.detach().double().cpu().flatten()
+    return float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-300))
+
+
+def _oracle_clip(sd, inp, cm, target, masks, T, dtype):
+    sd = {k: (v.clone().to(dtype).requires_grad_(True) if v.is_floating_point() and "running" not in k
+              else (v.clone().to(dtype) if v.is_floating_point() else v.clone())) for k, v in sd.items()}
+    heat = hide = cell = None
+    loss = 0
+    heats = []
+    for t in range(T):
+        heat, cell, hide = O.unipose_lstm_forward(inp.to(dtype), cm.to(dtype), t, heat, hide, cell, sd, training=True,
+                                                  dropout_masks=[m.to(dtype) for m in masks[t]])
+        loss = loss + F.mse_loss(heat, target[:, t].to(dtype))
+        heats.append(heat.detach())
+    loss.backward()
+    return heats, loss.detach(), sd
+
+
+CHECK = ["conv5.weight", "conv5.bias", "conv3.weight", "conv1.weight", "conv1.bias", "lstm.conv_gx_lstm.weight",
+         "lstm.conv_fh_lstm.weight", "lstm.conv_oh_lstm.bias", "lstm.conv_ix_lstm.bias", "lstm_0.conv_g_lstm.weight",
+         "lstm_0.conv_o_lstm.bias", "decoder.last_conv.8.weight", "decoder.last_conv.8.bias", "decoder.last_conv.0.weight",
+         "wasp.global_avg_pool.1.weight", "wasp.conv1.weight", "wasp.aspp3.atrous_conv.weight",
+         "backbone.layer3.11.conv2.weight", "backbone.conv1.weight"]
+
+
+def test_video_clip_training_matches_oracle_autograd():
+    from unipose_b200.model import uniposeLSTM
+    B, T, S = 1, 3, 96
+    hs = S // 8
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = uniposeLSTM.unipose(num_classes=13, precision="fp32")
+    sd = O.synth_state_dict(13, video=True, seed=3)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().train()
+    inp = O.synth_input(B * T, S, S, seed=33).view(B, T, 3, S, S)
+    cm = torch.from_numpy(E.gaussian_heatmaps(B, T, S, S, seed=8, sigma=9.0)[:, 1:T + 1]).reshape(B, T, 1, S, S)
+    target = torch.from_numpy(E.gaussian_heatmaps(B * T, 13, hs, hs, seed=9)).view(B, T, 14, hs, hs)
+    g = torch.Generator().manual_seed(17)
+    masks = []
+    for t in range(T):
+        per = []
+        for shape, p in (((B, 256, S // 16, S // 16), 0.5), ((B, 256, hs, hs), 0.5), ((B, 256, hs, hs), 0.1)):
+            per.append((torch.rand(shape, generator=g) >= p).float() / (1.0 - p))
+        masks.append(per)
+
+    from unipose_b200 import train
+    heat = torch.zeros(B, 14, hs, hs).cuda()
+    hide = torch.zeros(B, 15, hs, hs).cuda()
+    cell = torch.zeros(B, 15, hs, hs).cuda()
+    loss = 0
+    heats = []
+    for t in range(T):     # the reference's loop (uniposeLSTM.py:124-128) with the dropout masks pinned for parity
+        heat, cell, hide = train.forward_train_video(m, inp.cuda(), cm.cuda(), t, hide, cell,
+                                                     dropout_masks=[x.cuda() for x in masks[t]])
+        assert heat.requires_grad and heat.shape == (B, 14, hs, hs) and cell.shape == (B, 15, hs, hs)
+        loss = loss + F.mse_loss(heat, target[:, t].cuda())
+        heats.append(heat.detach())
+    loss.backward()
+
+    ref_heats, ref_loss, ref_sd = _oracle_clip(sd, inp, cm, target, masks, T, torch.float32)
+    h64, l64, sd64 = _oracle_clip(sd, inp, cm, target, masks, T, torch.float64)
+    for t in range(T):
+        assert _rel_l2(heats[t], h64[t]) < 2e-3, (t, _rel_l2(heats[t], h64[t]))
+    assert abs(float(loss.detach()) - float(l64)) < 2e-3 * float(l64)
+    params = dict(m.named_parameters())
+    report = {}
+    for k in CHECK:
+        assert params[k].grad is not None, k
+        ours = _rel_l2(params[k].grad, sd64[k].grad)
+        floor = _rel_l2(ref_sd[k].grad, sd64[k].grad)
+        report[k] = (ours, floor, _cos(params[k].grad, sd64[k].grad))
+    print("video clip grad rel-L2 (ours vs fp64, reference-fp32 vs fp64, cosine):",
+          {k: "%.1e / %.1e / %.5f" % v for k, v in report.items()})
+    for k, (ours, floor, cos) in report.items():
+        # same criterion as the image model (tests/test_gpu_train.py): 40x the reference's own fp32-vs-fp64 error,
+        # never above 0.1; the recurrent / middle-CNN parameters sit right behind the loss and must be tight
+        assert ours <= min(max(40.0 * floor, 2e-3), 0.1), (k, ours, floor)
+        assert cos > 0.995, (k, report[k])
+    for k in ("conv5.weight", "conv5.bias", "lstm.conv_fh_lstm.weight", "lstm_0.conv_g_lstm.weight"):
+        assert report[k][0] < 5e-3, (k, report[k])
+
+
+def test_video_training_loop_runs_through_module_call():
+    """model(input, centermap, j, heat, hide, cell) in .train() mode, five frames, one backward, one optimizer step."""
+    from unipose_b200.model import uniposeLSTM
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = uniposeLSTM.unipose(num_classes=13, precision="bf16")
+    m.load_state_dict(O.synth_state_dict(13, video=True, seed=4), strict=True)
+    m = m.cuda().train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    B, T, S = 1, 5, 96
+    hs = S // 8
+    inp = O.synth_input(B * T, S, S, seed=34).view(B, T, 3, S, S).cuda()
+    cm = torch.rand(B, T, 1, S, S).cuda()
+    target = torch.rand(B, T, 14, hs, hs).cuda()
+    losses = []
+    for _ in range(2):
+        opt.zero_grad()
+        heat = torch.zeros(14, hs, hs).cuda()
+        hide = torch.zeros(15, hs, hs).cuda()
+        cell = torch.zeros(15, hs, hs).cuda()
+        loss = 0
+        for j in range(T):
+            heat, cell, hide = m(inp, cm, j, heat, hide, cell)
+            loss = loss + F.mse_loss(heat, target[:, j])
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[1] < losses[0], losses
+    assert m.lstm.conv_fh_lstm.weight.grad is not None and m.backbone.conv1.weight.grad is not None

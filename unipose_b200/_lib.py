@@ -84,8 +84,9 @@ _SIGNATURES = {
     "up_global_sumpool": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P],
     "up_upsample_bilinear_ac_nchw_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "up_avgpool9s8p1_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    "up_convlstm_cell0_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "up_convlstm_cell_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "up_convlstm_cell0_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "up_convlstm_cell_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "up_convlstm_cell_bwd": [_P] * 17 + [_I, _I, _I, _I, _I, _P],
     "up_argmax2d": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "up_calc_dists": [_P, _P, _P, _I, _I, _D, _D, _P],
     "up_dist_acc": [_P, _P, _I, _I, _D, _P],

@@ -96,7 +96,8 @@ __device__ __forceinline__ void lstm_accumulate(const float* __restrict__ src, i
 // LSTM_0: gates g,i,o from x only.
 __global__ void __launch_bounds__(kLstmTile * kLstmTile)
     convlstm_cell0_kernel(const float* __restrict__ x, const float* __restrict__ w3, const float* __restrict__ b3,
-                          float* __restrict__ cell, float* __restrict__ hide, int cin, int c, int h, int w, int ngroups) {
+                          float* __restrict__ cell, float* __restrict__ hide, float* __restrict__ gates, int cin, int c,
+                          int h, int w, int ngroups) {
   __shared__ float tile[(kLstmTile + 2) * (kLstmTile + 2)];
   extern __shared__ float wsm[];
   const int b = blockIdx.z / ngroups, co0 = (blockIdx.z % ngroups) * kLstmCoG;
@@ -121,6 +122,13 @@ __global__ void __launch_bounds__(kLstmTile * kLstmTile)
     const long long idx = ((static_cast<long long>(b) * c + co) * h + oy) * w + ox;
     cell[idx] = cl;
     hide[idx] = o * cl;
+    if (gates) {       // training: activated gates [b][3][c][h][w] for the backward pass
+      const long long plane = static_cast<long long>(c) * h * w;
+      float* gp = gates + static_cast<long long>(b) * 3 * plane + (static_cast<long long>(co) * h + oy) * w + ox;
+      gp[0] = g;
+      gp[plane] = i;
+      gp[2 * plane] = o;
+    }
   }
 }
 
@@ -128,8 +136,8 @@ __global__ void __launch_bounds__(kLstmTile * kLstmTile)
 __global__ void __launch_bounds__(kLstmTile * kLstmTile)
     convlstm_cell_kernel(const float* __restrict__ x, const float* __restrict__ hp, const float* __restrict__ cp,
                          const float* __restrict__ wx, const float* __restrict__ bx, const float* __restrict__ wh,
-                         const float* __restrict__ bh, float* __restrict__ cell, float* __restrict__ hide, int cin,
-                         int c, int h, int w, int ngroups) {
+                         const float* __restrict__ bh, float* __restrict__ cell, float* __restrict__ hide,
+                         float* __restrict__ gates, int cin, int c, int h, int w, int ngroups) {
   __shared__ float tile[(kLstmTile + 2) * (kLstmTile + 2)];
   extern __shared__ float wsm[];   // [x filters | h filters]
   const int b = blockIdx.z / ngroups, co0 = (blockIdx.z % ngroups) * kLstmCoG;
@@ -156,10 +164,134 @@ __global__ void __launch_bounds__(kLstmTile * kLstmTile)
     const float os = (acc[2][j] + bx[2 * c + co]) + (acch[2][j] + bh[2 * c + co]);
     const float fs = (acc[3][j] + bx[3 * c + co]) + (acch[3][j] + bh[3 * c + co]);
     const long long idx = ((static_cast<long long>(b) * c + co) * h + oy) * w + ox;
-    const float cl = sigmoidf_(fs) * cp[idx] + sigmoidf_(is) * tanhf(gs);
+    const float fg = sigmoidf_(fs), ig = sigmoidf_(is), gg = tanhf(gs), og = sigmoidf_(os);
+    const float cl = fg * cp[idx] + ig * gg;
     cell[idx] = cl;
-    hide[idx] = sigmoidf_(os) * tanhf(cl);
+    hide[idx] = og * tanhf(cl);
+    if (gates) {       // training: activated gates [b][4][c][h][w] in the order g, i, o, f
+      const long long plane = static_cast<long long>(c) * h * w;
+      float* gp = gates + static_cast<long long>(b) * 4 * plane + (static_cast<long long>(co) * h + oy) * w + ox;
+      gp[0] = gg;
+      gp[plane] = ig;
+      gp[2 * plane] = og;
+      gp[3 * plane] = fg;
+    }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// ConvLSTM cell backward (what loss.backward() runs through LSTM_0 / LSTM, uniposeLSTM.py:16-24,40-64,132)
+// ------------------------------------------------------------------------------------------
+// Pointwise part: gradients of the gate PRE-activations (and of c_prev) from dcell / dhide.
+//   LSTM_0: cell = tanh(g*i), hide = o*cell              LSTM: cell = f*c_prev + i*g, hide = o*tanh(cell)
+// gates: activated [b][G][c][h][w] (g, i, o(, f));  dpre: same shape.
+__global__ void convlstm_gate_grad_kernel(const float* __restrict__ gates, const float* __restrict__ cell,
+                                          const float* __restrict__ c_prev, const float* __restrict__ dcell,
+                                          const float* __restrict__ dhide, float* __restrict__ dpre,
+                                          float* __restrict__ dc_prev, long long per_image, int ngates, long long total) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const long long b = i / per_image, r = i - b * per_image;
+  const float* gp = gates + b * ngates * per_image + r;
+  float* dp = dpre + b * ngates * per_image + r;
+  const float g = gp[0], ig = gp[per_image], o = gp[2 * per_image];
+  const float dh = dhide ? dhide[i] : 0.f;
+  const float dc_in = dcell ? dcell[i] : 0.f;
+  if (ngates == 3) {
+    const float cl = cell[i];
+    const float dct = dc_in + dh * o;                 // d loss / d cell
+    const float dgi = dct * (1.f - cl * cl);          // through tanh(g*i)
+    dp[0] = dgi * ig * (1.f - g * g);
+    dp[per_image] = dgi * g * ig * (1.f - ig);
+    dp[2 * per_image] = dh * cl * o * (1.f - o);
+  } else {
+    const float f = gp[3 * per_image];
+    const float tc = tanhf(cell[i]);
+    const float dct = dc_in + dh * o * (1.f - tc * tc);
+    dp[0] = dct * ig * (1.f - g * g);
+    dp[per_image] = dct * g * ig * (1.f - ig);
+    dp[2 * per_image] = dh * tc * o * (1.f - o);
+    dp[3 * per_image] = dct * c_prev[i] * f * (1.f - f);
+    dc_prev[i] = dct * f;
+  }
+}
+
+// dIn[b][ci][y][x] = sum_{gate,co,ky,kx} dpre[b][gate][co][y+1-ky][x+1-kx] * w[gate][co][ci][ky][kx]   (3x3, padding 1)
+__global__ void __launch_bounds__(256)
+    convlstm_input_grad_kernel(const float* __restrict__ dpre, const float* __restrict__ wts, float* __restrict__ din,
+                               int ngates, int c, int cin, int h, int w, long long total) {
+  extern __shared__ float wsm[];        // [ngates][c][cin][9]
+  const int nw = ngates * c * cin * 9;
+  for (int e = threadIdx.x; e < nw; e += blockDim.x) wsm[e] = wts[e];
+  __syncthreads();
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int x = static_cast<int>(i % w);
+  const int y = static_cast<int>((i / w) % h);
+  const int ci = static_cast<int>((i / (static_cast<long long>(w) * h)) % cin);
+  const long long b = i / (static_cast<long long>(w) * h * cin);
+  const float* dp = dpre + b * ngates * c * h * w;
+  float acc = 0.f;
+  for (int gc = 0; gc < ngates * c; ++gc) {
+    const float* plane = dp + static_cast<long long>(gc) * h * w;
+    const float* wp = wsm + (gc * cin + ci) * 9;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + 1 - ky;
+      if (yy < 0 || yy >= h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + 1 - kx;
+        if (xx < 0 || xx >= w) continue;
+        acc = fmaf(plane[yy * w + xx], wp[ky * 3 + kx], acc);
+      }
+    }
+  }
+  din[i] = acc;
+}
+
+// One block per (gate*c + co, ci): dW[gate][co][ci][ky][kx] = sum_{b,y,x} dpre[b][gate][co][y][x] * in[b][ci][y+ky-1][x+kx-1];
+// blocks with ci == 0 also produce db[gate][co] = sum dpre.  Fixed-order block reduction: deterministic.
+__global__ void __launch_bounds__(256)
+    convlstm_weight_grad_kernel(const float* __restrict__ dpre, const float* __restrict__ in, float* __restrict__ dw,
+                                float* __restrict__ db, int nb, int ngates, int c, int cin, int h, int w) {
+  const int gc = blockIdx.x, ci = blockIdx.y;
+  float acc[10];
+#pragma unroll
+  for (int t = 0; t < 10; ++t) acc[t] = 0.f;
+  const int hw = h * w;
+  for (int e = threadIdx.x; e < nb * hw; e += blockDim.x) {
+    const int b = e / hw, r = e - b * hw;
+    const int y = r / w, x = r - y * w;
+    const float d = dpre[(static_cast<long long>(b) * ngates * c + gc) * hw + r];
+    const float* ip = in + (static_cast<long long>(b) * cin + ci) * hw;
+    acc[9] += d;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= w) continue;
+        acc[ky * 3 + kx] = fmaf(d, ip[yy * w + xx], acc[ky * 3 + kx]);
+      }
+    }
+  }
+  __shared__ float red[10][256];
+#pragma unroll
+  for (int t = 0; t < 10; ++t) red[t][threadIdx.x] = acc[t];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+#pragma unroll
+      for (int t = 0; t < 10; ++t) red[t][threadIdx.x] += red[t][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 9) dw[(static_cast<long long>(gc) * cin + ci) * 9 + threadIdx.x] = red[threadIdx.x][0];
+  if (threadIdx.x == 9 && ci == 0 && db) db[gc] = red[9][0];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -274,31 +406,68 @@ extern "C" int up_avgpool9s8p1_f32(const float* x, float* y, int n, int c, int h
 }
 
 extern "C" int up_convlstm_cell0_fwd(const float* x, const float* w3, const float* b3, float* cell, float* hide,
-                                     int b, int cin, int c, int h, int w, void* stream) {
+                                     int b, int cin, int c, int h, int w, float* gates, void* stream) {
   UP_CHECK_ARG(x && w3 && b3 && cell && hide, "up_convlstm_cell0_fwd: null argument");
   UP_CHECK_ARG(b > 0 && cin > 0 && c > 0 && c <= kLstmCMax, "up_convlstm_cell0_fwd: c must be <= %d", kLstmCMax);
   const int ngroups = (c + kLstmCoG - 1) / kLstmCoG;
   UP_CHECK_ARG(cin <= 64, "up_convlstm_cell0_fwd: cin must be <= 64");
   dim3 grid((w + kLstmTile - 1) / kLstmTile, (h + kLstmTile - 1) / kLstmTile, b * ngroups);
   const size_t wbytes = static_cast<size_t>(3) * kLstmCoG * cin * 9 * sizeof(float);
-  convlstm_cell0_kernel<<<grid, kLstmTile * kLstmTile, wbytes, (cudaStream_t)stream>>>(x, w3, b3, cell, hide, cin, c, h,
-                                                                                      w, ngroups);
+  convlstm_cell0_kernel<<<grid, kLstmTile * kLstmTile, wbytes, (cudaStream_t)stream>>>(x, w3, b3, cell, hide, gates, cin,
+                                                                                      c, h, w, ngroups);
   UP_CHECK_LAUNCH("convlstm_cell0_kernel");
   return 0;
 }
 
 extern "C" int up_convlstm_cell_fwd(const float* x, const float* h_prev, const float* c_prev, const float* wx,
                                     const float* bx, const float* wh, const float* bh, float* cell, float* hide, int b,
-                                    int cin, int c, int h, int w, void* stream) {
+                                    int cin, int c, int h, int w, float* gates, void* stream) {
   UP_CHECK_ARG(x && h_prev && c_prev && wx && bx && wh && bh && cell && hide, "up_convlstm_cell_fwd: null argument");
   UP_CHECK_ARG(b > 0 && cin > 0 && c > 0 && c <= kLstmCMax, "up_convlstm_cell_fwd: c must be <= %d", kLstmCMax);
   const int ngroups = (c + kLstmCoG - 1) / kLstmCoG;
   UP_CHECK_ARG(cin <= 32, "up_convlstm_cell_fwd: cin must be <= 32 (filters are staged in 48 KB of shared memory)");
   dim3 grid((w + kLstmTile - 1) / kLstmTile, (h + kLstmTile - 1) / kLstmTile, b * ngroups);
   const size_t wbytes = static_cast<size_t>(4) * kLstmCoG * (cin + c) * 9 * sizeof(float);
-  convlstm_cell_kernel<<<grid, kLstmTile * kLstmTile, wbytes, (cudaStream_t)stream>>>(x, h_prev, c_prev, wx, bx, wh, bh,
-                                                                                     cell, hide, cin, c, h, w, ngroups);
+  convlstm_cell_kernel<<<grid, kLstmTile * kLstmTile, wbytes, (cudaStream_t)stream>>>(
+      x, h_prev, c_prev, wx, bx, wh, bh, cell, hide, gates, cin, c, h, w, ngroups);
   UP_CHECK_LAUNCH("convlstm_cell_kernel");
+  return 0;
+}
+
+extern "C" int up_convlstm_cell_bwd(const float* x, const float* h_prev, const float* c_prev, const float* gates,
+                                    const float* cell, const float* dcell, const float* dhide, const float* wx,
+                                    const float* wh, float* dx, float* dh_prev, float* dc_prev, float* dwx, float* dbx,
+                                    float* dwh, float* dbh, float* dpre, int b, int cin, int c, int h, int w,
+                                    void* stream) {
+  UP_CHECK_ARG(x && gates && cell && wx && dx && dwx && dbx && dpre, "up_convlstm_cell_bwd: null argument");
+  UP_CHECK_ARG(dcell || dhide, "up_convlstm_cell_bwd: at least one of dcell / dhide is required");
+  const bool full = wh != nullptr;      // LSTM (4 gates, recurrent inputs) vs LSTM_0 (3 gates)
+  if (full) UP_CHECK_ARG(h_prev && c_prev && dh_prev && dc_prev && dwh && dbh, "up_convlstm_cell_bwd: recurrent arguments missing");
+  UP_CHECK_ARG(b > 0 && cin > 0 && c > 0 && c <= kLstmCMax && cin <= 32, "up_convlstm_cell_bwd: bad dims");
+  const int ng = full ? 4 : 3;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long per_image = static_cast<long long>(c) * h * w;
+  const long long total = per_image * b;
+  convlstm_gate_grad_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(gates, cell, c_prev, dcell, dhide, dpre,
+                                                                                  dc_prev, per_image, ng, total);
+  UP_CHECK_LAUNCH("convlstm_gate_grad_kernel");
+  {
+    const long long tx = static_cast<long long>(b) * cin * h * w;
+    const size_t wb = static_cast<size_t>(ng) * c * cin * 9 * sizeof(float);
+    UP_CHECK_ARG(wb <= 48 * 1024, "up_convlstm_cell_bwd: filters exceed 48 KB of shared memory");
+    convlstm_input_grad_kernel<<<static_cast<int>((tx + 255) / 256), 256, wb, st>>>(dpre, wx, dx, ng, c, cin, h, w, tx);
+    UP_CHECK_LAUNCH("convlstm_input_grad_kernel(x)");
+    convlstm_weight_grad_kernel<<<dim3(ng * c, cin), 256, 0, st>>>(dpre, x, dwx, dbx, b, ng, c, cin, h, w);
+    UP_CHECK_LAUNCH("convlstm_weight_grad_kernel(x)");
+  }
+  if (full) {
+    const long long th = static_cast<long long>(b) * c * h * w;
+    const size_t wb = static_cast<size_t>(ng) * c * c * 9 * sizeof(float);
+    convlstm_input_grad_kernel<<<static_cast<int>((th + 255) / 256), 256, wb, st>>>(dpre, wh, dh_prev, ng, c, c, h, w, th);
+    UP_CHECK_LAUNCH("convlstm_input_grad_kernel(h)");
+    convlstm_weight_grad_kernel<<<dim3(ng * c, c), 256, 0, st>>>(dpre, h_prev, dwh, dbh, b, ng, c, c, h, w);
+    UP_CHECK_LAUNCH("convlstm_weight_grad_kernel(h)");
+  }
   return 0;
 }
 

@@ -46,13 +46,13 @@ class LSTM_0(PlanModule):
     def sources(self):
         return [p for c in self._gates() for p in (c.weight, c.bias)]
 
-    def launch(self, x, cell, hide, stacked=None):
+    def launch(self, x, cell, hide, stacked=None, gates=None):
         """x fp32 NCHW (contiguous, CUDA) -> cell, hide written in place.  `stacked`: pre-stacked gate weights (plans
         keep them in static buffers refreshed by a pack job, so a captured graph never bakes a temporary's address)."""
         w3, b3 = stacked if stacked is not None else self.stacked()
         b, cin, h, w = x.shape
         ops._lib.call("up_convlstm_cell0_fwd", ops._ptr(x), ops._ptr(w3), ops._ptr(b3), ops._ptr(cell), ops._ptr(hide),
-                      b, cin, w3.shape[1], h, w, ops._stream())
+                      b, cin, w3.shape[1], h, w, ops._ptr(gates), ops._stream())
 
     def forward(self, x):
         ops.require_cuda(x, "LSTM_0 input")
@@ -86,12 +86,12 @@ class LSTM(PlanModule):
         return [p for sfx in 'xh' for g in 'giof' for p in (getattr(self, 'conv_%s%s_lstm' % (g, sfx)).weight,
                                                             getattr(self, 'conv_%s%s_lstm' % (g, sfx)).bias)]
 
-    def launch(self, x, h_prev, c_prev, cell, hide, stacked=None):
+    def launch(self, x, h_prev, c_prev, cell, hide, stacked=None, gates=None):
         wx, bx, wh, bh = stacked if stacked is not None else self.stacked()
         b, cin, h, w = x.shape
         ops._lib.call("up_convlstm_cell_fwd", ops._ptr(x), ops._ptr(h_prev), ops._ptr(c_prev), ops._ptr(wx),
                       ops._ptr(bx), ops._ptr(wh), ops._ptr(bh), ops._ptr(cell), ops._ptr(hide), b, cin, wx.shape[1],
-                      h, w, ops._stream())
+                      h, w, ops._ptr(gates), ops._stream())
 
     def forward(self, x, prevHide, prevCell):
         ops.require_cuda(x, "LSTM input")
@@ -228,6 +228,10 @@ class unipose(PlanModule):
     def forward(self, input, centermap, iter, previous, previousHide, previousCell):
         import os
         self._check_inputs([input, centermap])
+        if self.training:
+            # train mode: the frame's training plan, chained to the previous frames by autograd through (cell, hide)
+            from .. import train
+            return train.forward_train_video(self, input, centermap, int(iter), previousHide, previousCell)
         self._bn_eval_only()
         b_, t_, _c, h, w = input.shape
         first = (iter == 0)

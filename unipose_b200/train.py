@@ -138,8 +138,12 @@ class TrainPlan:
     # ---- ops with adjoints --------------------------------------------------------------------------
     def conv_unit(self, x, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], *, relu: bool, residual=None, stride=1,
                   dil=1, pad=None, mask=None, x_groups=1, x_group_nstride=0, x_window=None, weight_fn=None,
-                  weight_fn_inv=None, cin_pad=None, cout_pad=None, x_needs_grad=True, out=None, nchw_out=None):
-        """conv (+ train-mode BatchNorm) (+ residual) (+ ReLU) (+ dropout mask); records its backward."""
+                  weight_fn_inv=None, cin_pad=None, cout_pad=None, x_needs_grad=True, out=None, nchw_out=None,
+                  nchw_grad=None):
+        """conv (+ train-mode BatchNorm) (+ residual) (+ ReLU) (+ dropout mask); records its backward.
+        bn=None: conv (+ bias) (+ ReLU) - the video model's middle CNN and pooling branch.  nchw_out: the conv writes
+        fp32 NCHW straight into (the first channels of) that tensor; its gradient is read from `nchw_grad` (default: the
+        plan's dheat), a tensor of the same shape."""
         xv = as_view(x)
         w_src = (lambda: conv.weight.detach()) if weight_fn is None else (lambda: weight_fn(conv.weight.detach()))
         w0 = w_src()
@@ -171,18 +175,24 @@ class TrainPlan:
         rec = dict(x=xv, conv=conv, bn=bn, relu=relu, residual=residual, mask=mask, pc=pc, z=z, stride=stride, dil=dil,
                    pad=pad, ho=ho, wo=wo, x_groups=x_groups, x_group_nstride=x_group_nstride, x_window=x_window,
                    weight_fn=weight_fn, weight_fn_inv=weight_fn_inv, x_needs_grad=x_needs_grad, cout=cout, cin=cin,
-                   co_r=co_r, ci_r=ci_r, kh=kh, kw=kw, nchw_out=nchw_out)
+                   co_r=co_r, ci_r=ci_r, kh=kh, kw=kw, nchw_out=nchw_out, nchw_grad=nchw_grad)
         if nchw_out is not None:
-            # network head: conv + bias straight into the fp32 NCHW heat-map tensor
-            self.fwd.append(lambda: ops.conv2d(xv, pc, nchw_out, cout_valid=co_r, **kw_conv))
+            # network head: conv + bias (+ ReLU) straight into the fp32 NCHW heat-map tensor
+            assert bn is None and mask is None and residual is None
+            self.fwd.append(lambda: ops.conv2d(xv, pc, nchw_out, cout_valid=co_r, out_c_total=nchw_out.shape[1],
+                                               relu=relu, **kw_conv))
             rec["y"] = None
             self.tape.append(lambda: self._conv_unit_bwd(rec))
             return nchw_out
-        self.fwd.append(lambda: ops.conv2d(xv, pc, z, **kw_conv))
         if bn is None:
+            if mask is not None or residual is not None:
+                raise NotImplementedError("conv without BatchNorm supports bias (+ ReLU) epilogues in training")
+            self.fwd.append(lambda: ops.conv2d(xv, pc, z, relu=relu, **kw_conv))
             y = z
-            if relu or mask is not None or residual is not None:
-                raise NotImplementedError("conv without BatchNorm only supports a plain (bias) epilogue in training")
+        else:
+            self.fwd.append(lambda: ops.conv2d(xv, pc, z, **kw_conv))
+        if bn is None:
+            pass
         else:
             c = cout
             sums = self.tensor((ops.bn_work_doubles(c),), dtype=torch.float64)   # sums + scratch + partial rows
@@ -208,7 +218,12 @@ class TrainPlan:
         # ---- gradient w.r.t. the conv output z ----
         if r["nchw_out"] is not None:
             dz = self.act(n, ho, wo, cout, zero=True)
-            dheat = self.dheat
+            dheat = r["nchw_grad"] if r["nchw_grad"] is not None else self.dheat
+            if r["relu"]:
+                gated = self.tensor(tuple(dheat.shape), zero=False)
+                yout = r["nchw_out"]
+                self.bwd.append(lambda: torch.mul(dheat, (yout > 0).to(dheat.dtype), out=gated))
+                dheat = gated
             self.bwd.append(lambda: ops.nchw_to_act(dheat, dz))
             if conv.bias is not None:
                 bsums = self.tensor((ops.bn_work_doubles(cout),), dtype=torch.float64)
@@ -227,7 +242,18 @@ class TrainPlan:
                 self.bwd.append(lambda dy=dy, tmp=tmp, mask=mask: ops.ew(dy, tmp, m=mask, op=1))
                 dy = as_view(tmp)
             if bn is None:
-                dz = dy          # plain conv: dz is the incoming gradient itself
+                dz = dy          # plain conv: dz is the incoming gradient itself ...
+                if r["relu"]:    # ... gated by the ReLU of the fused epilogue
+                    tmp = self.act(n, ho, wo, cout)
+                    self.bwd.append(lambda dy=dy, tmp=tmp, y=y: ops.ew(dy, tmp, m=y, op=2))
+                    dz = as_view(tmp)
+                if conv.bias is not None:
+                    bsums = self.tensor((ops.bn_work_doubles(cout),), dtype=torch.float64)
+                    gb = self.param_grad(conv.bias)
+                    dzb = dz
+                    self.bwd.append(lambda: ops.bn_stats(dzb, cout, bsums))
+                    self.bwd.append(lambda: gb.copy_(bsums[:r["co_r"]]))
+                    self._grad_final(conv.bias)
             else:
                 dz = self.act(n, ho, wo, cout)
                 dres, dres_tmp, rv = None, None, None
@@ -425,15 +451,12 @@ def _stem_window_weight_inv(g: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def build_image_train_plan(model, shape, device, precision: str, flat: bool = False) -> TrainPlan:
+def _emit_trunk(tp: TrainPlan, model, n: int, h: int, w: int, head_out: torch.Tensor, head_grad=None) -> None:
+    """backbone -> WASP -> decoder in train mode (model/unipose.py:27-38 / model/uniposeLSTM.py:108-113) over tp.input
+    [n,3,h,w]; the head conv writes fp32 NCHW into the first channels of `head_out`, its gradient is read from
+    `head_grad` (default tp.dheat)."""
     from .model.modules.backbone.resnet import stem_window_weight
-    n, _, h, w = shape
-    if h % 16 or w % 16:
-        raise ValueError("unipose_b200: input height/width must be multiples of 16")
-    tp = TrainPlan(device, precision)
-    tp.input = torch.zeros(shape, dtype=torch.float32, device=device)
     bb, wasp, dec = model.backbone, model.wasp, model.decoder
-
     # ---- backbone ----
     x2 = tp.act(n, h // 2, w // 2 + 3, 16, zero=True)
     tp.fwd.append(lambda: ops.pack_input_s2d(tp.input, x2, wpad_left=2))
@@ -456,7 +479,7 @@ def build_image_train_plan(model, shape, device, precision: str, flat: bool = Fa
     feat = x
     hh, ww = feat.h, feat.w
 
-    # ---- WASP (wasp.py:66-90) ----
+    # ---- WASP (wasp.py:66-90; waspVideo.py:67-91: no BatchNorm in the pooling branch) ----
     S = tp.act(4 * n, hh, ww, 256)
     br = [View(S, n_off=i * n, n=n) for i in range(4)]
     aspp = [wasp.aspp1, wasp.aspp2, wasp.aspp3, wasp.aspp4]
@@ -472,8 +495,6 @@ def build_image_train_plan(model, shape, device, precision: str, flat: bool = Fa
     tp.global_avgpool(feat, g)
     gap_seq = wasp.global_avg_pool
     gap_bn = gap_seq[2] if isinstance(gap_seq[2], nn.BatchNorm2d) else None
-    if gap_bn is None:
-        raise NotImplementedError("unipose_b200: training the video WASP (no BatchNorm in the pooling branch) is not supported yet")
     g2 = tp.conv_unit(g, gap_seq[1], gap_bn, relu=True)
     tp.broadcast_hw(g2, View(U, n_off=4 * n, n=n))
     mask_w = tp.act(n, hh, ww, 256)
@@ -494,10 +515,115 @@ def build_image_train_plan(model, shape, device, precision: str, flat: bool = Fa
     tp.masks.append((m2, lc[7].p))
     d1 = tp.conv_unit(cat, lc[0], lc[1], relu=True, pad=1, cin_pad=320, mask=m1)
     d2 = tp.conv_unit(d1, lc[4], lc[5], relu=True, pad=1, mask=m2)
-    tp.heat = torch.zeros((n, dec.num_out, hc, wc), dtype=torch.float32, device=device)
+    tp.conv_unit(d2, lc[8], None, relu=False, nchw_out=head_out, nchw_grad=head_grad)
+
+
+def build_image_train_plan(model, shape, device, precision: str, flat: bool = False) -> TrainPlan:
+    n, _, h, w = shape
+    if h % 16 or w % 16:
+        raise ValueError("unipose_b200: input height/width must be multiples of 16")
+    tp = TrainPlan(device, precision)
+    tp.input = torch.zeros(shape, dtype=torch.float32, device=device)
+    tp.heat = torch.zeros((n, model.decoder.num_out, h // 8, w // 8), dtype=torch.float32, device=device)
     tp.dheat = torch.zeros_like(tp.heat)
-    tp.conv_unit(d2, lc[8], None, relu=False, nchw_out=tp.heat)
+    _emit_trunk(tp, model, n, h, w, tp.heat)
     tp.finalize(flat=flat)
+    return tp
+
+
+def build_video_frame_train_plan(model, b_: int, h: int, w: int, first: bool, device, precision: str) -> TrainPlan:
+    """One frame of model/uniposeLSTM.unipose.forward (:98-147) in train mode with everything its backward needs:
+    trunk -> cat(heat-maps, pooled centre map) -> LSTM_0 / LSTM (activated gates saved) -> 11x11 / 1x1 middle CNN with
+    bias + ReLU epilogues.  The frames of a clip are chained by torch autograd through (cell, hide) - the reference
+    runs ONE backward over all 5 frames (uniposeLSTM.py:116-132)."""
+    if h % 16 or w % 16:
+        raise ValueError("unipose_b200: input height/width must be multiples of 16")
+    tp = TrainPlan(device, precision)
+    hs, ws = h // 8, w // 8
+    k1 = model.decoder.num_out
+    cell_mod = model.lstm_0 if first else model.lstm
+    lstm_c = model.lstm_0.conv_g_lstm.in_channels
+    planes = model.lstm_0.conv_g_lstm.out_channels
+    ng = 3 if first else 4
+
+    def f32(*shape):
+        return torch.zeros(shape, dtype=torch.float32, device=device)
+    tp.input = f32(b_, 3, h, w)
+    tp.cmap = f32(b_, 1, h, w)
+    tp.cat, tp.dcat = f32(b_, lstm_c, hs, ws), f32(b_, lstm_c, hs, ws)
+    tp.heat = f32(b_, model.conv5.out_channels, hs, ws)
+    tp.dheat = torch.zeros_like(tp.heat)
+    tp.cell, tp.hide = f32(b_, planes, hs, ws), f32(b_, planes, hs, ws)
+    tp.hp, tp.cp = f32(b_, planes, hs, ws), f32(b_, planes, hs, ws)
+    tp.dhide_ext, tp.dcell_ext = f32(b_, planes, hs, ws), f32(b_, planes, hs, ws)
+    tp.dhide_mid, tp.dhide_tot = f32(b_, planes, hs, ws), f32(b_, planes, hs, ws)
+    tp.dhp, tp.dcp = f32(b_, planes, hs, ws), f32(b_, planes, hs, ws)
+    gates, dpre = f32(b_, ng, planes, hs, ws), f32(b_, ng, planes, hs, ws)
+
+    # ---- trunk: heat-maps into channels [0, K+1) of the LSTM input, centre map into the last one ----
+    _emit_trunk(tp, model, b_, h, w, tp.cat, head_grad=tp.dcat)
+    tp.fwd.append(lambda: ops._lib.call("up_avgpool9s8p1_f32", ops._ptr(tp.cmap), ops._ptr(tp.cat), b_, 1, h, w, hs, ws,
+                                        lstm_c, k1, ops._stream()))
+
+    # ---- ConvLSTM cell ----
+    gate_w = [torch.empty_like(t) for t in cell_mod.stacked()]
+    gate_g = [torch.zeros_like(t) for t in gate_w]
+
+    def restack():
+        for dst, src in zip(gate_w, cell_mod.stacked()):
+            dst.copy_(src)
+    tp.fwd.append(restack)
+    if first:
+        tp.fwd.append(lambda: model.lstm_0.launch(tp.cat, tp.cell, tp.hide, stacked=gate_w, gates=gates))
+    else:
+        tp.fwd.append(lambda: model.lstm.launch(tp.cat, tp.hp, tp.cp, tp.cell, tp.hide, stacked=gate_w, gates=gates))
+    lstm_params = cell_mod.sources()
+    for prm in lstm_params:
+        if id(prm) not in tp._live_ids:
+            tp._live_ids.add(id(prm))
+            tp.live_params.append(prm)
+
+    def lstm_bwd():
+        tp.bwd.append(lambda: torch.add(tp.dhide_mid, tp.dhide_ext, out=tp.dhide_tot))
+        null = None
+        if first:
+            args = (tp.cat, null, null, gates, tp.cell, tp.dcell_ext, tp.dhide_tot, gate_w[0], null, tp.dcat, null, null,
+                    gate_g[0], gate_g[1], null, null, dpre)
+        else:
+            args = (tp.cat, tp.hp, tp.cp, gates, tp.cell, tp.dcell_ext, tp.dhide_tot, gate_w[0], gate_w[2], tp.dcat, tp.dhp,
+                    tp.dcp, gate_g[0], gate_g[1], gate_g[2], gate_g[3], dpre)
+        tp.bwd.append(lambda: ops._lib.call("up_convlstm_cell_bwd", *[ops._ptr(a) for a in args], b_, lstm_c, planes, hs, ws,
+                                            ops._stream()))
+        # the stacked gradients back to the reference's per-gate parameters
+        if first:
+            convs = [(c, 0, i) for i, c in enumerate(model.lstm_0._gates())]
+        else:
+            convs = [(getattr(model.lstm, 'conv_%s%s_lstm' % (g, sfx)), 0 if sfx == 'x' else 2, i)
+                     for sfx in 'xh' for i, g in enumerate('giof')]
+        for conv, base, i in convs:
+            gw, gb = tp.param_grad(conv.weight), tp.param_grad(conv.bias)
+            tp.bwd.append(lambda gw=gw, gb=gb, base=base, i=i: (gw.copy_(gate_g[base][i]), gb.copy_(gate_g[base + 1][i])))
+            tp._grad_final(conv.weight)
+            tp._grad_final(conv.bias)
+    tp.tape.append(lstm_bwd)
+
+    # ---- middle CNN: conv 11x11 x3, 1x1 x2, ReLU after every one including the last (uniposeLSTM.py:120-124) ----
+    hin = tp.act(b_, hs, ws, 64, zero=True)
+    tp.fwd.append(lambda: ops.nchw_to_act(tp.hide, hin))
+
+    def hin_bwd():
+        if tp.has_grad(hin):
+            ghin = tp.grad_view(hin)
+            tp.bwd.append(lambda: ops.act_to_nchw(ghin, planes, tp.dhide_mid))
+        else:
+            tp.bwd.append(lambda: tp.dhide_mid.zero_())
+    tp.tape.append(hin_bwd)
+    a1 = tp.conv_unit(hin, model.conv1, None, relu=True, pad=5, cin_pad=64)
+    a2 = tp.conv_unit(a1, model.conv2, None, relu=True, pad=5)
+    a3 = tp.conv_unit(a2, model.conv3, None, relu=True, pad=5)
+    a4 = tp.conv_unit(a3, model.conv4, None, relu=True)
+    tp.conv_unit(a4, model.conv5, None, relu=True, nchw_out=tp.heat)
+    tp.finalize(flat=False)
     return tp
 
 
@@ -533,6 +659,64 @@ def forward_train(model, input: torch.Tensor, dropout_masks=None) -> torch.Tenso
         plan = build_image_train_plan(model, tuple(input.shape), input.device, model._precision())
         model._plans[key] = plan
     return _TrainFn.apply(plan, dropout_masks, input, *plan.params)
+
+
+class _VideoFrameFn(torch.autograd.Function):
+    """One frame of the video model; (cell, hide) carry the autograd chain from frame to frame."""
+
+    @staticmethod
+    def forward(ctx, plan: TrainPlan, masks, frame, cmap, hide_prev, cell_prev, *params):
+        with torch.cuda.device(plan.device):
+            plan.cmap.copy_(cmap.detach().float())
+            if hide_prev is not None:
+                plan.hp.copy_(hide_prev.detach().float().reshape(plan.hp.shape))
+                plan.cp.copy_(cell_prev.detach().float().reshape(plan.cp.shape))
+        plan.run_forward(frame.detach().float(), masks)
+        ctx.plan = plan
+        ctx.counter = plan.fwd_counter
+        ctx.recurrent = hide_prev is not None
+        return plan.heat.clone(), plan.cell.clone(), plan.hide.clone()
+
+    @staticmethod
+    def backward(ctx, dheat, dcell, dhide):
+        plan: TrainPlan = ctx.plan
+        if plan.fwd_counter != ctx.counter:
+            raise RuntimeError("unipose_b200: backward() after another forward() of the same frame slot - the training "
+                               "plan keeps one set of activations per frame index")
+        with torch.cuda.device(plan.device):
+            plan.dcell_ext.copy_(dcell.detach().float())
+            plan.dhide_ext.copy_(dhide.detach().float())
+        plan.run_backward(dheat.detach().float().contiguous())
+        grads = tuple(plan.pgrad[id(p)].clone() for p in plan.params)
+        rec = (plan.dhp.clone(), plan.dcp.clone()) if ctx.recurrent else (None, None)
+        return (None, None, None, None) + rec + grads
+
+
+def forward_train_video(model, input, centermap, it: int, prev_hide, prev_cell, dropout_masks=None):
+    """Train-mode forward of model/uniposeLSTM.unipose for frame `it` of the clip `input` [B,T,3,H,W]; the returned
+    (heat, cell, hide) carry grad_fns, so the reference's loop - five calls, summed MSE, one backward
+    (uniposeLSTM.py:116-132) - runs unchanged."""
+    b_, _t, _c, h, w = input.shape
+    first = (it == 0)
+    frozen_sig = tuple(m.training for m in model.modules() if isinstance(m, nn.BatchNorm2d))
+    key = ("train_video", b_, h, w, int(it), model._precision(), input.device.index, frozen_sig)
+    plan = model._plans.get(key)
+    if plan is None:
+        plan = build_video_frame_train_plan(model, b_, h, w, first, input.device, model._precision())
+        model._plans[key] = plan
+    hp = cp = None
+    if not first:
+        planes = model.lstm_0.conv_g_lstm.out_channels
+        hs, ws = h // 8, w // 8
+
+        def state(t, what):
+            if t.dim() == 3:
+                t = t.unsqueeze(0)
+            if tuple(t.shape) != (b_, planes, hs, ws):
+                raise ValueError("unipose_b200: %s must have shape %s (got %s)" % (what, (b_, planes, hs, ws), tuple(t.shape)))
+            return t
+        hp, cp = state(prev_hide, "previousHide"), state(prev_cell, "previousCell")
+    return _VideoFrameFn.apply(plan, dropout_masks, input[:, it], centermap[:, it], hp, cp, *plan.params)
 
 
 # ----------------------------------------------------------------------------------------------------
