@@ -243,6 +243,7 @@ def test_video_temporal_batching_matches_per_frame_path(monkeypatch):
     res = {}
     for flag in ("1", "0"):
         monkeypatch.setenv("UNIPOSE_B200_TEMPORAL_BATCH", flag)
+        m._plans.clear()
         heat = hide = cell = None
         outs = []
         for it in range(T):

@@ -222,9 +222,9 @@ class TrainPlan:
             if r["relu"]:
                 gated = self.tensor(tuple(dheat.shape), zero=False)
                 yout = r["nchw_out"]
-                self.bwd.append(lambda: torch.mul(dheat, (yout > 0).to(dheat.dtype), out=gated))
+                self.bwd.append(lambda src=dheat, yout=yout, gated=gated: torch.mul(src, (yout > 0).to(src.dtype), out=gated))
                 dheat = gated
-            self.bwd.append(lambda: ops.nchw_to_act(dheat, dz))
+            self.bwd.append(lambda src=dheat, dz=dz: ops.nchw_to_act(src, dz))
             if conv.bias is not None:
                 bsums = self.tensor((ops.bn_work_doubles(cout),), dtype=torch.float64)
                 gb = self.param_grad(conv.bias)
