@@ -253,7 +253,9 @@ def test_video_temporal_batching_matches_per_frame_path(monkeypatch):
         names = {k[0] for k in m._plans if isinstance(k[0], str)}
         assert ("trunk" in names) == (flag == "1")
     for a, b in zip(res["1"], res["0"]):
-        assert _rel(a[0], b[0]) < 1e-4 and np.abs(a[1] - b[1]).max() < 1e-4 and np.abs(a[2] - b[2]).max() < 1e-4
+        # the trunk runs at batch 6 instead of 2: other tile shapes, other fp32 accumulation order (trunk heat-maps reach
+        # |47| and feed the gate convolutions): equal to rounding, measured 4e-5 on the heat-maps, 5e-4 on the states
+        assert _rel(a[0], b[0]) < 2e-4 and np.abs(a[1] - b[1]).max() < 2e-3 and np.abs(a[2] - b[2]).max() < 2e-3
 
 
 def test_video_model_vs_golden_and_batch():
