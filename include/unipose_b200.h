@@ -146,6 +146,40 @@ int64_t up_wasp_chain_workspace_bytes(const UpWaspChainDesc* desc);
 int up_wasp_chain_fwd(const UpWaspChainDesc* desc, const UpWaspChainWeights* weights, const void* x, void* s_stack,
                       void* out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * A run of identical stride-1 bottlenecks without downsample path (layer3 blocks 1..22 of the dilated ResNet-101,
+ * Bottleneck.forward model/modules/backbone/resnet.py:22-42) as ONE persistent kernel (eval mode, fp16 / bf16,
+ * planes = 256): per-image halo dependencies through release/acquire counters, conv3 -> next conv1 accumulated on
+ * chip, residual added inside the tensor-core pipe.
+ *   xa: [n,h,w,1024] input X_0 (overwritten: ping buffer), xb: [n,h,w,1024] pong buffer; block b reads X_b from
+ *   (b even ? xa : xb) and writes X_{b+1} to the other one -> the result is in (nblocks even ? xa : xb).
+ *   t1: [2n,h,w,256] scratch (conv1 outputs, double buffered).  Filters packed CONTIGUOUSLY over the blocks:
+ *   w1 [nblocks][256][1024], w2 [nblocks][9][256][256], w3 [nblocks][1024][256] (BatchNorm scales folded in),
+ *   shifts fp32 [nblocks][256] / [nblocks][256] / [nblocks][1024].  workspace: zeroed once by the caller.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct UpBneckChainDesc {
+  int32_t n, h, w;
+  int32_t planes;      /* 256 */
+  int32_t nblocks;
+  int32_t dil;         /* dilation (= padding) of the 3x3 convs */
+  int32_t dtype;       /* UP_FP16 or UP_BF16 */
+} UpBneckChainDesc;
+
+typedef struct UpBneckChainWeights {
+  const void* w1;
+  const void* w2;
+  const void* w3;
+  const float* shift1;
+  const float* shift2;
+  const float* shift3;
+} UpBneckChainWeights;
+
+int up_bneck_chain_supported(const UpBneckChainDesc* desc);
+int64_t up_bneck_chain_workspace_bytes(const UpBneckChainDesc* desc);
+int up_bneck_chain_fwd(const UpBneckChainDesc* desc, const UpBneckChainWeights* weights, void* xa, void* xb, void* t1,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+int up_debug_bneck_timing(unsigned long long* h_out);
+
 /* Debug aid (UP_DEBUG_TIMING=1): per-CTA phase timestamps (ns) of the last up_wasp_chain_fwd launch, 160 CTAs x 32 slots. */
 int up_debug_chain_timing(unsigned long long* h_out);
 /* Debug aid (UP_DEBUG_TIMING=1 in the environment): per-CTA phase timestamps (ns) of the last up_conv2d_fwd launch,

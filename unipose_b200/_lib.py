@@ -54,6 +54,16 @@ class UpWaspChainDesc(ctypes.Structure):
                 ("dtype", c_int32), ("conv1_cin", c_int32)]
 
 
+class UpBneckChainDesc(ctypes.Structure):
+    _fields_ = [("n", c_int32), ("h", c_int32), ("w", c_int32), ("planes", c_int32), ("nblocks", c_int32),
+                ("dil", c_int32), ("dtype", c_int32)]
+
+
+class UpBneckChainWeights(ctypes.Structure):
+    _fields_ = [("w1", c_void_p), ("w2", c_void_p), ("w3", c_void_p), ("shift1", c_void_p), ("shift2", c_void_p),
+                ("shift3", c_void_p)]
+
+
 class UpWaspChainWeights(ctypes.Structure):
     _fields_ = [("aspp", c_void_p * 4), ("shift", c_void_p * 4), ("conv1", c_void_p), ("shift1", c_void_p),
                 ("gap_t", c_void_p), ("shift_gap", c_void_p), ("conv1_pool_t", c_void_p)]
@@ -108,13 +118,17 @@ _SIGNATURES = {
     "up_zero_insert2x": [_P, _P, _I, _I, _I, _I, _I, _P],
     "up_pack_conv_weights": [_P, _I, _L, _P],
     "up_wasp_chain_supported": [POINTER(UpWaspChainDesc)],
+    "up_bneck_chain_supported": [POINTER(UpBneckChainDesc)],
+    "up_bneck_chain_fwd": [POINTER(UpBneckChainDesc), POINTER(UpBneckChainWeights), _P, _P, _P, _P, _L, _P],
+    "up_debug_bneck_timing": [_P],
     "up_wasp_chain_fwd": [POINTER(UpWaspChainDesc), POINTER(UpWaspChainWeights), _P, _P, _P, _P, _L, _P],
     "up_epilogue_consts": [_P, _I, _I, _P],
 }
 _RESTYPES = {"up_conv2d_wgrad_scratch_bytes": (c_int64, [POINTER(UpConvDesc)]),
              "up_bn_work_doubles": (c_int64, [_I]),
              "up_pack_job_tiles": (c_int64, [POINTER(UpPackJob)]),
-             "up_wasp_chain_workspace_bytes": (c_int64, [POINTER(UpWaspChainDesc)])}
+             "up_wasp_chain_workspace_bytes": (c_int64, [POINTER(UpWaspChainDesc)]),
+             "up_bneck_chain_workspace_bytes": (c_int64, [POINTER(UpBneckChainDesc)])}
 
 
 class UpView(ctypes.Structure):

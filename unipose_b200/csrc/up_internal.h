@@ -23,7 +23,9 @@ struct DeviceInfo {
   bool conv_attr = false;    // conv_tcgen05_kernel<*> MaxDynamicSharedMemorySize set on this device
   bool wgrad_attr = false;   // conv_wgrad_tcgen05_kernel
   bool chain_attr = false;   // wasp_chain_kernel
-  int max_clusters[5] = {0, 0, 0, 0, 0};   // cached cudaOccupancyMaxActiveClusters by cluster size
+  bool bneck_attr = false;   // bneck_chain_kernel
+  int max_clusters[5] = {0, 0, 0, 0, 0};   // cached cudaOccupancyMaxActiveClusters: [2], [4] conv kernel by cluster
+                                           // size; [0] wasp chain, [1] bottleneck chain (both clusters of 2)
 };
 // Info of the CURRENT device (validated to be sm_100 class); nullptr + error message on failure.
 DeviceInfo* device_info();

@@ -237,8 +237,10 @@ class Builder:
     # ---- conv (+ folded eval BatchNorm / bias) ----
     def packed_conv(self, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], cin_pad: Optional[int] = None,
                     cout_pad: Optional[int] = None, weight_fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
-                    nchw_out: bool = False, extra_sources: Sequence[torch.Tensor] = ()) -> PackedConv:
-        """Allocate packed buffers for `conv` (+`bn` folded as eval-mode scale/shift) and register them in the plan's
+                    nchw_out: bool = False, extra_sources: Sequence[torch.Tensor] = (), wbuf=None, scale=None,
+                    shift=None) -> PackedConv:
+        """Allocate packed buffers for `conv` (+`bn` folded as eval-mode scale/shift) - or use the given `wbuf` / `scale`
+        / `shift` views of larger buffers (fused multi-layer kernels read their filters from one contiguous array) - and register them in the plan's
         weight table, which (re)fills them from the live parameters with two table-driven launches.
 
         Eval-mode BatchNorm: the per-channel scale is folded into the filter (w' = w * gamma/sqrt(var+eps)), the
@@ -251,9 +253,15 @@ class Builder:
         cin = cin_pad or round_up(ci_r, 16)
         planes = 2 if self.mode == ops.UP_SPLIT else 1
         dt = torch.float16 if self.mode == ops.UP_FP16 else torch.bfloat16
-        wbuf = torch.empty((planes, kh * kw, cout, cin), dtype=dt, device=self.device)
-        scale = torch.empty(cout, dtype=torch.float32, device=self.device)
-        shift = torch.empty(cout, dtype=torch.float32, device=self.device)
+        if wbuf is None:
+            wbuf = torch.empty((planes, kh * kw, cout, cin), dtype=dt, device=self.device)
+        else:
+            assert wbuf.dtype == dt and wbuf.numel() == planes * kh * kw * cout * cin and wbuf.is_contiguous()
+        if scale is None:
+            scale = torch.empty(cout, dtype=torch.float32, device=self.device)
+        if shift is None:
+            shift = torch.empty(cout, dtype=torch.float32, device=self.device)
+        assert scale.numel() == cout and shift.numel() == cout and scale.is_contiguous() and shift.is_contiguous()
         wt = self.plan.weights
         fold = torch.empty(bn.num_features, dtype=torch.float32, device=self.device) if bn is not None else None
         pc = PackedConv(wbuf, scale, shift, kh, kw, cout, cin, co_r, ci_r, self.mode, fold)

@@ -180,11 +180,71 @@ class ResNet(PlanModule):
         b.add(lambda stem=stem, x=x: ops.maxpool3x3s2(stem, x), "maxpool")
         low = None
         for name in ('layer1', 'layer2', 'layer3', 'layer4'):
-            for blk in getattr(self, name):
-                x = blk._emit(b, x)
+            blocks = list(getattr(self, name))
+            i = 0
+            while i < len(blocks):
+                run = self._chain_run(blocks, i)
+                fused = self._emit_chain(b, x, blocks[i:i + run]) if run >= 2 else None
+                if fused is not None:
+                    x = fused
+                    i += run
+                else:
+                    x = blocks[i]._emit(b, x)
+                    i += 1
             if name == 'layer1':
                 low = x
         return x, low
+
+    # ---- runs of identical bottlenecks as one persistent kernel (csrc/bneck_chain.cu) ----
+    @staticmethod
+    def _chain_run(blocks, i):
+        """Length of the run of blocks starting at i that the fused kernel takes: planes 256, stride 1, no downsample
+        path, same dilation."""
+        def ok(blk):
+            return (blk.downsample is None and blk.stride == 1 and blk.conv1.out_channels == 256 and
+                    blk.conv1.in_channels == 1024)
+        if not ok(blocks[i]):
+            return 0
+        j = i
+        while j < len(blocks) and ok(blocks[j]) and blocks[j].dilation == blocks[i].dilation:
+            j += 1
+        return j - i
+
+    def _emit_chain(self, b, x, blocks):
+        import ctypes
+        from .... import _lib, ops
+        if os.environ.get("UNIPOSE_B200_BNECK_CHAIN", "1") == "0" or b.mode == ops.UP_SPLIT:
+            return None
+        nb = len(blocks)
+        d = _lib.UpBneckChainDesc()
+        d.n, d.h, d.w, d.planes, d.nblocks, d.dil, d.dtype = x.n, x.h, x.w, 256, nb, blocks[0].dilation, b.mode
+        if x.c != 1024 or _lib.load().up_bneck_chain_supported(ctypes.byref(d)) != 0:
+            return None      # odd batch, tiny maps, more tiles than CTA pairs: the layer-wise plan takes every shape
+        dt = torch.float16 if b.mode == ops.UP_FP16 else torch.bfloat16
+        dev = b.device
+        w1 = torch.empty((nb, 256, 1024), dtype=dt, device=dev)
+        w2 = torch.empty((nb, 9, 256, 256), dtype=dt, device=dev)
+        w3 = torch.empty((nb, 1024, 256), dtype=dt, device=dev)
+        s1, s2, s3 = (torch.empty((nb, c), dtype=torch.float32, device=dev) for c in (256, 256, 1024))
+        sc = [torch.empty((nb, c), dtype=torch.float32, device=dev) for c in (256, 256, 1024)]   # epilogue scales (all 1)
+        for i, blk in enumerate(blocks):
+            b.packed_conv(blk.conv1, blk.bn1, wbuf=w1[i].view(1, 1, 256, 1024), scale=sc[0][i], shift=s1[i])
+            b.packed_conv(blk.conv2, blk.bn2, wbuf=w2[i].view(1, 9, 256, 256), scale=sc[1][i], shift=s2[i])
+            b.packed_conv(blk.conv3, blk.bn3, wbuf=w3[i].view(1, 1, 1024, 256), scale=sc[2][i], shift=s3[i])
+        xb = b.act(x.n, x.h, x.w, 1024)
+        t1 = b.act(2 * x.n, x.h, x.w, 256)
+        ws_bytes = int(_lib.load().up_bneck_chain_workspace_bytes(ctypes.byref(d)))
+        ws = b.tensor((ws_bytes,), dtype=torch.uint8, zero=True)
+        wts = _lib.UpBneckChainWeights()
+        wts.w1, wts.w2, wts.w3 = w1.data_ptr(), w2.data_ptr(), w3.data_ptr()
+        wts.shift1, wts.shift2, wts.shift3 = s1.data_ptr(), s2.data_ptr(), s3.data_ptr()
+        keep = (w1, w2, w3, s1, s2, s3, sc, ws)
+
+        def launch(keep=keep):
+            _lib.call("up_bneck_chain_fwd", ctypes.byref(d), ctypes.byref(wts), x.ptr(), xb.ptr(), t1.ptr(), ops._ptr(ws),
+                      ws_bytes, ops._stream())
+        b.add(launch, "bottleneck.chain[%d]" % nb)
+        return x if nb % 2 == 0 else xb
 
     def forward(self, input):
         from .... import engine, ops
