@@ -213,26 +213,46 @@ __global__ void __launch_bounds__(kBcThreads, 1)
         par ^= 1u;
       }
     };
-    // one k-block: optional 16 KB activation tile into the A half, `brows` filter rows (64 channels) into the B half
-    auto issue = [&](const CUtensorMap* amap, int ac, int aw, int ah, int an, const CUtensorMap* bmap, int bc, int brow,
-                     uint32_t brows) {
+    // one ring slot (32 KB): up to four TMA boxes under one barrier.  kind 0: activation tile (A half) + 128 filter
+    // rows (B half) - a regular k-block; kinds 1..3 are the merged B-only / residual slots of the fused phases.
+    auto acquire = [&](uint32_t bytes) -> uint32_t {
       mbar_wait(empty_bar(slot), par, 16000000000LL);
+      const uint32_t dst = smem_base + slot * kBcSlotBytes;
       if (elect_one()) {
-        const uint32_t dst = smem_base + slot * kBcSlotBytes;
-        const uint32_t bytes = (amap ? kBcABytes : 0u) + brows * 128u;
         if (crank == 0) mbar_arrive_expect_tx(full_bar(slot), 2u * bytes);
         else mbar_arrive_remote(full_bar(slot), 0u);
-        if (amap) tma_load_5d_2cta(amap, dst, full_bar(slot), ac, aw, 0, ah, an);
+      }
+      return dst;
+    };
+    auto issue = [&](const CUtensorMap* amap, int ac, int aw, int ah, int an, const CUtensorMap* bmap, int bc, int brow) {
+      const uint32_t dst = acquire(kBcSlotBytes);
+      if (elect_one()) {
+        tma_load_5d_2cta(amap, dst, full_bar(slot), ac, aw, 0, ah, an);
         tma_load_2d_2cta(bmap, dst + kBcABytes, full_bar(slot), bc, brow);
+      }
+      __syncwarp();
+      advance();
+    };
+    // two 128-row filter chunks (64 channels each) side by side: the B operands of two consecutive B-only k-steps
+    auto issue_b2 = [&](const CUtensorMap* bmap, int bc0, int brow) {
+      const uint32_t dst = acquire(kBcSlotBytes);
+      if (elect_one()) {
+        tma_load_2d_2cta(bmap, dst, full_bar(slot), bc0, brow);
+        tma_load_2d_2cta(bmap, dst + kBcABytes, full_bar(slot), bc0 + 64, brow);
       }
       __syncwarp();
       advance();
     };
     // P1: conv1 of the first block over X_0
     for (int chunk = 0; chunk < kBcC / 64; ++chunk)
-      issue(&tmXa, chunk * 64, w0, h0, n0, &tmW1, chunk * 64, static_cast<int>(crank) * 128, 128u);
+      issue(&tmXa, chunk * 64, w0, h0, n0, &tmW1, chunk * 64, static_cast<int>(crank) * 128);
     for (int b = 0; b < nb; ++b) {
-      // P2: halo of T1_b - every tile of this image group has stored it
+      // P2, centre tap first: its activation tile is this CTA's own t1 tile, still in the staging set T - only the
+      // filter chunks are loaded, and nothing here waits for the neighbours
+      const int wrow = (b * 9 + 4) * kBcP + static_cast<int>(crank) * 128;
+      issue_b2(&tmW2, 0, wrow);
+      issue_b2(&tmW2, 128, wrow);
+      // the other taps read halo tiles of T1_b: every tile of this image group has stored it
       if (lane == 0) bc_wait_counter(ctr + b, per);
       __syncwarp();
       bc_fence_async();
@@ -242,23 +262,33 @@ __global__ void __launch_bounds__(kBcThreads, 1)
       bc_taps(p.dil, w0, p.bw, p.W, kw_lo, kw_hi);
       const int tnn = n0 + (b & 1) * p.N;
       for (int kh = kh_lo; kh <= kh_hi; ++kh)
-        for (int kw = kw_lo; kw <= kw_hi; ++kw)
+        for (int kw = kw_lo; kw <= kw_hi; ++kw) {
+          if (kh == 1 && kw == 1) continue;
           for (int chunk = 0; chunk < kBcP / 64; ++chunk)
             issue(&tmT, chunk * 64, w0 + (kw - 1) * p.dil, h0 + (kh - 1) * p.dil, tnn, &tmW2, chunk * 64,
-                  (b * 9 + kh * 3 + kw) * kBcP + static_cast<int>(crank) * 128, 128u);
-      // P3: conv3 N-tiles (with the residual tile in the A half of the first two k-blocks) interleaved with the next
-      // block's conv1 slices, in exactly the order the MMA issuer consumes them
+                  (b * 9 + kh * 3 + kw) * kBcP + static_cast<int>(crank) * 128);
+        }
+      // P3: per conv3 N-tile one slot with its four 64-row filter chunks and one slot with the two residual chunks of
+      // X_b; per next-conv1 slice one slot with its two filter chunks - in the order the MMA issuer consumes them
       const CUtensorMap* xmap = (b & 1) ? &tmXb : &tmXa;
       const bool next = b + 1 < nb;
       auto c3 = [&](int j) {
-        for (int c = 0; c < 4; ++c)
-          issue(c < 2 ? xmap : nullptr, j * 128 + c * 64, w0, h0, n0, &tmW3, c * 64,
-                b * kBcC + j * 128 + static_cast<int>(crank) * 64, 64u);
+        uint32_t dst = acquire(kBcSlotBytes);
+        if (elect_one()) {
+          const int brow = b * kBcC + j * 128 + static_cast<int>(crank) * 64;
+          for (int c = 0; c < 4; ++c) tma_load_2d_2cta(&tmW3, dst + c * 8192u, full_bar(slot), c * 64, brow);
+        }
+        __syncwarp();
+        advance();
+        dst = acquire(kBcSlotBytes);
+        if (elect_one()) {
+          for (int c = 0; c < 2; ++c)
+            tma_load_5d_2cta(xmap, dst + c * kBcABytes, full_bar(slot), j * 128 + c * 64, w0, 0, h0, n0);
+        }
+        __syncwarp();
+        advance();
       };
-      auto g2 = [&](int j) {
-        for (int c = 0; c < 2; ++c)
-          issue(nullptr, 0, 0, 0, 0, &tmW1, j * 128 + c * 64, (b + 1) * kBcP + static_cast<int>(crank) * 128, 128u);
-      };
+      auto g2 = [&](int j) { issue_b2(&tmW1, j * 128, (b + 1) * kBcP + static_cast<int>(crank) * 128); };
       c3(0);
       for (int j = 1; j < kBcNT; ++j) {
         c3(j);
@@ -308,14 +338,39 @@ __global__ void __launch_bounds__(kBcThreads, 1)
       advance();
     }
     for (int b = 0; b < nb; ++b) {
-      // ---- P2: conv2 ----
+      // ---- P2: conv2 (centre tap from the staged t1 tile, then the halo taps) ----
       int kh_lo, kh_hi, kw_lo, kw_hi;
       bc_taps(p.dil, h0, p.bh, p.H, kh_lo, kh_hi);
       bc_taps(p.dil, w0, p.bw, p.W, kw_lo, kw_hi);
-      const int nkb = (kh_hi - kh_lo + 1) * (kw_hi - kw_lo + 1) * (kBcP / 64);
+      const int nkb = ((kh_hi - kh_lo + 1) * (kw_hi - kw_lo + 1) - 1) * (kBcP / 64);
       wait_acc(0);
       wait_acc(1);
       tcgen05_after_thread_sync();
+      for (int s2 = 0; s2 < 2; ++s2) {
+        mbar_wait(s2readyT(2 * s2), 0u);           // t1 chunks (T use 2b: even parity) staged in both CTAs
+        mbar_wait(s2readyT(2 * s2 + 1), 0u);
+        mbar_wait(full_bar(slot), phase);
+        tcgen05_after_thread_sync();
+        if (elect_one()) {
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = 2 * s2 + cc;
+            const uint64_t ad = tdesc0 + static_cast<uint64_t>((kBcBuf >> 4) * c);
+            const uint64_t bd = adesc0 + static_cast<uint64_t>(slot_step * slot) + static_cast<uint64_t>((kBcABytes >> 4) * cc);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_2cta(tmem_base, ad + 2u * k, bd + 2u * k, p.idesc256, (c | k) ? 1u : 0u);
+          }
+          umma_commit_2cta_mc(empty_bar(slot), 3);
+          if (s2 == 1) {
+            for (int g = 0; g < 4; ++g) umma_commit_2cta_mc(availT(g), 3);       // t1 tile consumed
+            if (nkb == 0) {
+              umma_commit_2cta_mc(tfull_bar(0), 3);
+              umma_commit_2cta_mc(tfull_bar(1), 3);
+            }
+          }
+        }
+        __syncwarp();
+        advance();
+      }
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(full_bar(slot), phase);
         tcgen05_after_thread_sync();
@@ -323,7 +378,7 @@ __global__ void __launch_bounds__(kBcThreads, 1)
           const uint64_t ad = adesc0 + static_cast<uint64_t>(slot_step * slot);
           const uint64_t bd = bdesc0 + static_cast<uint64_t>(slot_step * slot);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_2cta(tmem_base, ad + 2u * k, bd + 2u * k, p.idesc256, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_f16_2cta(tmem_base, ad + 2u * k, bd + 2u * k, p.idesc256, 1u);
           umma_commit_2cta_mc(empty_bar(slot), 3);
           if (kb == nkb - 1) {
             umma_commit_2cta_mc(tfull_bar(0), 3);
@@ -341,54 +396,64 @@ __global__ void __launch_bounds__(kBcThreads, 1)
         wait_acc(h);
         tcgen05_after_thread_sync();
         const uint32_t tacc = tmem_base + static_cast<uint32_t>(h) * 128u;
-        for (int c = 0; c < 4; ++c) {
-          if (j == 0) mbar_wait(s2readyT(c), b & 1u);       // t2 chunk c is in the staging set (both CTAs)
-          mbar_wait(full_bar(slot), phase);
-          tcgen05_after_thread_sync();
-          if (elect_one()) {
+        if (j == 0)
+          for (int c = 0; c < 4; ++c) mbar_wait(s2readyT(c), 1u);     // t2 (T use 2b+1: odd parity) staged in both CTAs
+        // slot 1: the four 64-row filter chunks of this N-tile; A = the staged t2 tile
+        mbar_wait(full_bar(slot), phase);
+        tcgen05_after_thread_sync();
+        if (elect_one()) {
+          for (int c = 0; c < 4; ++c) {
             const uint64_t ad = tdesc0 + static_cast<uint64_t>((kBcBuf >> 4) * c);
-            const uint64_t bd = bdesc0 + static_cast<uint64_t>(slot_step * slot);
+            const uint64_t bd = adesc0 + static_cast<uint64_t>(slot_step * slot) + static_cast<uint64_t>((8192u >> 4) * c);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16_2cta(tacc, ad + 2u * k, bd + 2u * k, p.idesc128, (c | k) ? 1u : 0u);
-            if (c < 2) {
-              // residual: D[:, c*64 .. c*64+63] += X_b tile x I   (exact: products with 1.0)
-              const uint64_t rd = adesc0 + static_cast<uint64_t>(slot_step * slot);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16_2cta(tacc + static_cast<uint32_t>(c) * 64u, rd + 2u * k, identdesc + 2u * k, p.idesc_res, 1u);
-            }
-            umma_commit_2cta_mc(empty_bar(slot), 3);
-            if (c == 3) {
-              umma_commit_2cta_mc(tfull_bar(h), 3);
-              if (j == kBcNT - 1)
-                for (int g = 0; g < 4; ++g) umma_commit_2cta_mc(availT(g), 3);     // t2 is dead
-            }
           }
-          __syncwarp();
-          advance();
+          umma_commit_2cta_mc(empty_bar(slot), 3);
         }
+        __syncwarp();
+        advance();
+        // slot 2: residual  D[:, c*64 .. c*64+63] += X_b tile chunk x I   (exact: products with 1.0)
+        mbar_wait(full_bar(slot), phase);
+        tcgen05_after_thread_sync();
+        if (elect_one()) {
+          for (int c = 0; c < 2; ++c) {
+            const uint64_t rd = adesc0 + static_cast<uint64_t>(slot_step * slot) + static_cast<uint64_t>((kBcABytes >> 4) * c);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_2cta(tacc + static_cast<uint32_t>(c) * 64u, rd + 2u * k, identdesc + 2u * k, p.idesc_res, 1u);
+          }
+          umma_commit_2cta_mc(empty_bar(slot), 3);
+          umma_commit_2cta_mc(tfull_bar(h), 3);
+          if (j == kBcNT - 1)
+            for (int g = 0; g < 4; ++g) umma_commit_2cta_mc(availT(g), 3);     // t2 is dead
+        }
+        __syncwarp();
+        advance();
       };
       auto g2 = [&](int j) {
         if (j == 0) {
           mbar_wait(d2empty_bar, (b & 1u) ^ 1u);
           tcgen05_after_thread_sync();
         }
+        mbar_wait(full_bar(slot), phase);
         for (int c = 0; c < 2; ++c) {
+          // chunk by chunk: the epilogue of the next N-tile may refill a staging buffer as soon as ITS MMAs are done
           mbar_wait(s2readyO(c), j & 1u);
-          mbar_wait(full_bar(slot), phase);
           tcgen05_after_thread_sync();
           if (elect_one()) {
             const uint64_t ad = odesc0 + static_cast<uint64_t>((kBcBuf >> 4) * c);
-            const uint64_t bd = bdesc0 + static_cast<uint64_t>(slot_step * slot);
+            const uint64_t bd = adesc0 + static_cast<uint64_t>(slot_step * slot) + static_cast<uint64_t>((kBcABytes >> 4) * c);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16_2cta(tmem_d2, ad + 2u * k, bd + 2u * k, p.idesc256, (j | c | k) ? 1u : 0u);
-            umma_commit_2cta_mc(empty_bar(slot), 3);
             umma_commit_2cta_mc(availO(c), 3);
-            if (j == kBcNT - 1 && c == 1) umma_commit_2cta_mc(d2full_bar, 3);
+            if (c == 1) {
+              umma_commit_2cta_mc(empty_bar(slot), 3);
+              if (j == kBcNT - 1) umma_commit_2cta_mc(d2full_bar, 3);
+            }
           }
           __syncwarp();
-          advance();
         }
+        advance();
       };
       c3(0);
       for (int j = 1; j < kBcNT; ++j) {
@@ -408,10 +473,7 @@ __global__ void __launch_bounds__(kBcThreads, 1)
       tma_store_commit();
     }
     tma_store_wait_read<0>();
-    for (int g = 0; g < 4; ++g) {
-      mbar_arrive(availT(g));
-      mbar_arrive(availT(g));
-    }
+    for (int g = 0; g < 4; ++g) mbar_arrive(availT(g));      // the second arrival: centre-tap MMAs of the next conv2
     tma_store_wait_all<0>();
     bc_fence_async();
     __threadfence();
@@ -446,10 +508,7 @@ __global__ void __launch_bounds__(kBcThreads, 1)
           tma_store_commit();
         }
         tma_store_wait_read<0>();
-        for (int g = 0; g < 4; ++g) {
-          mbar_arrive(availT(g));
-          mbar_arrive(availT(g));
-        }
+        for (int g = 0; g < 4; ++g) mbar_arrive(availT(g));
         tma_store_wait_all<0>();       // X_{b+1} and T1_{b+1} of this tile are in global memory
         bc_fence_async();
         __threadfence();
@@ -530,7 +589,7 @@ __global__ void __launch_bounds__(kBcThreads, 1)
     wait_full(0);
     wait_full(1);
     tcgen05_after_thread_sync();
-    epilogue(tmem_base, 4, p.shift1, false, false);
+    epilogue(tmem_base, 4, p.shift1, false, true);
     tcgen05_before_thread_sync();
     __syncwarp();
     release(0);
@@ -562,7 +621,7 @@ __global__ void __launch_bounds__(kBcThreads, 1)
         // ---- T1_{b+1} = ReLU(bn1(conv1(X_{b+1}))) from the second accumulator ----
         mbar_wait(d2full_bar, b & 1u);
         tcgen05_after_thread_sync();
-        epilogue(tmem_d2, 4, p.shift1 + (b + 1) * kBcP, false, false);
+        epilogue(tmem_d2, 4, p.shift1 + (b + 1) * kBcP, false, true);
         tcgen05_before_thread_sync();
         __syncwarp();
         if (lane == 0) {
