@@ -41,6 +41,7 @@ static int encode_map(CUtensorMap* m, int fmt, int rank, const void* base, const
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
   CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 0  ? CU_TENSOR_MAP_SWIZZLE_NONE
                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = fn(m, fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                   static_cast<cuuint32_t>(rank), const_cast<void*>(base), d, s, b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

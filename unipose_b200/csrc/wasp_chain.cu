@@ -62,6 +62,8 @@ struct WcParams {
   int pairs_per_wave, waves;
   int slots;
   int c_per;                  // pooling-branch output channels computed per tile (power of two >= 8)
+  int l2_prefetch;            // 1: bulk L2 prefetch of the tile's x rows before aspp1's k-loop
+  int gap_smem;               // 1: the pooling sums read aspp1's activation tiles from the TMA ring (no second pass over x)
   uint32_t idesc;
   WcStage st[4];
   const uint16_t* x;
@@ -121,6 +123,20 @@ __device__ __forceinline__ void wc_taps(int taps, int dil, int x0, int ext, int 
   }
 }
 
+// ring k-blocks one tile consumes per wave: per stage the in-bounds taps x channel chunks + 4 second-GEMM chunks
+__device__ __forceinline__ int wc_wave_kblocks(const WcParams& p, const WcTile& t) {
+  int total = 0;
+  for (int s = 0; s < 4; ++s) {
+    int kh_lo, kh_hi, kw_lo, kw_hi;
+    wc_taps(p.st[s].taps, p.st[s].dil, t.h0, p.bh, p.H, kh_lo, kh_hi);
+    wc_taps(p.st[s].taps, p.st[s].dil, t.w0, p.bw, p.W, kw_lo, kw_hi);
+    const int ntaps = (kh_hi - kh_lo + 1) * (kw_hi - kw_lo + 1);
+    // stage 0: one slot per chunk; later stages: the centre tap takes two merged slots; second GEMM: two merged slots
+    total += (s == 0 ? ntaps * p.st[s].chunks : (ntaps - 1) * p.st[s].chunks + 2) + 2;
+  }
+  return total;
+}
+
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -168,7 +184,7 @@ __global__ void __launch_bounds__(kWcThreads, 1)
                       const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmB0,
                       const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
                       const __grid_constant__ CUtensorMap tmB3, const __grid_constant__ CUtensorMap tmBc,
-                      const WcParams p) {
+                      const __grid_constant__ CUtensorMap tmXp, const WcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -190,7 +206,8 @@ __global__ void __launch_bounds__(kWcThreads, 1)
   auto avail_bar = [&](int g) { return tfull_bar + 32u + 8u * g; };
   auto ready_bar = [&](int g) { return tfull_bar + 32u + 8u * (kWcGroups + g); };
   auto s2ready_bar = [&](int g) { return tfull_bar + 32u + 8u * (2 * kWcGroups + g); };
-  const uint32_t tmem_slot = tfull_bar + 32u + 8u * (3 * kWcGroups);
+  auto gapdone_bar = [&](int sl) { return tfull_bar + 32u + 8u * (3 * kWcGroups + sl); };
+  const uint32_t tmem_slot = tfull_bar + 32u + 8u * (3 * kWcGroups + kWcMaxSlots);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5;
@@ -219,6 +236,7 @@ __global__ void __launch_bounds__(kWcThreads, 1)
       mbar_init(ready_bar(g), kWcEpiThreads / 32);              // local epilogue warps -> store thread
       mbar_init(s2ready_bar(g), 2 * (kWcEpiThreads / 32));      // epilogue warps of BOTH CTAs -> MMA issuer
     }
+    for (int sl = 0; sl < p.slots; ++sl) mbar_init(gapdone_bar(sl), kWcEpiThreads / 32);   // pooling warps -> producer
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2cta(tmem_slot, 512);
@@ -236,6 +254,22 @@ __global__ void __launch_bounds__(kWcThreads, 1)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    if (p.l2_prefetch && lane == 0) {
+      // Pull this CTA's whole aspp1 tile (128 pixels x cin channels) towards L2 in 512-byte rows before the k-loop
+      // starts reading it in 128-byte rows: when x comes from DRAM, 64-channel boxes 4 KB apart open a DRAM page per
+      // pixel and k-block; the prefetch touches every page once with 4x longer bursts, and all requests are in flight
+      // at the same time.
+      const WcTile t0 = wc_tile(p, 0, cluster_id, crank);
+      if (t0.active) {
+        for (int c = 0; c < p.cin; c += 256) {
+          asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tmXp)),
+                       "r"(c), "r"(t0.w0), "r"(0), "r"(t0.h0), "r"(t0.n0)
+                       : "memory");
+        }
+      }
+    }
+    __syncwarp();
     uint32_t slot = 0, par = 1;
     auto advance = [&]() {
       if (++slot == static_cast<uint32_t>(p.slots)) {
@@ -243,31 +277,62 @@ __global__ void __launch_bounds__(kWcThreads, 1)
         par ^= 1u;
       }
     };
+    uint32_t nwave = 0;
+    const int chunks0 = p.st[0].chunks;
     for (int wave = 0; wave < p.waves; ++wave) {
       const WcTile t = wc_tile(p, wave, cluster_id, crank);
       if (!t.active) continue;
+      int kbw = 0;      // k-block index within this wave
+      // a slot last filled by an aspp1 k-block is also read by the pooling warps: wait for them before refilling it
+      auto wait_slot = [&]() {
+        mbar_wait(empty_bar(slot), par, 16000000000LL);
+        if (p.gap_smem && kbw >= p.slots && kbw < chunks0 + p.slots) {
+          const uint32_t use = nwave * static_cast<uint32_t>(chunks0 / p.slots) + static_cast<uint32_t>((kbw - p.slots) / p.slots);
+          mbar_wait(gapdone_bar(slot), use & 1u, 16000000000LL);
+        }
+        ++kbw;
+      };
       for (int s = 0; s < 4; ++s) {
         const WcStage st = p.st[s];
-        if (s > 0) {
-          // every tile of this image group has stored x_s (the halo source) to global memory
-          if (lane == 0) wc_wait_counter(p.counters + t.tn * kWcCtrStride + (s - 1), per);
-          __syncwarp();
-          fence_proxy_async_all();
-        }
-        if (wave == 0 && lane == 0) WC_STAMP(4 + 6 * s);      // dependencies of stage s satisfied
         int kh_lo, kh_hi, kw_lo, kw_hi;
         wc_taps(st.taps, st.dil, t.h0, p.bh, p.H, kh_lo, kh_hi);
         wc_taps(st.taps, st.dil, t.w0, p.bw, p.W, kw_lo, kw_hi);
         const CUtensorMap* amap = s == 0 ? &tmX : &tmS;
         const CUtensorMap* bmap = s == 0 ? &tmB0 : (s == 1 ? &tmB1 : (s == 2 ? &tmB2 : &tmB3));
         const int an = s == 0 ? t.n0 : t.n0 + (s - 1) * p.N;
+        // two 128-row filter chunks (64 channels each) in one slot: the B operands of two B-only k-steps
+        auto issue_b2 = [&](const CUtensorMap* m, int c0, int row) {
+          wait_slot();
+          if (elect_one()) {
+            const uint32_t dst = smem_base + slot * kWcSlotBytes;
+            if (crank == 0) mbar_arrive_expect_tx(full_bar(slot), 2u * kWcSlotBytes);
+            else mbar_arrive_remote(full_bar(slot), 0u);
+            tma_load_2d_2cta(m, dst, full_bar(slot), c0, row);
+            tma_load_2d_2cta(m, dst + kWcABytes, full_bar(slot), c0 + 64, row);
+          }
+          __syncwarp();
+          advance();
+        };
+        if (s > 0) {
+          // centre tap first: its activation tile is this CTA's own x_s tile, still in the staging buffers - filter
+          // chunks only, and nothing here waits for the neighbours
+          const int crow = 4 * kWcCout + static_cast<int>(crank) * (kWcCout / 2);
+          issue_b2(bmap, 0, crow);
+          issue_b2(bmap, 128, crow);
+          // the other taps: every tile of this image group has stored x_s (the halo source) to global memory
+          if (lane == 0) wc_wait_counter(p.counters + t.tn * kWcCtrStride + (s - 1), per);
+          __syncwarp();
+          fence_proxy_async_all();
+        }
+        if (wave == 0 && lane == 0) WC_STAMP(4 + 6 * s);      // dependencies of stage s satisfied
         for (int kh = kh_lo; kh <= kh_hi; ++kh) {
           const int oh = st.taps == 1 ? 0 : (kh - 1) * st.dil;
           for (int kw = kw_lo; kw <= kw_hi; ++kw) {
+            if (s > 0 && kh == 1 && kw == 1) continue;
             const int ow = st.taps == 1 ? 0 : (kw - 1) * st.dil;
             const int brow = (st.taps == 1 ? 0 : (kh * 3 + kw)) * kWcCout + static_cast<int>(crank) * (kWcCout / 2);
             for (int chunk = 0; chunk < st.chunks; ++chunk) {
-              mbar_wait(empty_bar(slot), par, 16000000000LL);
+              wait_slot();
               if (elect_one()) {
                 const uint32_t dst = smem_base + slot * kWcSlotBytes;
                 if (crank == 0) mbar_arrive_expect_tx(full_bar(slot), 2u * kWcSlotBytes);
@@ -280,20 +345,11 @@ __global__ void __launch_bounds__(kWcThreads, 1)
             }
           }
         }
-        // conv1' K-split group s: four 64-channel filter chunks for the second GEMM (B operand only)
-        for (int g = 0; g < kWcGroups; ++g) {
-          mbar_wait(empty_bar(slot), par, 16000000000LL);
-          if (elect_one()) {
-            const uint32_t dst = smem_base + slot * kWcSlotBytes;
-            if (crank == 0) mbar_arrive_expect_tx(full_bar(slot), 2u * kWcBBytes);
-            else mbar_arrive_remote(full_bar(slot), 0u);
-            tma_load_2d_2cta(&tmBc, dst + kWcABytes, full_bar(slot), s * kWcCout + g * 64,
-                             static_cast<int>(crank) * (kWcCout / 2));
-          }
-          __syncwarp();
-          advance();
-        }
+        // conv1' K-split group s: four 64-channel filter chunks for the second GEMM (B operand only), two per slot
+        issue_b2(&tmBc, s * kWcCout, static_cast<int>(crank) * (kWcCout / 2));
+        issue_b2(&tmBc, s * kWcCout + 128, static_cast<int>(crank) * (kWcCout / 2));
       }
+      ++nwave;
     }
   } else if (warp == 1 && crank == 0) {
     // ===================== MMA issuer (leader CTA) =====================
@@ -318,9 +374,34 @@ __global__ void __launch_bounds__(kWcThreads, 1)
         int kh_lo, kh_hi, kw_lo, kw_hi;
         wc_taps(st.taps, st.dil, t.h0, p.bh, p.H, kh_lo, kh_hi);
         wc_taps(st.taps, st.dil, t.w0, p.bw, p.W, kw_lo, kw_hi);
-        const int nkb = (kh_hi - kh_lo + 1) * (kw_hi - kw_lo + 1) * st.chunks;
+        const int ntaps = (kh_hi - kh_lo + 1) * (kw_hi - kw_lo + 1);
+        const int nkb = (s == 0 ? ntaps : ntaps - 1) * st.chunks;
         mbar_wait(tempty_bar, (nst & 1u) ^ 1u);     // the epilogue of the previous stage has drained the accumulator
         tcgen05_after_thread_sync();
+        if (s > 0) {
+          // centre tap: A = this CTA's x_s tile in the staging buffers (their s2ready phases were awaited by the second
+          // GEMM of the previous stage), B = two filter chunks per slot
+          for (int s2 = 0; s2 < 2; ++s2) {
+            mbar_wait(full_bar(slot), phase);
+            tcgen05_after_thread_sync();
+            if (elect_one()) {
+              for (int cc = 0; cc < 2; ++cc) {
+                const int c = 2 * s2 + cc;
+                const uint64_t ad = sdesc0 + static_cast<uint64_t>((kWcBuf >> 4) * c);
+                const uint64_t bd = adesc0 + static_cast<uint64_t>(slot_step * slot) + static_cast<uint64_t>((kWcABytes >> 4) * cc);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16_2cta(tmem_acc, ad + 2u * k, bd + 2u * k, p.idesc, (c | k) ? 1u : 0u);
+              }
+              umma_commit_2cta_mc(empty_bar(slot), 3);
+              if (s2 == 1) {
+                for (int g = 0; g < kWcGroups; ++g) umma_commit_2cta_mc(avail_bar(g), 3);   // x_s tile consumed
+                if (nkb == 0) umma_commit_2cta_mc(tfull_bar, 3);
+              }
+            }
+            __syncwarp();
+            advance();
+          }
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(slot), phase);
           tcgen05_after_thread_sync();
@@ -328,7 +409,8 @@ __global__ void __launch_bounds__(kWcThreads, 1)
             const uint64_t ad = adesc0 + static_cast<uint64_t>(slot_step * slot);
             const uint64_t bd = bdesc0 + static_cast<uint64_t>(slot_step * slot);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16_2cta(tmem_acc, ad + 2u * k, bd + 2u * k, p.idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_f16_2cta(tmem_acc, ad + 2u * k, bd + 2u * k, p.idesc, (s > 0 || (kb | k)) ? 1u : 0u);
             umma_commit_2cta_mc(empty_bar(slot), 3);
             if (kb == nkb - 1) {
               umma_commit_2cta_mc(tfull_bar, 3);
@@ -338,27 +420,33 @@ __global__ void __launch_bounds__(kWcThreads, 1)
           __syncwarp();
           advance();
         }
-        // second GEMM: D2 += x_s (the staging buffers the epilogue is filling) x W1'_s
+        // second GEMM: D2 += x_s (the staging buffers the epilogue is filling) x W1'_s, two filter chunks per slot
         if (s == 0) {
           mbar_wait(d2empty_bar, (nwave & 1u) ^ 1u);
           tcgen05_after_thread_sync();
         }
-        for (int g = 0; g < kWcGroups; ++g) {
-          mbar_wait(s2ready_bar(g), nst & 1u);
+        for (int s2 = 0; s2 < 2; ++s2) {
           mbar_wait(full_bar(slot), phase);
-          tcgen05_after_thread_sync();
-          if (elect_one()) {
-            const uint64_t ad = sdesc0 + static_cast<uint64_t>((kWcBuf >> 4) * g);
-            const uint64_t bd = bdesc0 + static_cast<uint64_t>(slot_step * slot);
+          for (int cc = 0; cc < 2; ++cc) {
+            const int g = 2 * s2 + cc;
+            mbar_wait(s2ready_bar(g), nst & 1u);
+            tcgen05_after_thread_sync();
+            if (elect_one()) {
+              const uint64_t ad = sdesc0 + static_cast<uint64_t>((kWcBuf >> 4) * g);
+              const uint64_t bd = adesc0 + static_cast<uint64_t>(slot_step * slot) + static_cast<uint64_t>((kWcABytes >> 4) * cc);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_2cta(tmem_d2, ad + 2u * k, bd + 2u * k, p.idesc, (s | g | k) ? 1u : 0u);
-            umma_commit_2cta_mc(empty_bar(slot), 3);
-            umma_commit_2cta_mc(avail_bar(g), 3);
-            if (s == 3 && g == kWcGroups - 1) umma_commit_2cta_mc(d2full_bar, 3);
-            if (wave == 0 && g == kWcGroups - 1) WC_STAMP(9 + 6 * s);   // second GEMM of stage s issued
+              for (int k = 0; k < 4; ++k)
+                umma_f16_2cta(tmem_d2, ad + 2u * k, bd + 2u * k, p.idesc, (s | g | k) ? 1u : 0u);
+              // the staging buffer is released by the centre tap of the next stage; after the last stage, here
+              if (s == 3) umma_commit_2cta_mc(avail_bar(g), 3);
+              if (cc == 1) {
+                umma_commit_2cta_mc(empty_bar(slot), 3);
+                if (s == 3 && g == kWcGroups - 1) umma_commit_2cta_mc(d2full_bar, 3);
+                if (wave == 0 && g == kWcGroups - 1) WC_STAMP(9 + 6 * s);   // second GEMM of stage s issued
+              }
+            }
+            __syncwarp();
           }
-          __syncwarp();
           advance();
         }
         ++nst;
@@ -412,6 +500,7 @@ __global__ void __launch_bounds__(kWcThreads, 1)
     const int rpi = p.bh * p.bw;               // tile rows per image
     const int wpi = rpi / 16;                  // epilogue warps (16 rows each) per image
     uint32_t nuse = 0, nst = 0, nwave = 0;
+    uint32_t kbase = 0;       // ring k-blocks of the previous waves (the pooling sums follow aspp1's slots)
 
     // one 128 x 256 accumulator -> ReLU(acc + shift) -> 16-bit -> staging buffers.  `sh` points at this thread's row of
     // shifts (column 0); second = also hand the buffers to the MMA issuer as the A operand of the second GEMM.
@@ -465,7 +554,42 @@ __global__ void __launch_bounds__(kWcThreads, 1)
       // ---- pooling branch, part 1: channel sums of this tile's pixels (nn.AdaptiveAvgPool2d, wasp.py:51) ----
       // The partial-sum scratch aliases the staging buffers: they must be drained (previous wave's output stores).
       for (int g = 0; g < kWcGroups; ++g) mbar_wait(avail_bar(g), (nuse & 1u) ^ 1u);
-      {
+      if (p.gap_smem) {
+        // aspp1's activation tiles pass through the TMA ring: once the MMAs of a k-block have consumed a slot (its
+        // `empty` barrier completes, in both CTAs of the pair) and before the producer refills it (it waits for
+        // `gapdone`), the eight epilogue warps add up their 16 rows of the 128 x 64 tile straight from shared memory.
+        const int c = lane & 7;                    // logical 16-byte chunk = 8 channels
+        const int rsub = lane >> 3;                // rows rsub, rsub + 4, rsub + 8, rsub + 12 of this warp's 16
+        for (int kb = 0; kb < p.st[0].chunks; ++kb) {
+          const uint32_t g = kbase + static_cast<uint32_t>(kb);
+          const uint32_t sl = g % static_cast<uint32_t>(p.slots), use = g / static_cast<uint32_t>(p.slots);
+          mbar_wait(empty_bar(sl), use & 1u, 16000000000LL);
+          const uint32_t tile = smem_base + sl * kWcSlotBytes;
+          float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t r = static_cast<uint32_t>(ew * 16 + rsub + 4 * i);
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(tile + r * 128u + ((static_cast<uint32_t>(c) ^ (r & 7u)) << 4)));
+            wc_add8<kFmt>(v, a);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            a[e] += __shfl_xor_sync(0xffffffffu, a[e], 8);
+            a[e] += __shfl_xor_sync(0xffffffffu, a[e], 16);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(gapdone_bar(sl));           // this warp is done with the slot
+          if (rsub == 0) {
+            float4* dst = reinterpret_cast<float4*>(s_red + ew * p.cin + kb * 64 + c * 8);
+            dst[0] = make_float4(a[0], a[1], a[2], a[3]);
+            dst[1] = make_float4(a[4], a[5], a[6], a[7]);
+          }
+        }
+        kbase += static_cast<uint32_t>(wc_wave_kblocks(p, t));
+      } else {
         const int nl = (ew * 16) / rpi;            // image of this warp's 16 rows
         const int n = t.n0 + nl;
         const int rem0 = ew * 16 - nl * rpi;
@@ -492,6 +616,8 @@ __global__ void __launch_bounds__(kWcThreads, 1)
           dst[0] = make_float4(a[0], a[1], a[2], a[3]);
           dst[1] = make_float4(a[4], a[5], a[6], a[7]);
         }
+      }
+      {
         named_bar_sync(1, kWcEpiThreads);
         for (int idx = etid; idx < p.bn * p.cin; idx += kWcEpiThreads) {
           const int img = idx / p.cin, ch = idx - img * p.cin;
@@ -518,8 +644,8 @@ __global__ void __launch_bounds__(kWcThreads, 1)
         if (wave == 0 && etid == 0) WC_STAMP(7 + 6 * s);       // epilogue of stage s done
         ++nst;
 
-        if (s == 0) {
-          // ---- pooling branch, part 2: mean over the whole image, then this tile's slice of the 1x1 conv
+        if (s == 1) {
+          // ---- pooling branch, part 2 (after the stage-1 epilogue: it then runs in the shadow of aspp3's k-loop): mean over the whole image, then this tile's slice of the 1x1 conv
           // (global_avg_pool[1..3], wasp.py:51-54).  All tiles of the image group have published their sums once
           // the group's stage-0 counter is complete (the store thread increments it after the sums were fenced).
           if (etid == 0) wc_wait_counter(ctr + 0, per);
@@ -612,8 +738,8 @@ __global__ void __launch_bounds__(kWcThreads, 1)
           if (etid == 0) red_release_gpu_add(ctr + 4, 1u);
           if (wave == 0 && etid == 0) WC_STAMP(28);
         }
-        if (s == 1) {
-          // ---- pooling branch, part 3: bias_img = W1'_5 . g2 + bn1 shift (the broadcast branch through conv1) ----
+        if (s == 2) {
+          // ---- pooling branch, part 3 (in the shadow of aspp4's k-loop): bias_img = W1'_5 . g2 + bn1 shift (the broadcast branch through conv1) ----
           if (etid == 0) wc_wait_counter(ctr + 4, per);
           named_bar_sync(1, kWcEpiThreads);
           for (int idx = etid; idx < p.bn * kWcCout; idx += kWcEpiThreads) {
@@ -850,7 +976,7 @@ extern "C" int up_wasp_chain_fwd(const UpWaspChainDesc* d, const UpWaspChainWeig
   if (p.pairs_per_wave > pairs) p.pairs_per_wave = pairs;
   p.waves = (pairs + p.pairs_per_wave - 1) / p.pairs_per_wave;
   const size_t pool_bytes = (2u * kWcMaxCin + 2u * kWcCout + 2u * kWcCout + 8u * kWcCout) * 4u;
-  const size_t fixed = 1024 + kWcGroups * kWcBuf + pool_bytes + 8 * (2 * kWcMaxSlots + 4 + 3 * kWcGroups) + 16;
+  const size_t fixed = 1024 + kWcGroups * kWcBuf + pool_bytes + 8 * (3 * kWcMaxSlots + 4 + 3 * kWcGroups) + 16;
   int slots = static_cast<int>((di->max_smem - fixed) / kWcSlotBytes);
   if (slots > kWcMaxSlots) slots = kWcMaxSlots;
   if (const char* e = getenv("UP_CHAIN_SLOTS")) {
@@ -859,6 +985,12 @@ extern "C" int up_wasp_chain_fwd(const UpWaspChainDesc* d, const UpWaspChainWeig
   }
   UP_CHECK_ARG(slots >= 2, "up_wasp_chain_fwd: not enough shared memory");
   p.slots = slots;
+  // pooling sums from the ring need every slot to see the same number of aspp1 k-blocks per wave
+  // (measured slower than direct loads - the slot turnaround grows by the read: off unless UP_CHAIN_GAP_SMEM=1)
+  p.gap_smem = 0;
+  if (const char* e = getenv("UP_CHAIN_GAP_SMEM")) p.gap_smem = (e[0] == '1' && (d->cin / 64) % slots == 0) ? 1 : 0;
+  p.l2_prefetch = 0;      // measured: no gain (x is DRAM-bound either way), slightly slower
+  if (const char* e = getenv("UP_CHAIN_L2_PREFETCH")) p.l2_prefetch = e[0] == '1' ? 1 : 0;
   p.idesc = make_idesc_f16(static_cast<uint32_t>(fmt), 256u, 256u);
   p.st[0] = WcStage{1, 1, d->cin / 64, w->shift[0]};
   for (int i = 1; i < 4; ++i) p.st[i] = WcStage{3, d->dil[i - 1], kWcCout / 64, w->shift[i]};
@@ -881,11 +1013,18 @@ extern "C" int up_wasp_chain_fwd(const UpWaspChainDesc* d, const UpWaspChainWeig
     p.dbg = g_wc_dbg;
   }
 
-  CUtensorMap tmX, tmS, tmO, tmB[4], tmBc;
+  CUtensorMap tmX, tmS, tmO, tmB[4], tmBc, tmXp;
   const uint32_t abox[5] = {64u, static_cast<uint32_t>(pl.bw), 1u, static_cast<uint32_t>(pl.bh),
                             static_cast<uint32_t>(pl.bn)};
   rc = encode_act_map(&tmX, fmt, x, d->n, d->h, d->w, d->cin, 1, abox, 128, "wasp.x");
   if (rc) return rc;
+  {
+    // prefetch view of x: 256-channel (512-byte) rows, no swizzle
+    const uint32_t pbox[5] = {256u, static_cast<uint32_t>(pl.bw), 1u, static_cast<uint32_t>(pl.bh),
+                              static_cast<uint32_t>(pl.bn)};
+    rc = encode_act_map(&tmXp, fmt, x, d->n, d->h, d->w, d->cin, 1, pbox, 0, "wasp.x.prefetch");
+    if (rc) return rc;
+  }
   rc = encode_act_map(&tmS, fmt, s_stack, 4 * d->n, d->h, d->w, kWcCout, 1, abox, 128, "wasp.stack");
   if (rc) return rc;
   rc = encode_act_map(&tmO, fmt, out, d->n, d->h, d->w, kWcCout, 1, abox, 128, "wasp.out");
@@ -920,8 +1059,8 @@ extern "C" int up_wasp_chain_fwd(const UpWaspChainDesc* d, const UpWaspChainWeig
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  rc = check_cuda(fmt == 0 ? cudaLaunchKernelEx(&cfg, wasp_chain_kernel<0>, tmX, tmS, tmO, tmB[0], tmB[1], tmB[2], tmB[3], tmBc, p)
-                           : cudaLaunchKernelEx(&cfg, wasp_chain_kernel<1>, tmX, tmS, tmO, tmB[0], tmB[1], tmB[2], tmB[3], tmBc, p),
+  rc = check_cuda(fmt == 0 ? cudaLaunchKernelEx(&cfg, wasp_chain_kernel<0>, tmX, tmS, tmO, tmB[0], tmB[1], tmB[2], tmB[3], tmBc, tmXp, p)
+                           : cudaLaunchKernelEx(&cfg, wasp_chain_kernel<1>, tmX, tmS, tmO, tmB[0], tmB[1], tmB[2], tmB[3], tmBc, tmXp, p),
                   "wasp_chain_kernel launch");
   return rc;
 }
