@@ -1,7 +1,7 @@
 """Turn an `ncu --csv --metrics ...` log into a per-kernel table: launches, time, DRAM GB/s, tensor-pipe %.
 
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,\\
-sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active --clock-control none --csv \\
+sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none --csv \\
         --log-file gpurun_out/k.csv python <workload>
     python tools/kernel_table.py gpurun_out/k.csv [skip_first_n_launches]
 """
@@ -31,7 +31,7 @@ for lid, d in per.items():
     a["n"] += 1
     a["ns"] += ns
     a["bytes"] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
-    a["tc_ns"] += ns * d.get("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", 0.0) / 100.0
+    a["tc_ns"] += ns * d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0.0) / 100.0
 tot = sum(a["ns"] for a in agg.values())
 print("%-44s %6s %10s %7s %10s %9s" % ("kernel", "n", "time us", "share", "DRAM GB/s", "tensor %"))
 for name, a in sorted(agg.items(), key=lambda x: -x[1]["ns"]):

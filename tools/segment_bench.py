@@ -56,13 +56,20 @@ def main():
     torch.cuda.synchronize()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     names = [n for n, _f, _s in plan.ops]
-    # segment boundaries: stem = up to and including the first maxpool; the backbone's blocks start at each
-    # "bottleneck.conv1"; 3 + 4 + 23 + 3 blocks
-    starts = [i for i, n in enumerate(names) if n == "bottleneck.conv1"]
-    assert len(starts) == 33, len(starts)
-    last_backbone = max(i for i, n in enumerate(names) if n == "bottleneck.conv3")
-    segs = [("stem", 0, starts[0]), ("layer1", starts[0], starts[3]), ("layer2", starts[3], starts[7]),
-            ("layer3", starts[7], starts[30]), ("layer4", starts[30], last_backbone + 1),
+    # segment boundaries: stem = everything before the first block; a block starts at "bottleneck.conv1", a fused run
+    # "bottleneck.chain[n]" counts n blocks; 3 + 4 + 23 + 3 blocks
+    import re
+    starts, nblk = [], 0
+    bounds = {0: None, 3: None, 7: None, 30: None}
+    for i, n in enumerate(names):
+        if n == "bottleneck.conv1" or n.startswith("bottleneck.chain"):
+            if nblk in bounds and bounds[nblk] is None:
+                bounds[nblk] = i
+            nblk += int(re.search(r"\[(\d+)\]", n).group(1)) if n.startswith("bottleneck.chain") else 1
+    assert nblk == 33, nblk
+    last_backbone = max(i for i, n in enumerate(names) if n == "bottleneck.conv3" or n.startswith("bottleneck.chain"))
+    segs = [("stem", 0, bounds[0]), ("layer1", bounds[0], bounds[3]), ("layer2", bounds[3], bounds[7]),
+            ("layer3", bounds[7], bounds[30]), ("layer4", bounds[30], last_backbone + 1),
             ("wasp+decoder", last_backbone + 1, len(names))]
     total = time_range(plan, 0, len(names), flush)
     print("whole plan: %d ops, %.1f us" % (len(names), total))
