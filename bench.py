@@ -408,9 +408,11 @@ def run_b200(args) -> int:
     out_host = torch.empty((B, args.joints + 1, S // 8, S // 8), dtype=torch.float32).pin_memory()
     main = torch.cuda.current_stream(dev)
     copy_stream = torch.cuda.Stream(device=dev)
+    d2h_stream = torch.cuda.Stream(device=dev)
     x_bufs = [torch.empty_like(x_dev) for _ in range(2)]
     ev_ready = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_heat = torch.cuda.Event()
 
     def e2e_step(i):
         b = i % 2
@@ -422,7 +424,13 @@ def run_b200(args) -> int:
         main.wait_event(ev_ready[b])
         heat = model(x_bufs[b])          # the reference-facing call (model/unipose.py:27)
         ev_free[b].record(main)
-        out_host.copy_(heat, non_blocking=True)
+        # the result goes back to the host on its own stream (the next forward does not wait for PCIe); the copy of step
+        # i is ordered before the copy of step i+1 on that stream, and the final barrier() synchronises the device
+        ev_heat.record(main)
+        d2h_stream.wait_event(ev_heat)
+        with torch.cuda.stream(d2h_stream):
+            out_host.copy_(heat, non_blocking=True)
+        heat.record_stream(d2h_stream)
 
     for i in range(4):
         e2e_step(i)
