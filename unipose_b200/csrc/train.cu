@@ -163,7 +163,12 @@ __global__ void __launch_bounds__(512)
   const long long per_block = (npix + gridDim.x - 1) / gridDim.x;
   const long long p0 = blockIdx.x * per_block;
   const long long p1 = min(p0 + per_block, npix);
-  constexpr int kUnroll = 4;   // pixels in flight per thread: the loads of one iteration are all issued before any use
+  // pixels in flight per thread: the loads of one iteration are all issued before any use (the three-operand backward
+  // reduction would spill at 4 within the 128-register budget of a 512-thread block)
+#ifndef UP_RED_UNROLL
+#define UP_RED_UNROLL 2      // measured on B200: 2 (no spills) 29.1 ms/step vs 4 (spills) 29.5
+#endif
+  constexpr int kUnroll = kWhat == 1 ? UP_RED_UNROLL : 4;
   for (long long px0 = p0 + plane_lane; px0 < p1; px0 += static_cast<long long>(kUnroll) * pstride) {
     float va[kUnroll][8], vz[kUnroll][8], vy[kUnroll][8];
 #pragma unroll
@@ -270,37 +275,47 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 }
 
 // y = [relu]( z * scale[c] + shift[c] (+ res) ) (* mask)
+// kElemUnroll octets per thread, `stride` (= total threads) apart, all loads issued before the first use.  More than one
+// octet per thread measured SLOWER on B200 (occupancy drops faster than memory-level parallelism rises): default 1.
+#ifndef UP_ELEM_UNROLL
+#define UP_ELEM_UNROLL 1     // measured on B200 (training step): 1 -> 29.1 ms, 2 -> 30.9 ms, 4 -> 36.3 ms
+#endif
+constexpr int kElemUnroll = UP_ELEM_UNROLL;
 template <int kMode>
 __global__ void scale_shift_act_kernel(TView z, TViewW y, TView res, TView mask, const float* __restrict__ scale,
                                        const float* __restrict__ shift, long long npix, int ch, int relu, int has_res,
                                        int has_mask) {
   const int c8 = ch / 8;
   const long long total = npix * c8;
-  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (i >= total) return;
-  const int g = static_cast<int>(i % c8);
-  const long long px = i / c8;
-  float v[8];
-  t_load8<kMode>(z.p + px * z.cs + z.coff + g * 8, z.plane, v);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  float v[kElemUnroll][8], r[kElemUnroll][8], m[kElemUnroll][8];
+  int g[kElemUnroll];
+  long long px[kElemUnroll];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], scale[g * 8 + e], shift[g * 8 + e]);
-  if (has_res) {
-    float r[8];
-    t_load8<kMode>(res.p + px * res.cs + res.coff + g * 8, res.plane, r);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] += r[e];
+  for (int u = 0; u < kElemUnroll; ++u) {
+    const long long i = i0 + u * stride;
+    if (i >= total) continue;
+    g[u] = static_cast<int>(i % c8);
+    px[u] = i / c8;
+    t_load8<kMode>(z.p + px[u] * z.cs + z.coff + g[u] * 8, z.plane, v[u]);
+    if (has_res) t_load8<kMode>(res.p + px[u] * res.cs + res.coff + g[u] * 8, res.plane, r[u]);
+    if (has_mask) t_load8<kMode>(mask.p + px[u] * mask.cs + mask.coff + g[u] * 8, mask.plane, m[u]);
   }
-  if (relu) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-  }
-  if (has_mask) {
-    float m[8];
-    t_load8<kMode>(mask.p + px * mask.cs + mask.coff + g * 8, mask.plane, m);
+  for (int u = 0; u < kElemUnroll; ++u) {
+    const long long i = i0 + u * stride;
+    if (i >= total) continue;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] *= m[e];
+    for (int e = 0; e < 8; ++e) {
+      float t = fmaf(v[u][e], scale[g[u] * 8 + e], shift[g[u] * 8 + e]);
+      if (has_res) t += r[u][e];
+      if (relu) t = fmaxf(t, 0.f);
+      if (has_mask) t *= m[u][e];
+      v[u][e] = t;
+    }
+    t_store8<kMode>(y.p + px[u] * y.cs + y.coff + g[u] * 8, y.plane, v[u]);
   }
-  t_store8<kMode>(y.p + px * y.cs + y.coff + g * 8, y.plane, v);
 }
 
 // dz = gamma*invstd * ( dy' - sum_dy/M - xhat * sum_dy_xhat/M ),  dy' = dy * (y > 0 if relu);  optional dres = dy'
@@ -310,32 +325,44 @@ __global__ void bn_bwd_apply_kernel(TView dy, TView y, TView z, TViewW dz, TView
                                     long long npix, int ch, int relu, int has_dres) {
   const int c8 = ch / 8;
   const long long total = npix * c8;
-  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (i >= total) return;
-  const int g = static_cast<int>(i % c8);
-  const long long px = i / c8;
-  float vd[8], vz[8], o[8];
-  t_load8<kMode>(dy.p + px * dy.cs + dy.coff + g * 8, dy.plane, vd);
-  t_load8<kMode>(z.p + px * z.cs + z.coff + g * 8, z.plane, vz);
-  if (relu) {
-    float vy[8];
-    t_load8<kMode>(y.p + px * y.cs + y.coff + g * 8, y.plane, vy);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  float vd[kElemUnroll][8], vz[kElemUnroll][8], vy[kElemUnroll][8];
+  int g[kElemUnroll];
+  long long px[kElemUnroll];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) vd[e] = vy[e] > 0.f ? vd[e] : 0.f;
+  for (int u = 0; u < kElemUnroll; ++u) {
+    const long long i = i0 + u * stride;
+    if (i >= total) continue;
+    g[u] = static_cast<int>(i % c8);
+    px[u] = i / c8;
+    t_load8<kMode>(dy.p + px[u] * dy.cs + dy.coff + g[u] * 8, dy.plane, vd[u]);
+    t_load8<kMode>(z.p + px[u] * z.cs + z.coff + g[u] * 8, z.plane, vz[u]);
+    if (relu) t_load8<kMode>(y.p + px[u] * y.cs + y.coff + g[u] * 8, y.plane, vy[u]);
   }
-  const float4* k1 = reinterpret_cast<const float4*>(coef + g * 8);
-  const float4* k2 = reinterpret_cast<const float4*>(coef + ch + g * 8);
-  const float4* k3 = reinterpret_cast<const float4*>(coef + 2 * ch + g * 8);
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const float4 a = __ldg(k1 + q), b = __ldg(k2 + q), c = __ldg(k3 + q);
-    o[4 * q + 0] = fmaf(a.x, vd[4 * q + 0], fmaf(b.x, vz[4 * q + 0], c.x));
-    o[4 * q + 1] = fmaf(a.y, vd[4 * q + 1], fmaf(b.y, vz[4 * q + 1], c.y));
-    o[4 * q + 2] = fmaf(a.z, vd[4 * q + 2], fmaf(b.z, vz[4 * q + 2], c.z));
-    o[4 * q + 3] = fmaf(a.w, vd[4 * q + 3], fmaf(b.w, vz[4 * q + 3], c.w));
+  for (int u = 0; u < kElemUnroll; ++u) {
+    const long long i = i0 + u * stride;
+    if (i >= total) continue;
+    float o[8];
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) vd[u][e] = vy[u][e] > 0.f ? vd[u][e] : 0.f;
+    }
+    const float4* k1 = reinterpret_cast<const float4*>(coef + g[u] * 8);
+    const float4* k2 = reinterpret_cast<const float4*>(coef + ch + g[u] * 8);
+    const float4* k3 = reinterpret_cast<const float4*>(coef + 2 * ch + g[u] * 8);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float4 a = __ldg(k1 + q), b = __ldg(k2 + q), c = __ldg(k3 + q);
+      o[4 * q + 0] = fmaf(a.x, vd[u][4 * q + 0], fmaf(b.x, vz[u][4 * q + 0], c.x));
+      o[4 * q + 1] = fmaf(a.y, vd[u][4 * q + 1], fmaf(b.y, vz[u][4 * q + 1], c.y));
+      o[4 * q + 2] = fmaf(a.z, vd[u][4 * q + 2], fmaf(b.z, vz[u][4 * q + 2], c.z));
+      o[4 * q + 3] = fmaf(a.w, vd[u][4 * q + 3], fmaf(b.w, vz[u][4 * q + 3], c.w));
+    }
+    t_store8<kMode>(dz.p + px[u] * dz.cs + dz.coff + g[u] * 8, dz.plane, o);
+    if (has_dres) t_store8<kMode>(dres.p + px[u] * dres.cs + dres.coff + g[u] * 8, dres.plane, vd[u]);
   }
-  t_store8<kMode>(dz.p + px * dz.cs + dz.coff + g * 8, dz.plane, o);
-  if (has_dres) t_store8<kMode>(dres.p + px * dres.cs + dres.coff + g * 8, dres.plane, vd);
 }
 
 // k1 = gamma*invstd, k2 = -k1*invstd*m1, k3 = -k1*m0 - k2*mean with m0 = sum_dy/M, m1 = sum_dy_xhat/M; padded
@@ -776,7 +803,7 @@ extern "C" int up_scale_shift_act(const UpView* z, const UpView* y, const UpView
   if (residual && (rc = check_view("up_scale_shift_act(residual)", residual, c))) return rc;
   if (mask && (rc = check_view("up_scale_shift_act(mask)", mask, c))) return rc;
   UP_CHECK_ARG(scale && shift && npix > 0, "up_scale_shift_act: bad argument");
-  UP_T_DISPATCH(dtype, (up::scale_shift_act_kernel<kMode><<<blocks_for(npix*(c / 8)), 256, 0, (cudaStream_t)stream>>>(
+  UP_T_DISPATCH(dtype, (up::scale_shift_act_kernel<kMode><<<blocks_for((npix*(c / 8) + up::kElemUnroll - 1) / up::kElemUnroll), 256, 0, (cudaStream_t)stream>>>(
                            tv(z), tvw(y), tv(residual), tv(mask), scale, shift, npix, c, relu, residual != nullptr,
                            mask != nullptr)));
   UP_CHECK_LAUNCH("scale_shift_act_kernel");
@@ -826,7 +853,7 @@ extern "C" int up_bn_bwd_apply(const UpView* dy, const UpView* y, const UpView* 
   up::bn_bwd_coef_kernel<<<(c + 127) / 128, 128, 0, st>>>(sums, static_cast<double>(npix), save_mean, save_invstd, gamma,
                                                            coef, c_real, c, frozen);
   UP_CHECK_LAUNCH("bn_bwd_coef_kernel");
-  UP_T_DISPATCH(dtype, (up::bn_bwd_apply_kernel<kMode><<<blocks_for(npix*(c / 8)), 256, 0, st>>>(
+  UP_T_DISPATCH(dtype, (up::bn_bwd_apply_kernel<kMode><<<blocks_for((npix*(c / 8) + up::kElemUnroll - 1) / up::kElemUnroll), 256, 0, st>>>(
                            tv(dy), tv(y), tv(z), tvw(dz), tvw(dres), coef, npix, c, relu, dres != nullptr)));
   UP_CHECK_LAUNCH("bn_bwd_apply_kernel");
   if (dgamma && dbeta) {
