@@ -177,6 +177,59 @@ def test_fused_train_step_matches_manual_adam():
     assert torch.equal(after["decoder.conv2.weight"].detach().cpu(), before["decoder.conv2.weight"].cpu())
 
 
+def test_fused_train_steps_parameter_deltas_match_torch_adam():
+    """Three fused steps (MSE + backward + Adam on flat buffers, the third one replayed from CUDA graphs) against three
+    steps of torch.optim.Adam on the CPU oracle graph: the accumulated parameter UPDATES themselves, not just their signs
+    (after several steps m / sqrt(v) no longer saturates at +-lr, so the deltas carry the gradient magnitudes)."""
+    from unipose_b200 import train
+    m, sd, x, target, masks = _setup(n=2, size=96, seed=5, precision="fp32")
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    ts = train.TrainStep(m, lr=1e-5)      # small steps: the test is about the update vector, not about chaotic dynamics
+    before = {k: v.detach().clone().cpu() for k, v in m.named_parameters()}
+    xc, tc = x.cuda(), target.cuda()
+    losses = [float(ts.step(xc, tc)) for _ in range(3)]
+    torch.cuda.synchronize()
+    assert ts.graph is not None
+    sd2 = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+           for k, v in sd.items()}
+    live = None
+    opt = None
+    ref_losses = []
+    for _ in range(3):
+        heat = O.unipose_forward(x, sd2, training=True)
+        loss = F.mse_loss(heat, target)
+        if opt is not None:
+            opt.zero_grad()
+        loss.backward()
+        if opt is None:
+            live = [k for k, v in sd2.items() if getattr(v, "grad", None) is not None]
+            opt = torch.optim.Adam([sd2[k] for k in live], lr=1e-5)
+        opt.step()
+        ref_losses.append(float(loss))
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) < 1e-2 * abs(b), (losses, ref_losses)   # 1.2184, 0.9615, 0.8548 vs 1.2185, 0.9635, 0.8610 measured
+    after = dict(m.named_parameters())
+    report = {}
+    for k in ("decoder.last_conv.8.weight", "decoder.last_conv.8.bias", "decoder.last_conv.4.weight", "wasp.conv2.weight",
+              "wasp.aspp3.atrous_conv.weight", "backbone.layer4.2.conv2.weight", "backbone.layer3.11.conv2.weight"):
+        upd = after[k].detach().cpu() - before[k]
+        ref_upd = sd2[k].detach() - sd[k]
+        report[k] = (_rel_l2(upd, ref_upd), _cos(upd, ref_upd))
+    print("3-step Adam parameter deltas (rel-L2, cosine vs torch.optim.Adam on the oracle):",
+          {k: "%.2e / %.4f" % v for k, v in report.items()})
+    # Adam divides by sqrt(v): elements whose gradient is at the noise level get O(1) relative changes in their update,
+    # so the bound is on the update VECTOR: head tight, deep layers within the gradient noise documented above
+    # measured on B200: head 2.0e-2 / 2.6e-4 (cosine 0.9998 / 1.0000), decoder 0.11 (0.994), WASP 0.19-0.22 (0.98),
+    # layer4 0.30 (0.954), layer3 0.35 (0.937) - Adam's element-wise 1 / sqrt(v) turns the gradient noise of the deep
+    # layers (tests above) into O(1) changes of the elements whose gradient is at the noise level
+    assert report["decoder.last_conv.8.weight"][0] < 3e-2 and report["decoder.last_conv.8.bias"][0] < 2e-3, report
+    for k, (rel, cos) in report.items():
+        assert rel < 0.45 and cos > 0.90, (k, rel, cos)
+    assert torch.equal(after["decoder.conv2.weight"].detach().cpu(), before["decoder.conv2.weight"])
+
+
 def test_train_step_graph_replay_matches_eager(monkeypatch):
     """From the third step on forward + loss + backward replay as one CUDA graph: same losses and weights as eager."""
     from unipose_b200 import train
