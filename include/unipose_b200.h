@@ -180,6 +180,23 @@ int up_bneck_chain_fwd(const UpBneckChainDesc* desc, const UpBneckChainWeights* 
                        void* workspace, int64_t workspace_bytes, void* stream);
 int up_debug_bneck_timing(unsigned long long* h_out);
 
+/* ------------------------------------------------------------------------------------------
+ * Second half of a bottleneck as one launch (eval mode, fp16 / bf16, planes 64 or 128, stride 1):
+ *   y = ReLU( bn3(conv3( ReLU(bn2(conv2_3x3(t1))) )) + residual )        Bottleneck.forward, resnet.py:28-41
+ * The 3x3 output stays in shared memory (it is the A operand of the 1x1 expansion); the residual enters the
+ * accumulator as identity MMAs.  t1 [n,h,w,planes], residual and y [n,h,w,4*planes], all dense NHWC 16-bit;
+ * w2 packed [9][planes][planes], w3 packed [1][4*planes][planes] (BatchNorm scales folded in), shifts fp32.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct UpBneckTailDesc {
+  int32_t n, h, w;
+  int32_t planes;      /* 64 or 128 */
+  int32_t dil;         /* dilation (= padding) of the 3x3 conv */
+  int32_t dtype;       /* UP_FP16 or UP_BF16 */
+} UpBneckTailDesc;
+int up_bneck_tail_supported(const UpBneckTailDesc* desc);
+int up_bneck_tail_fwd(const UpBneckTailDesc* desc, const void* t1, const void* w2, const float* shift2, const void* w3,
+                      const float* shift3, const void* residual, void* y, void* stream);
+
 /* Debug aid (UP_DEBUG_TIMING=1): per-CTA phase timestamps (ns) of the last up_wasp_chain_fwd launch, 160 CTAs x 32 slots. */
 int up_debug_chain_timing(unsigned long long* h_out);
 /* Debug aid (UP_DEBUG_TIMING=1 in the environment): per-CTA phase timestamps (ns) of the last up_conv2d_fwd launch,

@@ -1,0 +1,50 @@
+"""The fused bottleneck tail (csrc/bneck_tail.cu: 3x3 conv + 1x1 expansion + residual + ReLU in one launch, layer1 /
+layer2) against the layer-wise plan and the CPU oracle, incl. partial tiles (368 -> 92x92 / 46x46 maps) and small maps."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unipose_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(precision, seed=0):
+    from unipose_b200.model.unipose import unipose
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = unipose(dataset="MPII", num_classes=16, precision=precision)
+    sd = O.synth_state_dict(16, seed=seed)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval(), sd
+
+
+def _run(m, x, tail, monkeypatch):
+    monkeypatch.setenv("UNIPOSE_B200_BNECK_TAIL", "1" if tail else "0")
+    m._plans.clear()
+    out = m(x.cuda())
+    torch.cuda.synchronize()
+    names = [n for n, f, s in m.plan_for(x.cuda()).ops if f is not None]
+    assert (names.count("bottleneck.tail") == 6) == tail, names       # layer1 x3 + layer2 blocks 1..3
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("n,size,precision", [(4, 384, "fp16"), (3, 368, "fp16"), (1, 96, "fp16"), (2, 256, "bf16"),
+                                              (2, 512, "fp16")])
+def test_bneck_tail_matches_layerwise_and_oracle(n, size, precision, monkeypatch):
+    m, sd = _model(precision, seed=13)
+    x = O.synth_input(n, size, size, seed=13)
+    with torch.no_grad():
+        ref = O.unipose_forward(x, sd).numpy()
+    got = _run(m, x, True, monkeypatch)
+    assert np.array_equal(got, m(x.cuda()).cpu().numpy())          # graph replay: same bits
+    base = _run(m, x, False, monkeypatch)
+    scale = float(np.abs(ref).max())
+    e_tail = float(np.abs(got - ref).max() / scale)
+    e_base = float(np.abs(base - ref).max() / scale)
+    print("bottleneck tail %dx%d^2 %s: max-rel %.3g (layer-wise %.3g)" % (n, size, precision, e_tail, e_base))
+    bound = 5e-3 if precision == "fp16" else 3e-2
+    assert e_tail < bound and e_base < bound, (e_tail, e_base)
+    assert e_tail < 2.0 * e_base + 1e-3

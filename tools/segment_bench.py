@@ -67,7 +67,7 @@ def main():
                 bounds[nblk] = i
             nblk += int(re.search(r"\[(\d+)\]", n).group(1)) if n.startswith("bottleneck.chain") else 1
     assert nblk == 33, nblk
-    last_backbone = max(i for i, n in enumerate(names) if n == "bottleneck.conv3" or n.startswith("bottleneck.chain"))
+    last_backbone = max(i for i, n in enumerate(names) if n.startswith("bottleneck."))
     segs = [("stem", 0, bounds[0]), ("layer1", bounds[0], bounds[3]), ("layer2", bounds[3], bounds[7]),
             ("layer3", bounds[7], bounds[30]), ("layer4", bounds[30], last_backbone + 1),
             ("wasp+decoder", last_backbone + 1, len(names))]

@@ -59,6 +59,10 @@ class UpBneckChainDesc(ctypes.Structure):
                 ("dil", c_int32), ("dtype", c_int32)]
 
 
+class UpBneckTailDesc(ctypes.Structure):
+    _fields_ = [("n", c_int32), ("h", c_int32), ("w", c_int32), ("planes", c_int32), ("dil", c_int32), ("dtype", c_int32)]
+
+
 class UpBneckChainWeights(ctypes.Structure):
     _fields_ = [("w1", c_void_p), ("w2", c_void_p), ("w3", c_void_p), ("shift1", c_void_p), ("shift2", c_void_p),
                 ("shift3", c_void_p)]
@@ -119,6 +123,8 @@ _SIGNATURES = {
     "up_pack_conv_weights": [_P, _I, _L, _P],
     "up_wasp_chain_supported": [POINTER(UpWaspChainDesc)],
     "up_bneck_chain_supported": [POINTER(UpBneckChainDesc)],
+    "up_bneck_tail_supported": [POINTER(UpBneckTailDesc)],
+    "up_bneck_tail_fwd": [POINTER(UpBneckTailDesc), _P, _P, _P, _P, _P, _P, _P, _P],
     "up_bneck_chain_fwd": [POINTER(UpBneckChainDesc), POINTER(UpBneckChainWeights), _P, _P, _P, _P, _L, _P],
     "up_debug_bneck_timing": [_P],
     "up_wasp_chain_fwd": [POINTER(UpWaspChainDesc), POINTER(UpWaspChainWeights), _P, _P, _P, _P, _L, _P],

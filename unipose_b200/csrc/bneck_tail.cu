@@ -1,0 +1,500 @@
+// The second half of a ResNet bottleneck - 3x3 conv (+BN+ReLU) -> 1x1 expansion (+BN) + residual + ReLU
+// (Bottleneck.forward, model/modules/backbone/resnet.py:28-41) - as ONE kernel per block for the bandwidth-bound
+// high-resolution layers (layer1: planes 64 at H/4, layer2: planes 128 at H/8).  The 3x3 output t2 never leaves the
+// SM: its epilogue writes it (16-bit, 128B-swizzled) into shared memory, where it is the A operand of the expansion.
+// Per 128-pixel tile:
+//   conv2   acc2[128 x P]   = sum over taps / 64-channel chunks of t1 (TMA, out-of-image rows zero-filled) x W2
+//   epi A   t2 = ReLU(acc2 + shift2) -> staging set T
+//   conv3   acc3[128 x 256] = T x W3[n-tile]  (+ residual tile x I: identity MMAs, exact)     for each 256-channel N-tile
+//   epi B   out = ReLU(acc3 + shift3) -> staging set O -> TMA store
+// Persistent CTAs (one per SM, no clusters: these layers are HBM-bound, halving the weight traffic buys nothing) walk
+// the tiles; the MMA issuer runs conv2 of tile i+1 BEFORE conv3 of tile i (acc2 is double buffered), so the tensor
+// pipe works on the next tile while the epilogue warps stage t2, and the 256-column output epilogue of tile i overlaps
+// conv2 of tile i+2.  Bytes per block: t1 (+halo) + residual + output - the t2 round trip (2 x N*H*W*P*2 B) and one
+// launch disappear.
+//
+// Warp roles (384 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM alloc + store thread, 3 idle, 4..11 epilogue.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "up_internal.h"
+#include "up_ptx.cuh"
+
+namespace up {
+
+constexpr int kBtThreads = 384;
+constexpr int kBtEpiWarp0 = 4;
+constexpr int kBtEpiThreads = 256;
+constexpr int kBtMaxSlots = 4;
+constexpr uint32_t kBtABytes = 16384;
+constexpr uint32_t kBtSlotBytes = 32768;
+constexpr uint32_t kBtBuf = 16384;
+
+struct BtParams {
+  int N, H, W;
+  int bn, bh, bw;
+  int tiles_h, tiles_w, tiles_n, total_tiles;
+  int P;                 // planes: 64 or 128
+  int pchunks;           // P / 64
+  int ntiles;            // 4P / 256 output N-tiles
+  int dil;
+  int slots;
+  uint32_t idesc2;       // M128 x N=P
+  uint32_t idesc3;       // M128 x N=256
+  uint32_t idesc_res;    // M128 x N=64
+  const float* shift2;   // [P]
+  const float* shift3;   // [4P]
+};
+
+struct BtTile {
+  int n0, h0, w0;
+};
+__device__ __forceinline__ BtTile bt_tile(const BtParams& p, int t) {
+  BtTile r;
+  r.w0 = (t % p.tiles_w) * p.bw;
+  t /= p.tiles_w;
+  r.h0 = (t % p.tiles_h) * p.bh;
+  r.n0 = (t / p.tiles_h) * p.bn;
+  return r;
+}
+__device__ __forceinline__ void bt_taps(int dil, int x0, int ext, int limit, int& lo, int& hi) {
+  lo = 3;
+  hi = -1;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int c = x0 + (k - 1) * dil;
+    if (c + ext > 0 && c < limit) {
+      lo = min(lo, k);
+      hi = max(hi, k);
+    }
+  }
+}
+template <int kFmt>
+__device__ __forceinline__ uint32_t bt_pack2_relu(float lo_elem, float hi_elem) {
+  uint32_t d;
+  if constexpr (kFmt == 0) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  return d;
+}
+
+template <int kFmt>
+__global__ void __launch_bounds__(kBtThreads, 1)
+    bneck_tail_kernel(const __grid_constant__ CUtensorMap tmT1, const __grid_constant__ CUtensorMap tmR,
+                      const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW2,
+                      const __grid_constant__ CUtensorMap tmW3, const BtParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t stgT = smem_base + p.slots * kBtSlotBytes;     // P/64 buffers: t2 tile
+  const uint32_t stgO = stgT + 2 * kBtBuf;                       // 4 buffers: one 256-channel N-tile of the output
+  const uint32_t ident = stgO + 4 * kBtBuf;                      // 64 x 64 identity (K-major, 128B swizzle), 8 KB
+  const uint32_t bars = ident + 8192u;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kBtMaxSlots + s); };
+  const uint32_t b0 = bars + 8u * (2 * kBtMaxSlots);
+  auto full2_bar = [&](int a) { return b0 + 8u * a; };            // [2] conv2 accumulators
+  auto empty2_bar = [&](int a) { return b0 + 8u * (2 + a); };
+  const uint32_t full3_bar = b0 + 8u * 4, empty3_bar = b0 + 8u * 5;
+  auto availT = [&](int g) { return b0 + 8u * (6 + g); };         // [2] MMA commit -> epilogue may refill
+  auto s2readyT = [&](int g) { return b0 + 8u * (8 + g); };       // [2] epilogue -> MMA
+  auto availO = [&](int g) { return b0 + 8u * (10 + g); };        // [4] store drained
+  auto readyO = [&](int g) { return b0 + 8u * (14 + g); };        // [4] epilogue -> store thread
+  const uint32_t tmem_slot = b0 + 8u * 18;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int first = blockIdx.x, step = gridDim.x;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmT1);
+    tma_prefetch_desc(&tmR);
+    tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmW3);
+    tma_prefetch_desc(&tmY);
+    for (int s = 0; s < p.slots; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(full2_bar(a), 1);
+      mbar_init(empty2_bar(a), kBtEpiThreads / 32);
+      mbar_init(availT(a), 1);
+      mbar_init(s2readyT(a), kBtEpiThreads / 32);
+    }
+    mbar_init(full3_bar, 1);
+    mbar_init(empty3_bar, kBtEpiThreads / 32);
+    for (int g = 0; g < 4; ++g) {
+      mbar_init(availO(g), 1);
+      mbar_init(readyO(g), kBtEpiThreads / 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  {
+    // K-major, 128B-swizzled 64 x 64 identity: row n holds a single 1.0 at k = n
+    const uint32_t one = kFmt == 1 ? 0x3F80u : 0x3C00u;
+    for (uint32_t i = threadIdx.x; i < 8192u / 16u; i += blockDim.x) {
+      const uint32_t n = i >> 3, chunk = i & 7u;
+      const uint32_t src_chunk = chunk ^ (n & 7u);
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      if (src_chunk == (n >> 3)) {
+        const uint32_t e = n & 7u;
+        w[e >> 1] = one << ((e & 1u) * 16u);
+      }
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ident + i * 16u), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                   "r"(w[3])
+                   : "memory");
+    }
+    fence_proxy_async_smem();
+  }
+  tcgen05_before_thread_sync();
+  __syncthreads();
+  tcgen05_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  // TMEM columns: conv2 accumulators at [0, P) and [P, 2P); the 256-column output accumulator at [256, 512)
+  const uint32_t tmem_acc3 = tmem_base + 256u;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  // Work order shared by producer and MMA issuer: conv2(tile 0); then for i >= 0: conv2(tile i+1) [if any], conv3(tile i)
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    uint32_t slot = 0, par = 1;
+    auto advance = [&]() {
+      if (++slot == static_cast<uint32_t>(p.slots)) {
+        slot = 0;
+        par ^= 1u;
+      }
+    };
+    auto conv2_loads = [&](int tile) {
+      const BtTile t = bt_tile(p, tile);
+      int kh_lo, kh_hi, kw_lo, kw_hi;
+      bt_taps(p.dil, t.h0, p.bh, p.H, kh_lo, kh_hi);
+      bt_taps(p.dil, t.w0, p.bw, p.W, kw_lo, kw_hi);
+      const uint32_t bbytes = static_cast<uint32_t>(p.P) * 128u;
+      for (int kh = kh_lo; kh <= kh_hi; ++kh)
+        for (int kw = kw_lo; kw <= kw_hi; ++kw)
+          for (int c = 0; c < p.pchunks; ++c) {
+            mbar_wait(empty_bar(slot), par, 16000000000LL);
+            if (elect_one()) {
+              const uint32_t dst = smem_base + slot * kBtSlotBytes;
+              mbar_arrive_expect_tx(full_bar(slot), kBtABytes + bbytes);
+              tma_load_5d(&tmT1, dst, full_bar(slot), c * 64, t.w0 + (kw - 1) * p.dil, 0, t.h0 + (kh - 1) * p.dil, t.n0);
+              tma_load_2d(&tmW2, dst + kBtABytes, full_bar(slot), c * 64, (kh * 3 + kw) * p.P);
+            }
+            __syncwarp();
+            advance();
+          }
+    };
+    auto conv3_loads = [&](int tile) {
+      const BtTile t = bt_tile(p, tile);
+      for (int nt = 0; nt < p.ntiles; ++nt) {
+        // the N-tile's filter: 256 rows x 64 channels per K-chunk = 32 KB = one whole slot
+        for (int c = 0; c < p.pchunks; ++c) {
+          mbar_wait(empty_bar(slot), par, 16000000000LL);
+          if (elect_one()) {
+            const uint32_t dst = smem_base + slot * kBtSlotBytes;
+            mbar_arrive_expect_tx(full_bar(slot), kBtSlotBytes);
+            tma_load_2d(&tmW3, dst, full_bar(slot), c * 64, nt * 256);
+          }
+          __syncwarp();
+          advance();
+        }
+        // the residual tile of this N-tile: 256 channels = two slots of two 64-channel chunks
+        for (int r2 = 0; r2 < 2; ++r2) {
+          mbar_wait(empty_bar(slot), par, 16000000000LL);
+          if (elect_one()) {
+            const uint32_t dst = smem_base + slot * kBtSlotBytes;
+            mbar_arrive_expect_tx(full_bar(slot), kBtSlotBytes);
+            for (int cc = 0; cc < 2; ++cc)
+              tma_load_5d(&tmR, dst + cc * kBtABytes, full_bar(slot), nt * 256 + (2 * r2 + cc) * 64, t.w0, 0, t.h0, t.n0);
+          }
+          __syncwarp();
+          advance();
+        }
+      }
+    };
+    if (first < p.total_tiles) conv2_loads(first);
+    for (int tile = first; tile < p.total_tiles; tile += step) {
+      if (tile + step < p.total_tiles) conv2_loads(tile + step);
+      conv3_loads(tile);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    uint32_t slot = 0, phase = 0;
+    auto advance = [&]() {
+      if (++slot == static_cast<uint32_t>(p.slots)) {
+        slot = 0;
+        phase ^= 1u;
+      }
+    };
+    const uint64_t adesc0 = make_smem_desc_kmajor(smem_base, 128);
+    const uint64_t tdesc0 = make_smem_desc_kmajor(stgT, 128);
+    const uint64_t identdesc = make_smem_desc_kmajor(ident, 128);
+    const uint32_t slot_step = kBtSlotBytes >> 4;
+    uint32_t n2[2] = {0u, 0u};      // uses of the conv2 accumulators
+    uint32_t n3 = 0;                // uses of the output accumulator
+    uint32_t nT = 0;                // t2 tiles consumed (s2readyT parity)
+    auto conv2_mma = [&](int tile, int it) {
+      const BtTile t = bt_tile(p, tile);
+      int kh_lo, kh_hi, kw_lo, kw_hi;
+      bt_taps(p.dil, t.h0, p.bh, p.H, kh_lo, kh_hi);
+      bt_taps(p.dil, t.w0, p.bw, p.W, kw_lo, kw_hi);
+      const int nkb = (kh_hi - kh_lo + 1) * (kw_hi - kw_lo + 1) * p.pchunks;
+      const int a = it & 1;
+      mbar_wait(empty2_bar(a), (n2[a] & 1u) ^ 1u);
+      ++n2[a];
+      tcgen05_after_thread_sync();
+      const uint32_t tacc = tmem_base + static_cast<uint32_t>(a * p.P);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(full_bar(slot), phase);
+        tcgen05_after_thread_sync();
+        if (elect_one()) {
+          const uint64_t ad = adesc0 + static_cast<uint64_t>(slot_step * slot);
+          const uint64_t bd = ad + static_cast<uint64_t>(kBtABytes >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tacc, ad + 2u * k, bd + 2u * k, p.idesc2, (kb | k) ? 1u : 0u);
+          umma_commit(empty_bar(slot));
+          if (kb == nkb - 1) umma_commit(full2_bar(a));
+        }
+        __syncwarp();
+        advance();
+      }
+    };
+    auto conv3_mma = [&]() {
+      for (int g = 0; g < p.pchunks; ++g) mbar_wait(s2readyT(g), nT & 1u);     // t2 of this tile is staged
+      for (int nt = 0; nt < p.ntiles; ++nt) {
+        mbar_wait(empty3_bar, (n3 & 1u) ^ 1u);
+        ++n3;
+        tcgen05_after_thread_sync();
+        for (int c = 0; c < p.pchunks; ++c) {
+          mbar_wait(full_bar(slot), phase);
+          tcgen05_after_thread_sync();
+          if (elect_one()) {
+            const uint64_t ad = tdesc0 + static_cast<uint64_t>((kBtBuf >> 4) * c);
+            const uint64_t bd = adesc0 + static_cast<uint64_t>(slot_step * slot);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_acc3, ad + 2u * k, bd + 2u * k, p.idesc3, (c | k) ? 1u : 0u);
+            umma_commit(empty_bar(slot));
+            if (nt == p.ntiles - 1 && c == p.pchunks - 1)
+              for (int g = 0; g < p.pchunks; ++g) umma_commit(availT(g));          // t2 consumed
+          }
+          __syncwarp();
+          advance();
+        }
+        for (int r2 = 0; r2 < 2; ++r2) {
+          mbar_wait(full_bar(slot), phase);
+          tcgen05_after_thread_sync();
+          if (elect_one()) {
+            for (int cc = 0; cc < 2; ++cc) {
+              // residual: D[:, g*64 .. g*64+63] += R chunk x I   (exact: products with 1.0)
+              const uint64_t rd = adesc0 + static_cast<uint64_t>(slot_step * slot) + static_cast<uint64_t>((kBtABytes >> 4) * cc);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tmem_acc3 + static_cast<uint32_t>(2 * r2 + cc) * 64u, rd + 2u * k, identdesc + 2u * k, p.idesc_res, 1u);
+            }
+            umma_commit(empty_bar(slot));
+            if (r2 == 1) umma_commit(full3_bar);
+          }
+          __syncwarp();
+          advance();
+        }
+      }
+      ++nT;
+    };
+    int it = 0;
+    if (first < p.total_tiles) conv2_mma(first, 0);
+    for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
+      if (tile + step < p.total_tiles) conv2_mma(tile + step, it + 1);
+      conv3_mma();
+    }
+  } else if (threadIdx.x == 64) {
+    // ===================== store thread =====================
+    uint32_t nO = 0;
+    for (int tile = first; tile < p.total_tiles; tile += step) {
+      const BtTile t = bt_tile(p, tile);
+      for (int nt = 0; nt < p.ntiles; ++nt) {
+        for (int g = 0; g < 4; ++g) {
+          mbar_wait(readyO(g), nO & 1u);
+          tma_store_5d(&tmY, stgO + g * kBtBuf, nt * 256 + g * 64, t.w0, 0, t.h0, t.n0);
+          tma_store_commit();
+        }
+        tma_store_wait_read<0>();
+        for (int g = 0; g < 4; ++g) mbar_arrive(availO(g));
+        ++nO;
+      }
+    }
+    tma_store_wait_all<0>();
+  } else if (warp >= kBtEpiWarp0) {
+    // ===================== epilogue (8 warps) =====================
+    const int ew = warp - kBtEpiWarp0;
+    const int quarter = ew & 3;
+    const int half = ew >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
+    const uint32_t row7 = static_cast<uint32_t>(row) & 7u;
+    const uint32_t tlane = static_cast<uint32_t>(quarter * 32) << 16;
+    uint32_t nT = 0, nO = 0, n3 = 0;
+    uint32_t n2[2] = {0u, 0u};
+    // `groups` x 64 accumulator columns -> ReLU(acc + shift) -> 16-bit -> staging buffers
+    auto epilogue = [&](uint32_t tmem_col0, int groups, const float* sh, bool setO) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_col0 + tlane + static_cast<uint32_t>(half * 32);
+      const uint32_t nuse = setO ? nO : nT;
+      tmem_ld_32x32b_x32(taddr, r);
+      for (int g = 0; g < groups; ++g) {
+        const float4* s4 = reinterpret_cast<const float4*>(sh + g * 64 + half * 32);
+        float v[32];
+        tmem_ld_wait();
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 h4 = __ldg(s4 + j4);
+          v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + h4.x;
+          v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + h4.y;
+          v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + h4.z;
+          v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + h4.w;
+        }
+        if (g + 1 < groups) tmem_ld_32x32b_x32(taddr + (g + 1) * 64, r);
+        uint32_t w[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) w[e] = bt_pack2_relu<kFmt>(v[2 * e], v[2 * e + 1]);
+        mbar_wait(setO ? availO(g) : availT(g), (nuse & 1u) ^ 1u);
+        const uint32_t rowaddr = (setO ? stgO : stgT) + g * kBtBuf + rowoff;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const uint32_t addr = rowaddr + (((static_cast<uint32_t>(half) * 4u + c4) ^ row7) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[4 * c4]), "r"(w[4 * c4 + 1]),
+                       "r"(w[4 * c4 + 2]), "r"(w[4 * c4 + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(setO ? readyO(g) : s2readyT(g));
+      }
+      if (setO) ++nO; else ++nT;
+    };
+    int it = 0;
+    for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
+      const int a = it & 1;
+      // ---- epilogue A: t2 ----
+      mbar_wait(full2_bar(a), n2[a] & 1u);
+      ++n2[a];
+      tcgen05_after_thread_sync();
+      epilogue(tmem_base + static_cast<uint32_t>(a * p.P), p.pchunks, p.shift2, false);
+      tcgen05_before_thread_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty2_bar(a));
+      // ---- epilogue B: the block's output, 256 channels per N-tile ----
+      for (int nt = 0; nt < p.ntiles; ++nt) {
+        mbar_wait(full3_bar, n3 & 1u);
+        ++n3;
+        tcgen05_after_thread_sync();
+        epilogue(tmem_acc3, 4, p.shift3 + nt * 256, true);
+        tcgen05_before_thread_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty3_bar);
+      }
+    }
+  }
+
+  tcgen05_before_thread_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_after_thread_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace up
+#include "up_conv_host.h"
+
+using namespace up;
+
+static int bt_check(const UpBneckTailDesc* d) {
+  if (!d) return fail(UP_ERR_INVALID, "up_bneck_tail: null descriptor");
+  if (d->dtype != UP_FP16 && d->dtype != UP_BF16) return fail(UP_ERR_UNSUPPORTED, "up_bneck_tail: fp16 / bf16 only");
+  if (d->planes != 64 && d->planes != 128) return fail(UP_ERR_UNSUPPORTED, "up_bneck_tail: planes must be 64 or 128 (got %d)", d->planes);
+  if (d->n <= 0 || d->h <= 0 || d->w <= 0 || d->dil < 1) return fail(UP_ERR_INVALID, "up_bneck_tail: bad dims");
+  return 0;
+}
+
+extern "C" int up_bneck_tail_supported(const UpBneckTailDesc* d) { return bt_check(d); }
+
+extern "C" int up_bneck_tail_fwd(const UpBneckTailDesc* d, const void* t1, const void* w2, const float* shift2,
+                                 const void* w3, const float* shift3, const void* residual, void* y, void* stream) {
+  UP_CHECK_ARG(d && t1 && w2 && shift2 && w3 && shift3 && residual && y, "up_bneck_tail_fwd: null argument");
+  int rc = bt_check(d);
+  if (rc) return rc;
+  DeviceInfo* di = device_info();
+  if (!di) return UP_ERR_CUDA;
+  if (!di->tail_attr) {
+    rc = check_cuda(cudaFuncSetAttribute(bneck_tail_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(di->max_smem)), "cudaFuncSetAttribute(bneck tail)");
+    if (rc) return rc;
+    rc = check_cuda(cudaFuncSetAttribute(bneck_tail_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(di->max_smem)), "cudaFuncSetAttribute(bneck tail bf16)");
+    if (rc) return rc;
+    di->tail_attr = true;
+  }
+  const int fmt = fmt_of_dtype(d->dtype);
+  BtParams p{};
+  p.N = d->n;
+  p.H = d->h;
+  p.W = d->w;
+  pick_tile(d->n, d->h, d->w, p.bn, p.bh, p.bw);
+  p.tiles_w = (d->w + p.bw - 1) / p.bw;
+  p.tiles_h = (d->h + p.bh - 1) / p.bh;
+  p.tiles_n = (d->n + p.bn - 1) / p.bn;
+  p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.P = d->planes;
+  p.pchunks = d->planes / 64;
+  p.ntiles = (4 * d->planes) / 256;
+  p.dil = d->dil;
+  const size_t fixed = 1024 + 6 * kBtBuf + 8192 + 8 * (2 * kBtMaxSlots + 18) + 16;
+  int slots = static_cast<int>((di->max_smem - fixed) / kBtSlotBytes);
+  if (slots > kBtMaxSlots) slots = kBtMaxSlots;
+  UP_CHECK_ARG(slots >= 2, "up_bneck_tail_fwd: not enough shared memory");
+  p.slots = slots;
+  p.idesc2 = make_idesc_f16(static_cast<uint32_t>(fmt), 128u, static_cast<uint32_t>(d->planes));
+  p.idesc3 = make_idesc_f16(static_cast<uint32_t>(fmt), 128u, 256u);
+  p.idesc_res = make_idesc_f16(static_cast<uint32_t>(fmt), 128u, 64u);
+  p.shift2 = shift2;
+  p.shift3 = shift3;
+  CUtensorMap tmT1, tmR, tmY, tmW2, tmW3;
+  const uint32_t abox[5] = {64u, static_cast<uint32_t>(p.bw), 1u, static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
+  rc = encode_act_map(&tmT1, fmt, t1, d->n, d->h, d->w, d->planes, 1, abox, 128, "tail.t1");
+  if (rc) return rc;
+  rc = encode_act_map(&tmR, fmt, residual, d->n, d->h, d->w, 4 * d->planes, 1, abox, 128, "tail.residual");
+  if (rc) return rc;
+  rc = encode_act_map(&tmY, fmt, y, d->n, d->h, d->w, 4 * d->planes, 1, abox, 128, "tail.y");
+  if (rc) return rc;
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(d->planes), static_cast<uint64_t>(9) * d->planes};
+    const uint64_t st[1] = {static_cast<uint64_t>(d->planes) * 2};
+    const uint32_t box[2] = {64u, static_cast<uint32_t>(d->planes)};
+    rc = encode_map(&tmW2, fmt, 2, w2, dims, st, box, 128, "tail.w2");
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(d->planes), static_cast<uint64_t>(4) * d->planes};
+    const uint64_t st[1] = {static_cast<uint64_t>(d->planes) * 2};
+    const uint32_t box[2] = {64u, 256u};
+    rc = encode_map(&tmW3, fmt, 2, w3, dims, st, box, 128, "tail.w3");
+    if (rc) return rc;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.total_tiles < di->sm_count ? p.total_tiles : di->sm_count);
+  cfg.blockDim = dim3(kBtThreads);
+  cfg.dynamicSmemBytes = fixed + static_cast<size_t>(slots) * kBtSlotBytes;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  rc = check_cuda(fmt == 0 ? cudaLaunchKernelEx(&cfg, bneck_tail_kernel<0>, tmT1, tmR, tmY, tmW2, tmW3, p)
+                           : cudaLaunchKernelEx(&cfg, bneck_tail_kernel<1>, tmT1, tmR, tmY, tmW2, tmW3, p),
+                  "bneck_tail_kernel launch");
+  return rc;
+}

@@ -24,6 +24,7 @@ struct DeviceInfo {
   bool wgrad_attr = false;   // conv_wgrad_tcgen05_kernel
   bool chain_attr = false;   // wasp_chain_kernel
   bool bneck_attr = false;   // bneck_chain_kernel
+  bool tail_attr = false;    // bneck_tail_kernel
   int max_clusters[5] = {0, 0, 0, 0, 0};   // cached cudaOccupancyMaxActiveClusters: [2], [4] conv kernel by cluster
                                            // size; [0] wasp chain, [1] bottleneck chain (both clusters of 2)
 };

@@ -83,16 +83,40 @@ class Bottleneck(PlanModule):
         ho, wo = (h - 1) // s + 1, (w - 1) // s + 1
         t1 = b.act(n, h, w, planes)
         b.conv(x, b.packed_conv(self.conv1, self.bn1), t1, "bottleneck.conv1", relu=True)
-        t2 = b.act(n, ho, wo, planes)
-        b.conv(t1, b.packed_conv(self.conv2, self.bn2), t2, "bottleneck.conv2", stride=s, dil=d, pad=d, relu=True)
         res = x
         if self.downsample is not None:
             res = b.act(n, ho, wo, planes * 4)
             b.conv(x, b.packed_conv(self.downsample[0], self.downsample[1]), res, "bottleneck.downsample",
                    stride=s, pad=0)
         out = b.act(n, ho, wo, planes * 4)
+        if self._emit_tail(b, t1, res, out):
+            return out
+        t2 = b.act(n, ho, wo, planes)
+        b.conv(t1, b.packed_conv(self.conv2, self.bn2), t2, "bottleneck.conv2", stride=s, dil=d, pad=d, relu=True)
         b.conv(t2, b.packed_conv(self.conv3, self.bn3), out, "bottleneck.conv3", relu=True, residual=res)
         return out
+
+    def _emit_tail(self, b, t1, res, out):
+        """conv2 (3x3) + conv3 (1x1 expansion) + residual + ReLU as ONE launch (csrc/bneck_tail.cu) for the
+        bandwidth-bound layers (planes 64 / 128, stride 1, fp16 / bf16): t2 never leaves shared memory."""
+        import ctypes
+        from .... import _lib, ops
+        planes = self.conv1.out_channels
+        if (os.environ.get("UNIPOSE_B200_BNECK_TAIL", "1") == "0" or b.mode == ops.UP_SPLIT or self.stride != 1 or
+                planes not in (64, 128) or not isinstance(res, ops.Act) or res.c != 4 * planes or t1.c != planes):
+            return False
+        d = _lib.UpBneckTailDesc()
+        d.n, d.h, d.w, d.planes, d.dil, d.dtype = t1.n, t1.h, t1.w, planes, self.dilation, b.mode
+        if _lib.load().up_bneck_tail_supported(ctypes.byref(d)) != 0:
+            return False
+        pc2 = b.packed_conv(self.conv2, self.bn2)
+        pc3 = b.packed_conv(self.conv3, self.bn3)
+
+        def launch(keep=(pc2, pc3)):
+            _lib.call("up_bneck_tail_fwd", ctypes.byref(d), t1.ptr(), ops._ptr(pc2.w), ops._ptr(pc2.shift), ops._ptr(pc3.w),
+                      ops._ptr(pc3.shift), res.ptr(), out.ptr(), ops._stream())
+        b.add(launch, "bottleneck.tail")
+        return True
 
 
 class ResNet(PlanModule):
