@@ -1,0 +1,48 @@
+"""Where does the training step go?  One eager step (no CUDA graphs) with a CUDA-event pair around every C-ABI call,
+aggregated per entry point (in-order single stream: the sum is the step minus launch gaps and torch-side ops)."""
+import collections, os, sys, warnings
+os.environ["UNIPOSE_B200_TRAIN_GRAPH"] = "0"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from unipose_b200 import _lib, synth, train
+from unipose_b200.model.unipose import unipose
+
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    m = unipose(dataset="MPII", num_classes=16, precision="bf16")
+synth.trained_like_init_(m, 0)
+m = m.cuda().train()
+x = synth.mpii_like_input(32, 384, 384).cuda()
+t = torch.rand(32, 17, 48, 48, device="cuda")
+ts = train.TrainStep(m)
+for _ in range(2):
+    ts.step(x, t)
+torch.cuda.synchronize()
+records = []
+orig = _lib.call
+
+
+def timed(name, *args):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    orig(name, *args)
+    b.record()
+    records.append((name, a, b))
+
+
+_lib.call = timed
+train.ops._lib.call = timed
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+ts.step(x, t)
+e1.record()
+torch.cuda.synchronize()
+agg = collections.OrderedDict()
+for name, a, b in records:
+    d = agg.setdefault(name, [0, 0.0])
+    d[0] += 1
+    d[1] += a.elapsed_time(b)
+tot = sum(v[1] for v in agg.values())
+print("eager step %.2f ms wall (events), %.2f ms inside %d C-ABI calls" % (e0.elapsed_time(e1), tot, len(records)))
+for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print("%-28s %5d calls %8.3f ms %5.1f%%" % (name, n, ms, 100 * ms / tot))

@@ -722,8 +722,13 @@ static inline int blocks_for(long long total) { return static_cast<int>((total +
 // Per-channel reductions: blocks of 512 threads, ~16 pixel-octets per thread (4 iterations of 4 loads in flight), at
 // most kBnRows = 296 blocks (2 per SM).  Block b writes its partial sums to row b of the work buffer.
 constexpr int kBnRows = 296;
+#ifndef UP_RED_PER_THREAD
+#define UP_RED_PER_THREAD 4
+#endif
 static inline int reduce_grid(long long npix, int octs) {
-  long long g = (npix * octs + 512LL * 16 - 1) / (512LL * 16);
+  // UP_RED_PER_THREAD octets per thread: 16 left the 24x24 / 48x48 layers (two thirds of the BatchNorms) with 36-72
+  // blocks on 148 SMs
+  long long g = (npix * octs + 512LL * UP_RED_PER_THREAD - 1) / (512LL * UP_RED_PER_THREAD);
   if (g > kBnRows) g = kBnRows;
   if (g < 1) g = 1;
   return static_cast<int>(g);
