@@ -19,6 +19,7 @@ for _ in range(2):
     ts.step(x, t)
 torch.cuda.synchronize()
 records = []
+rec_args = []
 orig = _lib.call
 
 
@@ -28,6 +29,7 @@ def timed(name, *args):
     orig(name, *args)
     b.record()
     records.append((name, a, b))
+    rec_args.append(args)
 
 
 _lib.call = timed
@@ -46,3 +48,25 @@ tot = sum(v[1] for v in agg.values())
 print("eager step %.2f ms wall (events), %.2f ms inside %d C-ABI calls" % (e0.elapsed_time(e1), tot, len(records)))
 for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print("%-28s %5d calls %8.3f ms %5.1f%%" % (name, n, ms, 100 * ms / tot))
+
+# per layer shape for the streaming BatchNorm kernels: effective bandwidth over the ALGORITHMIC bytes (2 B per element
+# per tensor touched)
+SHAPE = {"up_bn_stats": lambda a: (a[1], a[2], 1),
+         "up_scale_shift_act": lambda a: (a[6], a[7], 2 + (a[2] is not None) + (a[3] is not None)),
+         "up_bn_bwd_reduce": lambda a: (a[5], a[6], 2 + (1 if a[7] else 0)),
+         "up_bn_bwd_apply": lambda a: (a[9], a[11], 3 + (1 if a[12] & 1 else 0) + (a[4] is not None))}
+if "--shapes" in sys.argv:
+    for kname in SHAPE:
+        by = collections.OrderedDict()
+        for (name, a, b), args in zip(records, rec_args):
+            if name != kname:
+                continue
+            npix, c, tensors = SHAPE[kname](args)
+            d = by.setdefault((npix, c, tensors), [0, 0.0])
+            d[0] += 1
+            d[1] += a.elapsed_time(b)
+        print("\n%s" % kname)
+        for (npix, c, tensors), (n, ms) in sorted(by.items(), key=lambda kv: -kv[1][1]):
+            gb = npix * c * 2 * tensors / 1e9
+            print("  npix %8d c %5d tensors %d : %3d calls %7.1f us each %7.3f ms total  %6.0f GB/s" %
+                  (npix, c, tensors, n, 1e3 * ms / n, ms, gb / (ms / n * 1e-3)))

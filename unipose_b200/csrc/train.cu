@@ -88,24 +88,56 @@ extern "C" int up_adam_step(float* param, const float* grad, float* exp_avg, flo
 // =============================================================================================
 namespace up {
 
+// A loaded channel octet stays packed (4 registers, 8 in split mode) until it is used: the streaming kernels below keep
+// several octets per thread in flight, and 8 converted floats per octet would halve the occupancy.
 template <int kMode>
-__device__ __forceinline__ void t_load8(const uint16_t* p, long long plane, float (&v)[8]) {
-  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+struct Raw8 {
+  uint4 h, l;   // l: the low plane of the bf16 pair format (unused otherwise)
+};
+
+template <int kMode>
+__device__ __forceinline__ Raw8<kMode> t_load_raw(const uint16_t* p, long long plane) {
+  Raw8<kMode> r;
+  r.h = __ldg(reinterpret_cast<const uint4*>(p));
+  if constexpr (kMode == 2) r.l = __ldg(reinterpret_cast<const uint4*>(p + plane));
+  else r.l = make_uint4(0, 0, 0, 0);
+  return r;
+}
+
+template <int kMode>
+__device__ __forceinline__ Raw8<kMode> raw_zero() {
+  Raw8<kMode> r;
+  r.h = make_uint4(0, 0, 0, 0);
+  r.l = r.h;
+  return r;
+}
+
+template <int kMode>
+__device__ __forceinline__ void t_cvt8(const Raw8<kMode>& r, float (&v)[8]) {
+  const uint32_t w[4] = {r.h.x, r.h.y, r.h.z, r.h.w};
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     v[2 * e + 0] = cvt16_to_f32<(kMode == 0 ? 0 : 1)>(static_cast<uint16_t>(w[e] & 0xFFFFu));
     v[2 * e + 1] = cvt16_to_f32<(kMode == 0 ? 0 : 1)>(static_cast<uint16_t>(w[e] >> 16));
   }
   if constexpr (kMode == 2) {
-    const uint4 l = __ldg(reinterpret_cast<const uint4*>(p + plane));
-    const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+    const uint32_t lw[4] = {r.l.x, r.l.y, r.l.z, r.l.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       v[2 * e + 0] += cvt16_to_f32<1>(static_cast<uint16_t>(lw[e] & 0xFFFFu));
       v[2 * e + 1] += cvt16_to_f32<1>(static_cast<uint16_t>(lw[e] >> 16));
     }
   }
+}
+
+template <int kMode>
+__device__ __forceinline__ void t_load8(const uint16_t* p, long long plane, float (&v)[8]) {
+  t_cvt8<kMode>(t_load_raw<kMode>(p, plane), v);
+}
+
+__device__ __forceinline__ void load_f8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
 }
 
 template <int kMode>
@@ -163,48 +195,48 @@ __global__ void __launch_bounds__(512)
   const long long per_block = (npix + gridDim.x - 1) / gridDim.x;
   const long long p0 = blockIdx.x * per_block;
   const long long p1 = min(p0 + per_block, npix);
-  // pixels in flight per thread: the loads of one iteration are all issued before any use (the three-operand backward
-  // reduction would spill at 4 within the 128-register budget of a 512-thread block)
+  // pixels in flight per thread: the loads of one iteration are all issued before any use and stay packed until then
+  // (measured with tools/bn_microbench.cu: 4 in flight, 512 threads: 5.0-6.4 TB/s on the three-tensor reduction)
 #ifndef UP_RED_UNROLL
-#define UP_RED_UNROLL 2      // measured on B200: 2 (no spills) 29.1 ms/step vs 4 (spills) 29.5
+#define UP_RED_UNROLL 4
 #endif
-  constexpr int kUnroll = kWhat == 1 ? UP_RED_UNROLL : 4;
+  constexpr int kUnroll = kMode == 2 ? 2 : UP_RED_UNROLL;
   for (long long px0 = p0 + plane_lane; px0 < p1; px0 += static_cast<long long>(kUnroll) * pstride) {
-    float va[kUnroll][8], vz[kUnroll][8], vy[kUnroll][8];
+    Raw8<kMode> ra[kUnroll], rz[kUnroll], ry[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const long long px = px0 + static_cast<long long>(u) * pstride;
+      ra[u] = raw_zero<kMode>();     // a zero octet adds nothing to either sum
+      rz[u] = ra[u];
+      ry[u] = ra[u];
       if (px < p1) {
-        t_load8<kMode>(a.p + px * a.cs + a.coff + oct * 8, a.plane, va[u]);
+        ra[u] = t_load_raw<kMode>(a.p + px * a.cs + a.coff + oct * 8, a.plane);
         if (kWhat == 1) {
-          t_load8<kMode>(c.p + px * c.cs + c.coff + oct * 8, c.plane, vz[u]);
-          if (relu) t_load8<kMode>(b.p + px * b.cs + b.coff + oct * 8, b.plane, vy[u]);
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          va[u][e] = 0.f;
-          vz[u][e] = 0.f;
-          vy[u][e] = 1.f;
+          rz[u] = t_load_raw<kMode>(c.p + px * c.cs + c.coff + oct * 8, c.plane);
+          if (relu) ry[u] = t_load_raw<kMode>(b.p + px * b.cs + b.coff + oct * 8, b.plane);
         }
       }
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
+      float va[8];
+      t_cvt8<kMode>(ra[u], va);
       if (kWhat == 0) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          s0[e] += va[u][e];
-          s1[e] = fmaf(va[u][e], va[u][e], s1[e]);
+          s0[e] += va[e];
+          s1[e] = fmaf(va[e], va[e], s1[e]);
         }
       } else {
-        const bool live = px0 + static_cast<long long>(u) * pstride < p1;
+        float vz[8], vy[8];
+        t_cvt8<kMode>(rz[u], vz);
+        if (relu) t_cvt8<kMode>(ry[u], vy);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          float d = va[u][e];
-          if (relu) d = vy[u][e] > 0.f ? d : 0.f;
+          float d = va[e];
+          if (relu) d = vy[e] > 0.f ? d : 0.f;
           s0[e] += d;
-          s1[e] = fmaf(d, live ? (vz[u][e] - mu[e]) * is[e] : 0.f, s1[e]);
+          s1[e] = fmaf(d, (vz[e] - mu[e]) * is[e], s1[e]);
         }
       }
     }
@@ -277,92 +309,150 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 // y = [relu]( z * scale[c] + shift[c] (+ res) ) (* mask)
 // kElemUnroll octets per thread, `stride` (= total threads) apart, all loads issued before the first use.  More than one
 // octet per thread measured SLOWER on B200 (occupancy drops faster than memory-level parallelism rises): default 1.
-#ifndef UP_ELEM_UNROLL
-#define UP_ELEM_UNROLL 1     // measured on B200 (training step): 1 -> 29.1 ms, 2 -> 30.9 ms, 4 -> 36.3 ms
-#endif
-constexpr int kElemUnroll = UP_ELEM_UNROLL;
+// The two streaming BatchNorm maps come in two forms.  "fast": c/8 is a power of two <= 256, so a block of 256 threads
+// owning 256*kU consecutive octets gives every thread ONE channel octet for all its kU octets: the per-channel
+// constants are loaded once into registers, the kU loads per tensor are issued back to back and stay packed.
+// Measured (tools/bn_microbench.cu, bf16, B200): 5.8-6.9 TB/s against 1.7-2.9 TB/s for the one-octet-per-thread form,
+// whose 16 scalar constant loads per octet were the bottleneck.  "generic": any c % 8 == 0, one octet per thread.
+template <int kMode, int kU>
+__global__ void __launch_bounds__(256)
+    scale_shift_act_fast_kernel(TView z, TViewW y, TView res, TView mask, const float* __restrict__ scale,
+                                const float* __restrict__ shift, long long total, int lg, int relu, int has_res,
+                                int has_mask) {
+  const int g = threadIdx.x & ((1 << lg) - 1);
+  const long long base = blockIdx.x * (256LL * kU) + threadIdx.x;
+  Raw8<kMode> rz[kU], rr[kU], rm[kU];
+#pragma unroll
+  for (int u = 0; u < kU; ++u) {
+    const long long i = base + u * 256;
+    if (i < total) {
+      const long long px = i >> lg;
+      rz[u] = t_load_raw<kMode>(z.p + px * z.cs + z.coff + g * 8, z.plane);
+      if (has_res) rr[u] = t_load_raw<kMode>(res.p + px * res.cs + res.coff + g * 8, res.plane);
+      if (has_mask) rm[u] = t_load_raw<kMode>(mask.p + px * mask.cs + mask.coff + g * 8, mask.plane);
+    }
+  }
+  float sc[8], sh[8];
+  load_f8(scale + g * 8, sc);
+  load_f8(shift + g * 8, sh);
+#pragma unroll
+  for (int u = 0; u < kU; ++u) {
+    const long long i = base + u * 256;
+    if (i < total) {
+      float v[8], r[8], m[8];
+      t_cvt8<kMode>(rz[u], v);
+      if (has_res) t_cvt8<kMode>(rr[u], r);
+      if (has_mask) t_cvt8<kMode>(rm[u], m);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float t = fmaf(v[e], sc[e], sh[e]);
+        if (has_res) t += r[e];
+        if (relu) t = fmaxf(t, 0.f);
+        if (has_mask) t *= m[e];
+        v[e] = t;
+      }
+      t_store8<kMode>(y.p + (i >> lg) * y.cs + y.coff + g * 8, y.plane, v);
+    }
+  }
+}
+
 template <int kMode>
 __global__ void scale_shift_act_kernel(TView z, TViewW y, TView res, TView mask, const float* __restrict__ scale,
                                        const float* __restrict__ shift, long long npix, int ch, int relu, int has_res,
                                        int has_mask) {
   const int c8 = ch / 8;
-  const long long total = npix * c8;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  float v[kElemUnroll][8], r[kElemUnroll][8], m[kElemUnroll][8];
-  int g[kElemUnroll];
-  long long px[kElemUnroll];
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= npix * c8) return;
+  const int g = static_cast<int>(i % c8);
+  const long long px = i / c8;
+  float v[8], r[8], m[8], sc[8], sh[8];
+  t_load8<kMode>(z.p + px * z.cs + z.coff + g * 8, z.plane, v);
+  if (has_res) t_load8<kMode>(res.p + px * res.cs + res.coff + g * 8, res.plane, r);
+  if (has_mask) t_load8<kMode>(mask.p + px * mask.cs + mask.coff + g * 8, mask.plane, m);
+  load_f8(scale + g * 8, sc);
+  load_f8(shift + g * 8, sh);
 #pragma unroll
-  for (int u = 0; u < kElemUnroll; ++u) {
-    const long long i = i0 + u * stride;
-    if (i >= total) continue;
-    g[u] = static_cast<int>(i % c8);
-    px[u] = i / c8;
-    t_load8<kMode>(z.p + px[u] * z.cs + z.coff + g[u] * 8, z.plane, v[u]);
-    if (has_res) t_load8<kMode>(res.p + px[u] * res.cs + res.coff + g[u] * 8, res.plane, r[u]);
-    if (has_mask) t_load8<kMode>(mask.p + px[u] * mask.cs + mask.coff + g[u] * 8, mask.plane, m[u]);
+  for (int e = 0; e < 8; ++e) {
+    float t = fmaf(v[e], sc[e], sh[e]);
+    if (has_res) t += r[e];
+    if (relu) t = fmaxf(t, 0.f);
+    if (has_mask) t *= m[e];
+    v[e] = t;
   }
-#pragma unroll
-  for (int u = 0; u < kElemUnroll; ++u) {
-    const long long i = i0 + u * stride;
-    if (i >= total) continue;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float t = fmaf(v[u][e], scale[g[u] * 8 + e], shift[g[u] * 8 + e]);
-      if (has_res) t += r[u][e];
-      if (relu) t = fmaxf(t, 0.f);
-      if (has_mask) t *= m[u][e];
-      v[u][e] = t;
-    }
-    t_store8<kMode>(y.p + px[u] * y.cs + y.coff + g[u] * 8, y.plane, v[u]);
-  }
+  t_store8<kMode>(y.p + px * y.cs + y.coff + g * 8, y.plane, v);
 }
 
 // dz = gamma*invstd * ( dy' - sum_dy/M - xhat * sum_dy_xhat/M ),  dy' = dy * (y > 0 if relu);  optional dres = dy'
 // The per-channel part is folded once (bn_bwd_coef_kernel, double arithmetic) into dz = k1*dy' + k2*z + k3.
 template <int kMode>
+__device__ __forceinline__ void bn_bwd_apply_octet(const Raw8<kMode>& rd, const Raw8<kMode>& rz, const Raw8<kMode>& ry,
+                                                   const float (&k1)[8], const float (&k2)[8], const float (&k3)[8],
+                                                   int relu, int has_dres, uint16_t* dzp, long long dz_plane,
+                                                   uint16_t* drp, long long dr_plane) {
+  float vd[8], vz[8], vy[8], o[8];
+  t_cvt8<kMode>(rd, vd);
+  t_cvt8<kMode>(rz, vz);
+  if (relu) {
+    t_cvt8<kMode>(ry, vy);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) vd[e] = vy[e] > 0.f ? vd[e] : 0.f;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = fmaf(k1[e], vd[e], fmaf(k2[e], vz[e], k3[e]));
+  t_store8<kMode>(dzp, dz_plane, o);
+  if (has_dres) t_store8<kMode>(drp, dr_plane, vd);
+}
+
+template <int kMode, int kU>
+__global__ void __launch_bounds__(256)
+    bn_bwd_apply_fast_kernel(TView dy, TView y, TView z, TViewW dz, TViewW dres, const float* __restrict__ coef,
+                             long long total, int lg, int ch, int relu, int has_dres) {
+  const int g = threadIdx.x & ((1 << lg) - 1);
+  const long long base = blockIdx.x * (256LL * kU) + threadIdx.x;
+  Raw8<kMode> rd[kU], rz[kU], ry[kU];
+#pragma unroll
+  for (int u = 0; u < kU; ++u) {
+    const long long i = base + u * 256;
+    if (i < total) {
+      const long long px = i >> lg;
+      rd[u] = t_load_raw<kMode>(dy.p + px * dy.cs + dy.coff + g * 8, dy.plane);
+      rz[u] = t_load_raw<kMode>(z.p + px * z.cs + z.coff + g * 8, z.plane);
+      if (relu) ry[u] = t_load_raw<kMode>(y.p + px * y.cs + y.coff + g * 8, y.plane);
+    }
+  }
+  float k1[8], k2[8], k3[8];
+  load_f8(coef + g * 8, k1);
+  load_f8(coef + ch + g * 8, k2);
+  load_f8(coef + 2 * ch + g * 8, k3);
+#pragma unroll
+  for (int u = 0; u < kU; ++u) {
+    const long long i = base + u * 256;
+    if (i < total) {
+      const long long px = i >> lg;
+      bn_bwd_apply_octet<kMode>(rd[u], rz[u], ry[u], k1, k2, k3, relu, has_dres, dz.p + px * dz.cs + dz.coff + g * 8,
+                                dz.plane, has_dres ? dres.p + px * dres.cs + dres.coff + g * 8 : nullptr, dres.plane);
+    }
+  }
+}
+
+template <int kMode>
 __global__ void bn_bwd_apply_kernel(TView dy, TView y, TView z, TViewW dz, TViewW dres, const float* __restrict__ coef,
                                     long long npix, int ch, int relu, int has_dres) {
   const int c8 = ch / 8;
-  const long long total = npix * c8;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  float vd[kElemUnroll][8], vz[kElemUnroll][8], vy[kElemUnroll][8];
-  int g[kElemUnroll];
-  long long px[kElemUnroll];
-#pragma unroll
-  for (int u = 0; u < kElemUnroll; ++u) {
-    const long long i = i0 + u * stride;
-    if (i >= total) continue;
-    g[u] = static_cast<int>(i % c8);
-    px[u] = i / c8;
-    t_load8<kMode>(dy.p + px[u] * dy.cs + dy.coff + g[u] * 8, dy.plane, vd[u]);
-    t_load8<kMode>(z.p + px[u] * z.cs + z.coff + g[u] * 8, z.plane, vz[u]);
-    if (relu) t_load8<kMode>(y.p + px[u] * y.cs + y.coff + g[u] * 8, y.plane, vy[u]);
-  }
-#pragma unroll
-  for (int u = 0; u < kElemUnroll; ++u) {
-    const long long i = i0 + u * stride;
-    if (i >= total) continue;
-    float o[8];
-    if (relu) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) vd[u][e] = vy[u][e] > 0.f ? vd[u][e] : 0.f;
-    }
-    const float4* k1 = reinterpret_cast<const float4*>(coef + g[u] * 8);
-    const float4* k2 = reinterpret_cast<const float4*>(coef + ch + g[u] * 8);
-    const float4* k3 = reinterpret_cast<const float4*>(coef + 2 * ch + g[u] * 8);
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const float4 a = __ldg(k1 + q), b = __ldg(k2 + q), c = __ldg(k3 + q);
-      o[4 * q + 0] = fmaf(a.x, vd[u][4 * q + 0], fmaf(b.x, vz[u][4 * q + 0], c.x));
-      o[4 * q + 1] = fmaf(a.y, vd[u][4 * q + 1], fmaf(b.y, vz[u][4 * q + 1], c.y));
-      o[4 * q + 2] = fmaf(a.z, vd[u][4 * q + 2], fmaf(b.z, vz[u][4 * q + 2], c.z));
-      o[4 * q + 3] = fmaf(a.w, vd[u][4 * q + 3], fmaf(b.w, vz[u][4 * q + 3], c.w));
-    }
-    t_store8<kMode>(dz.p + px[u] * dz.cs + dz.coff + g[u] * 8, dz.plane, o);
-    if (has_dres) t_store8<kMode>(dres.p + px[u] * dres.cs + dres.coff + g[u] * 8, dres.plane, vd[u]);
-  }
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= npix * c8) return;
+  const int g = static_cast<int>(i % c8);
+  const long long px = i / c8;
+  const Raw8<kMode> rd = t_load_raw<kMode>(dy.p + px * dy.cs + dy.coff + g * 8, dy.plane);
+  const Raw8<kMode> rz = t_load_raw<kMode>(z.p + px * z.cs + z.coff + g * 8, z.plane);
+  Raw8<kMode> ry = rd;
+  if (relu) ry = t_load_raw<kMode>(y.p + px * y.cs + y.coff + g * 8, y.plane);
+  float k1[8], k2[8], k3[8];
+  load_f8(coef + g * 8, k1);
+  load_f8(coef + ch + g * 8, k2);
+  load_f8(coef + 2 * ch + g * 8, k3);
+  bn_bwd_apply_octet<kMode>(rd, rz, ry, k1, k2, k3, relu, has_dres, dz.p + px * dz.cs + dz.coff + g * 8, dz.plane,
+                            has_dres ? dres.p + px * dres.cs + dres.coff + g * 8 : nullptr, dres.plane);
 }
 
 // k1 = gamma*invstd, k2 = -k1*invstd*m1, k3 = -k1*m0 - k2*mean with m0 = sum_dy/M, m1 = sum_dy_xhat/M; padded
@@ -723,7 +813,7 @@ static inline int blocks_for(long long total) { return static_cast<int>((total +
 // most kBnRows = 296 blocks (2 per SM).  Block b writes its partial sums to row b of the work buffer.
 constexpr int kBnRows = 296;
 #ifndef UP_RED_PER_THREAD
-#define UP_RED_PER_THREAD 4
+#define UP_RED_PER_THREAD 8
 #endif
 static inline int reduce_grid(long long npix, int octs) {
   // UP_RED_PER_THREAD octets per thread: 16 left the 24x24 / 48x48 layers (two thirds of the BatchNorms) with 36-72
@@ -808,9 +898,23 @@ extern "C" int up_scale_shift_act(const UpView* z, const UpView* y, const UpView
   if (residual && (rc = check_view("up_scale_shift_act(residual)", residual, c))) return rc;
   if (mask && (rc = check_view("up_scale_shift_act(mask)", mask, c))) return rc;
   UP_CHECK_ARG(scale && shift && npix > 0, "up_scale_shift_act: bad argument");
-  UP_T_DISPATCH(dtype, (up::scale_shift_act_kernel<kMode><<<blocks_for((npix*(c / 8) + up::kElemUnroll - 1) / up::kElemUnroll), 256, 0, (cudaStream_t)stream>>>(
-                           tv(z), tvw(y), tv(residual), tv(mask), scale, shift, npix, c, relu, residual != nullptr,
-                           mask != nullptr)));
+  const int c8 = c / 8;
+  const long long total = npix * c8;
+  if (c8 <= 256 && (c8 & (c8 - 1)) == 0) {
+    int lg = 0;
+    while ((1 << lg) < c8) ++lg;
+    UP_T_DISPATCH(dtype, ({
+                    constexpr int kU = kMode == 2 ? 2 : 4;
+                    up::scale_shift_act_fast_kernel<kMode, kU>
+                        <<<static_cast<unsigned>((total + 256 * kU - 1) / (256 * kU)), 256, 0, (cudaStream_t)stream>>>(
+                            tv(z), tvw(y), tv(residual), tv(mask), scale, shift, total, lg, relu, residual != nullptr,
+                            mask != nullptr);
+                  }));
+  } else {
+    UP_T_DISPATCH(dtype, (up::scale_shift_act_kernel<kMode><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
+                             tv(z), tvw(y), tv(residual), tv(mask), scale, shift, npix, c, relu, residual != nullptr,
+                             mask != nullptr)));
+  }
   UP_CHECK_LAUNCH("scale_shift_act_kernel");
   return 0;
 }
@@ -858,8 +962,19 @@ extern "C" int up_bn_bwd_apply(const UpView* dy, const UpView* y, const UpView* 
   up::bn_bwd_coef_kernel<<<(c + 127) / 128, 128, 0, st>>>(sums, static_cast<double>(npix), save_mean, save_invstd, gamma,
                                                            coef, c_real, c, frozen);
   UP_CHECK_LAUNCH("bn_bwd_coef_kernel");
-  UP_T_DISPATCH(dtype, (up::bn_bwd_apply_kernel<kMode><<<blocks_for((npix*(c / 8) + up::kElemUnroll - 1) / up::kElemUnroll), 256, 0, st>>>(
-                           tv(dy), tv(y), tv(z), tvw(dz), tvw(dres), coef, npix, c, relu, dres != nullptr)));
+  const int c8 = c / 8;
+  const long long total = npix * c8;
+  if (c8 <= 256 && (c8 & (c8 - 1)) == 0) {
+    int lg = 0;
+    while ((1 << lg) < c8) ++lg;
+    constexpr int kU = 2;
+    UP_T_DISPATCH(dtype, (up::bn_bwd_apply_fast_kernel<kMode, kU>
+                          <<<static_cast<unsigned>((total + 256 * kU - 1) / (256 * kU)), 256, 0, st>>>(
+                              tv(dy), tv(y), tv(z), tvw(dz), tvw(dres), coef, total, lg, c, relu & 1, dres != nullptr)));
+  } else {
+    UP_T_DISPATCH(dtype, (up::bn_bwd_apply_kernel<kMode><<<blocks_for(total), 256, 0, st>>>(
+                             tv(dy), tv(y), tv(z), tvw(dz), tvw(dres), coef, npix, c, relu & 1, dres != nullptr)));
+  }
   UP_CHECK_LAUNCH("bn_bwd_apply_kernel");
   if (dgamma && dbeta) {
     up::bn_bwd_params_kernel<<<(c_real + 127) / 128, 128, 0, st>>>(sums, dgamma, dbeta, c_real, c);
