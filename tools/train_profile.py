@@ -20,6 +20,7 @@ for _ in range(2):
 torch.cuda.synchronize()
 records = []
 rec_args = []
+rec_snap = []
 orig = _lib.call
 
 
@@ -30,6 +31,11 @@ def timed(name, *args):
     b.record()
     records.append((name, a, b))
     rec_args.append(args)
+    snap = None
+    if name in ("up_conv2d_fwd", "up_conv2d_wgrad"):
+        d = args[0]._obj        # ctypes.byref(desc): the descriptor is reused by the caller, so copy the geometry now
+        snap = (d.n, d.h, d.w, d.ho, d.wo, d.cin, d.cout, d.kh, d.kw, d.stride, d.dil, d.flags)
+    rec_snap.append(snap)
 
 
 _lib.call = timed
@@ -70,3 +76,20 @@ if "--shapes" in sys.argv:
             gb = npix * c * 2 * tensors / 1e9
             print("  npix %8d c %5d tensors %d : %3d calls %7.1f us each %7.3f ms total  %6.0f GB/s" %
                   (npix, c, tensors, n, 1e3 * ms / n, ms, gb / (ms / n * 1e-3)))
+
+# convolutions by geometry: executed FLOPs (2 * n*ho*wo * cout * cin*kh*kw) and TFLOP/s
+if "--convs" in sys.argv:
+    for kname in ("up_conv2d_fwd", "up_conv2d_wgrad"):
+        by = collections.OrderedDict()
+        for (name, a, b), args in zip(records, rec_snap):
+            if name != kname:
+                continue
+            d = by.setdefault(args, [0, 0.0])
+            d[0] += 1
+            d[1] += a.elapsed_time(b)
+        print("\n%s   (n h w -> ho wo | cin cout k stride dil | flags)" % kname)
+        for key, (n, ms) in sorted(by.items(), key=lambda kv: -kv[1][1]):
+            nb, h, w, ho, wo, cin, cout, kh, kw, stride, dil, flags = key
+            fl = 2.0 * nb * ho * wo * cout * cin * kh * kw
+            print("  %3d %3dx%3d -> %3dx%3d | %4d -> %4d k%d s%d d%2d | f%3d : %3d calls %7.1f us each %7.3f ms  %6.0f TFLOP/s" %
+                  (nb, h, w, ho, wo, cin, cout, kh, stride, dil, flags, n, 1e3 * ms / n, ms, fl / (ms / n * 1e-3) / 1e12))
