@@ -401,25 +401,30 @@ int up_bn_stats(const UpView* z, int64_t npix, int c, int dtype, double* work, v
 int up_bn_finalize(const double* sums, int64_t count, const float* gamma, const float* beta, float* running_mean,
                    float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
                    float* save_invstd, int c_real, int c, void* stream);
+/* up_bn_stats + up_bn_finalize over the same npix pixels in two launches instead of three (the partial rows are
+ * reduced and turned into the epilogue constants by one kernel); bit-identical to the two calls. */
+int up_bn_stats_finalize(const UpView* z, int64_t npix, int c, int dtype, double* work, const float* gamma,
+                         const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                         float* scale, float* shift, float* save_mean, float* save_invstd, int c_real, void* stream);
 /* Frozen (eval-mode) BatchNorm inside a training step - the reference's freeze_bn=True / model.freeze_bn()
  * (model/unipose.py:24-25,40-43): scale/shift from the RUNNING statistics, plus save_mean = running_mean and
- * save_invstd = 1/sqrt(running_var + eps) for the backward (up_bn_bwd_reduce / up_bn_bwd_apply with relu | 2). */
+ * save_invstd = 1/sqrt(running_var + eps) for the backward (up_bn_bwd with flags | 2). */
 int up_bn_eval_prepare(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                        float eps, float* scale, float* shift, float* save_mean, float* save_invstd, int c_real, int c,
                        void* stream);
 int up_scale_shift_act(const UpView* z, const UpView* y, const UpView* residual, const UpView* mask,
                        const float* scale, const float* shift, int64_t npix, int c, int relu, int dtype,
                        void* stream);
-/* BatchNorm (+ReLU) backward: reduce sum(dy'), sum(dy'*xhat) with dy' = dy*(y>0) -> work[0 .. 2*c); then
- *   dz = gamma*invstd*(dy' - sum_dy/M - xhat*sum_dy_xhat/M), optional dres = dy', dgamma / dbeta (optional).
- * `work` holds up_bn_work_doubles(c) doubles (see up_bn_stats).
- * `relu` is a bit mask: 1 = gate by the forward output (y > 0); 2 (up_bn_bwd_apply only) = frozen BatchNorm, whose
- * statistics are constants: dz = gamma*invstd*dy' (dgamma / dbeta unchanged). */
-int up_bn_bwd_reduce(const UpView* dy, const UpView* y, const UpView* z, const float* save_mean,
-                     const float* save_invstd, int64_t npix, int c, int relu, int dtype, double* work, void* stream);
-int up_bn_bwd_apply(const UpView* dy, const UpView* y, const UpView* z, const UpView* dz, const UpView* dres,
-                    const float* save_mean, const float* save_invstd, const float* gamma, double* work,
-                    int64_t npix, int c_real, int c, int relu, int dtype, float* dgamma, float* dbeta, void* stream);
+/* BatchNorm (+ReLU) backward (autograd of nn.BatchNorm2d + nn.ReLU, reference call site unipose.py:123), three
+ * launches: reduce sum(dy'), sum(dy'*xhat) with dy' = dy*(y>0) into one partial row per block; rows -> work[0 .. 2*c)
+ * -> per-channel coefficients (+ dgamma / dbeta, optional, both or neither); then
+ *   dz = gamma*invstd*(dy' - sum_dy/M - xhat*sum_dy_xhat/M), optional dres = dy'.
+ * `work` holds up_bn_work_doubles(c) doubles (see up_bn_stats); c/8 must be a power of two <= 256.
+ * `flags` is a bit mask: 1 = gate by the forward output (y > 0); 2 = frozen BatchNorm, whose statistics are
+ * constants: dz = gamma*invstd*dy' (dgamma / dbeta are still the two sums). */
+int up_bn_bwd(const UpView* dy, const UpView* y, const UpView* z, const UpView* dz, const UpView* dres,
+              const float* save_mean, const float* save_invstd, const float* gamma, double* work, int64_t npix,
+              int c_real, int c, int flags, int dtype, float* dgamma, float* dbeta, void* stream);
 /* out (+)= a            (mode_op 0)
  * out (+)= a * m        (mode_op 1, dropout mask)
  * out (+)= a * (m > 0)  (mode_op 2, ReLU gate with the forward output m) */

@@ -138,6 +138,18 @@ def test_batchnorm_train_forward_backward(prec, c, relu, res):
     rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
     ops.bn_stats(za, c, sums)
     ops.bn_finalize(sums, n * h * w, bn, scale, shift, mean, invstd, c, c)
+    # the two-launch form the training plan uses: same numbers, bit for bit (same reduction order)
+    bn2 = torch.nn.BatchNorm2d(c).to(dev)
+    bn2.load_state_dict(bn.state_dict())
+    with torch.no_grad():
+        bn2.running_mean.copy_(rm0)
+        bn2.running_var.copy_(rv0)
+    sums2 = torch.zeros_like(sums)
+    scale2, shift2, mean2, invstd2 = (torch.empty(c, device=dev) for _ in range(4))
+    ops.bn_stats_finalize(za, sums2, bn2, scale2, shift2, mean2, invstd2, c, c)
+    for a, b in ((scale, scale2), (shift, shift2), (mean, mean2), (invstd, invstd2),
+                 (bn.running_mean, bn2.running_mean), (bn.running_var, bn2.running_var), (sums[:2 * c], sums2[:2 * c])):
+        assert torch.equal(a, b)
     ya = ops.Act(n, h, w, c, mode, dev)
     ops.scale_shift_act(za, ya, scale, shift, relu=relu, residual=ra if res else None)
     # reference: F.batch_norm in training mode on the same (quantised) input, fp64

@@ -57,10 +57,9 @@ for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 
 # per layer shape for the streaming BatchNorm kernels: effective bandwidth over the ALGORITHMIC bytes (2 B per element
 # per tensor touched)
-SHAPE = {"up_bn_stats": lambda a: (a[1], a[2], 1),
+SHAPE = {"up_bn_stats_finalize": lambda a: (a[1], a[2], 1),
          "up_scale_shift_act": lambda a: (a[6], a[7], 2 + (a[2] is not None) + (a[3] is not None)),
-         "up_bn_bwd_reduce": lambda a: (a[5], a[6], 2 + (1 if a[7] else 0)),
-         "up_bn_bwd_apply": lambda a: (a[9], a[11], 3 + (1 if a[12] & 1 else 0) + (a[4] is not None))}
+         "up_bn_bwd": lambda a: (a[9], a[11], 5 + 2 * (a[12] & 1) + (a[4] is not None))}
 if "--shapes" in sys.argv:
     for kname in SHAPE:
         by = collections.OrderedDict()

@@ -111,10 +111,10 @@ _SIGNATURES = {
     "up_conv2d_wgrad": [POINTER(UpConvDesc), _P, _P, _P, _I, _I, _P, _L, _I, _P],
     "up_bn_stats": [_P, _L, _I, _I, _P, _P],
     "up_bn_finalize": [_P, _L, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _I, _I, _P],
+    "up_bn_stats_finalize": [_P, _L, _I, _I, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _I, _P],
     "up_bn_eval_prepare": [_P, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _P],
     "up_scale_shift_act": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
-    "up_bn_bwd_reduce": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _P, _P],
-    "up_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P, _P, _P],
+    "up_bn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P, _P, _P],
     "up_ew_mul": [_P, _P, _P, _L, _I, _I, _I, _I, _P],
     "up_maxpool3x3s2_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "up_upsample_bilinear_ac_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],

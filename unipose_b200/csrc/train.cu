@@ -277,32 +277,103 @@ __global__ void reduce_rows_kernel(const float* __restrict__ rows, int nrows, in
   }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
-                                   float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ save_mean, float* __restrict__ save_invstd, int c_real, int c) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c) return;
-  if (i >= c_real) {
-    scale[i] = 0.f;
-    shift[i] = 0.f;
-    save_mean[i] = 0.f;
-    save_invstd[i] = 0.f;
+struct BnFinalizeArgs {
+  double count;
+  const float *gamma, *beta;
+  float *rmean, *rvar;
+  float momentum, eps;
+  float *scale, *shift, *save_mean, *save_invstd;
+  int c_real, c;
+};
+
+__device__ __forceinline__ void bn_finalize_channel(int i, double sum, double sumsq, const BnFinalizeArgs& a) {
+  if (i >= a.c_real) {
+    a.scale[i] = 0.f;
+    a.shift[i] = 0.f;
+    a.save_mean[i] = 0.f;
+    a.save_invstd[i] = 0.f;
     return;
   }
-  const double mean = sums[i] / count;
-  double var = sums[c + i] / count - mean * mean;
+  const double mean = sum / a.count;
+  double var = sumsq / a.count - mean * mean;
   if (var < 0.0) var = 0.0;
-  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  const float sc = gamma[i] * invstd;
-  scale[i] = sc;
-  shift[i] = beta[i] - static_cast<float>(mean) * sc;
-  save_mean[i] = static_cast<float>(mean);
-  save_invstd[i] = invstd;
-  if (rmean) {
-    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-    rmean[i] = (1.f - momentum) * rmean[i] + momentum * static_cast<float>(mean);
-    rvar[i] = (1.f - momentum) * rvar[i] + momentum * static_cast<float>(unbiased);
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+  const float sc = a.gamma[i] * invstd;
+  a.scale[i] = sc;
+  a.shift[i] = a.beta[i] - static_cast<float>(mean) * sc;
+  a.save_mean[i] = static_cast<float>(mean);
+  a.save_invstd[i] = invstd;
+  if (a.rmean) {
+    const double unbiased = a.count > 1.0 ? var * a.count / (a.count - 1.0) : var;
+    a.rmean[i] = (1.f - a.momentum) * a.rmean[i] + a.momentum * static_cast<float>(mean);
+    a.rvar[i] = (1.f - a.momentum) * a.rvar[i] + a.momentum * static_cast<float>(unbiased);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const BnFinalizeArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.c) return;
+  bn_finalize_channel(i, sums[i], sums[a.c + i], a);
+}
+
+// k1 = gamma*invstd, k2 = -k1*invstd*m1, k3 = -k1*m0 - k2*mean with m0 = sum_dy/M, m1 = sum_dy_xhat/M; padded
+// channels get zeros.  coef = [k1 | k2 | k3], c floats each.
+// frozen (eval-mode BatchNorm inside a training step: the statistics are constants): dz = gamma*invstd*dy'.
+struct BnBwdCoefArgs {
+  double count;
+  const float *mean, *invstd, *gamma;
+  float *coef, *dgamma, *dbeta;
+  int c_real, c, frozen;
+};
+
+__device__ __forceinline__ void bn_bwd_coef_channel(int i, double sum_dy, double sum_dy_xhat, const BnBwdCoefArgs& a) {
+  double k1 = 0.0, k2 = 0.0, k3 = 0.0;
+  if (i < a.c_real) {
+    const double m0 = sum_dy / a.count, m1 = sum_dy_xhat / a.count;
+    k1 = static_cast<double>(a.gamma[i]) * a.invstd[i];
+    if (!a.frozen) {
+      k2 = -k1 * a.invstd[i] * m1;
+      k3 = -k1 * m0 - k2 * a.mean[i];
+    }
+    if (a.dgamma) {
+      a.dbeta[i] = static_cast<float>(sum_dy);
+      a.dgamma[i] = static_cast<float>(sum_dy_xhat);
+    }
+  }
+  a.coef[i] = static_cast<float>(k1);
+  a.coef[a.c + i] = static_cast<float>(k2);
+  a.coef[2 * a.c + i] = static_cast<float>(k3);
+}
+
+// The partial rows of a per-channel reduction -> the two sums of every channel (same order as reduce_rows_kernel) ->
+// what the streaming kernel that follows needs, in ONE launch: the forward statistics and epilogue constants
+// (kWhat 0) or the backward coefficients and dgamma / dbeta (kWhat 1).  blockDim = (32, 16).
+template <int kWhat, class Args>
+__global__ void bn_finish_kernel(const float* __restrict__ rows, int nrows, double* __restrict__ sums, const Args a) {
+  __shared__ double part[2][16][33];
+  const int c = a.c;
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  double s0 = 0.0, s1 = 0.0;
+  if (i < c) {
+    for (int r = threadIdx.y; r < nrows; r += 16) {
+      s0 += rows[static_cast<long long>(r) * 2 * c + i];
+      s1 += rows[static_cast<long long>(r) * 2 * c + c + i];
+    }
+  }
+  part[0][threadIdx.y][threadIdx.x] = s0;
+  part[1][threadIdx.y][threadIdx.x] = s1;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < c) {
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      t0 += part[0][q][threadIdx.x];
+      t1 += part[1][q][threadIdx.x];
+    }
+    sums[i] = t0;
+    sums[c + i] = t1;
+    if constexpr (kWhat == 0) bn_finalize_channel(i, t0, t1, a);
+    else bn_bwd_coef_channel(i, t0, t1, a);
   }
 }
 
@@ -433,56 +504,6 @@ __global__ void __launch_bounds__(256)
                                 dz.plane, has_dres ? dres.p + px * dres.cs + dres.coff + g * 8 : nullptr, dres.plane);
     }
   }
-}
-
-template <int kMode>
-__global__ void bn_bwd_apply_kernel(TView dy, TView y, TView z, TViewW dz, TViewW dres, const float* __restrict__ coef,
-                                    long long npix, int ch, int relu, int has_dres) {
-  const int c8 = ch / 8;
-  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (i >= npix * c8) return;
-  const int g = static_cast<int>(i % c8);
-  const long long px = i / c8;
-  const Raw8<kMode> rd = t_load_raw<kMode>(dy.p + px * dy.cs + dy.coff + g * 8, dy.plane);
-  const Raw8<kMode> rz = t_load_raw<kMode>(z.p + px * z.cs + z.coff + g * 8, z.plane);
-  Raw8<kMode> ry = rd;
-  if (relu) ry = t_load_raw<kMode>(y.p + px * y.cs + y.coff + g * 8, y.plane);
-  float k1[8], k2[8], k3[8];
-  load_f8(coef + g * 8, k1);
-  load_f8(coef + ch + g * 8, k2);
-  load_f8(coef + 2 * ch + g * 8, k3);
-  bn_bwd_apply_octet<kMode>(rd, rz, ry, k1, k2, k3, relu, has_dres, dz.p + px * dz.cs + dz.coff + g * 8, dz.plane,
-                            has_dres ? dres.p + px * dres.cs + dres.coff + g * 8 : nullptr, dres.plane);
-}
-
-// k1 = gamma*invstd, k2 = -k1*invstd*m1, k3 = -k1*m0 - k2*mean with m0 = sum_dy/M, m1 = sum_dy_xhat/M; padded
-// channels get zeros.  coef = [k1 | k2 | k3], c floats each.
-// frozen (eval-mode BatchNorm inside a training step: the statistics are constants): dz = gamma*invstd*dy'.
-__global__ void bn_bwd_coef_kernel(const double* __restrict__ sums, double count, const float* __restrict__ mean,
-                                   const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                   float* __restrict__ coef, int c_real, int c, int frozen) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c) return;
-  double k1 = 0.0, k2 = 0.0, k3 = 0.0;
-  if (i < c_real) {
-    const double m0 = sums[i] / count, m1 = sums[c + i] / count;
-    k1 = static_cast<double>(gamma[i]) * invstd[i];
-    if (!frozen) {
-      k2 = -k1 * invstd[i] * m1;
-      k3 = -k1 * m0 - k2 * mean[i];
-    }
-  }
-  coef[i] = static_cast<float>(k1);
-  coef[c + i] = static_cast<float>(k2);
-  coef[2 * c + i] = static_cast<float>(k3);
-}
-
-__global__ void bn_bwd_params_kernel(const double* __restrict__ sums, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta, int c_real, int c) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c_real) return;
-  dbeta[i] = static_cast<float>(sums[i]);
-  dgamma[i] = static_cast<float>(sums[c + i]);
 }
 
 // out = (accumulate ? out : 0) + a * b_mask   /  generic masked ReLU-gate / plain add:  op 0: out = a (*mask)
@@ -848,10 +869,34 @@ extern "C" int up_bn_finalize(const double* sums, int64_t count, const float* ga
                               float* shift, float* save_mean, float* save_invstd, int c_real, int c, void* stream) {
   UP_CHECK_ARG(sums && gamma && beta && scale && shift && save_mean && save_invstd && count > 0 && c >= c_real,
                "up_bn_finalize: bad argument");
-  up::bn_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      sums, static_cast<double>(count), gamma, beta, running_mean, running_var, momentum, eps, scale, shift, save_mean,
-      save_invstd, c_real, c);
+  const up::BnFinalizeArgs a{static_cast<double>(count), gamma, beta, running_mean, running_var, momentum, eps,
+                             scale, shift, save_mean, save_invstd, c_real, c};
+  up::bn_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, a);
   UP_CHECK_LAUNCH("bn_finalize_kernel");
+  return 0;
+}
+
+extern "C" int up_bn_stats_finalize(const UpView* x, int64_t npix, int c, int dtype, double* work, const float* gamma,
+                                    const float* beta, float* running_mean, float* running_var, float momentum,
+                                    float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
+                                    int c_real, void* stream) {
+  int rc = check_view("up_bn_stats_finalize", x, c);
+  if (rc) return rc;
+  const int octs = c / 8;
+  UP_CHECK_ARG(octs <= 256 && (octs & (octs - 1)) == 0, "up_bn_stats_finalize: c/8 must be a power of two <= 256 (c = %d)",
+               c);
+  UP_CHECK_ARG(work && gamma && beta && scale && shift && save_mean && save_invstd && npix > 0 && c >= c_real,
+               "up_bn_stats_finalize: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = reduce_grid(npix, octs);
+  float* rows = reinterpret_cast<float*>(work + 4 * c);
+  UP_T_DISPATCH(dtype, (up::channel_reduce_kernel<kMode, 0><<<grid, 512, 512 * 16 * sizeof(float), st>>>(
+                           tv(x), up::TView{}, up::TView{}, nullptr, nullptr, rows, npix, c, 0)));
+  UP_CHECK_LAUNCH("channel_reduce_kernel<stats>");
+  const up::BnFinalizeArgs a{static_cast<double>(npix), gamma, beta, running_mean, running_var, momentum, eps,
+                             scale, shift, save_mean, save_invstd, c_real, c};
+  up::bn_finish_kernel<0><<<(c + 31) / 32, dim3(32, 16), 0, st>>>(rows, grid, work, a);
+  UP_CHECK_LAUNCH("bn_finish_kernel<stats>");
   return 0;
 }
 
@@ -919,67 +964,46 @@ extern "C" int up_scale_shift_act(const UpView* z, const UpView* y, const UpView
   return 0;
 }
 
-extern "C" int up_bn_bwd_reduce(const UpView* dy, const UpView* y, const UpView* z, const float* save_mean,
-                                const float* save_invstd, int64_t npix, int c, int relu, int dtype, double* sums,
-                                void* stream) {
-  int rc = check_view("up_bn_bwd_reduce(dy)", dy, c);
+extern "C" int up_bn_bwd(const UpView* dy, const UpView* y, const UpView* z, const UpView* dz, const UpView* dres,
+                         const float* save_mean, const float* save_invstd, const float* gamma, double* work,
+                         int64_t npix, int c_real, int c, int flags, int dtype, float* dgamma, float* dbeta,
+                         void* stream) {
+  // flags: bit 0 = the forward applied a ReLU (gate dy by y > 0), bit 1 = frozen statistics (eval-mode BatchNorm)
+  const int relu = flags & 1, frozen = (flags & 2) ? 1 : 0;
+  int rc = check_view("up_bn_bwd(dy)", dy, c);
   if (rc) return rc;
-  rc = check_view("up_bn_bwd_reduce(z)", z, c);
+  rc = check_view("up_bn_bwd(z)", z, c);
   if (rc) return rc;
-  if (relu && (rc = check_view("up_bn_bwd_reduce(y)", y, c))) return rc;
+  rc = check_view("up_bn_bwd(dz)", dz, c);
+  if (rc) return rc;
+  if (relu && (rc = check_view("up_bn_bwd(y)", y, c))) return rc;
+  if (dres && (rc = check_view("up_bn_bwd(dres)", dres, c))) return rc;
   const int octs = c / 8;
-  UP_CHECK_ARG(octs <= 256 && (octs & (octs - 1)) == 0, "up_bn_bwd_reduce: c/8 must be a power of two <= 256");
-  UP_CHECK_ARG(save_mean && save_invstd && sums && npix > 0, "up_bn_bwd_reduce: bad argument");
+  UP_CHECK_ARG(octs <= 256 && (octs & (octs - 1)) == 0, "up_bn_bwd: c/8 must be a power of two <= 256");
+  UP_CHECK_ARG(save_mean && save_invstd && gamma && work && npix > 0 && c_real <= c, "up_bn_bwd: bad argument");
+  UP_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "up_bn_bwd: dgamma and dbeta come together");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // 1. per-channel sums of (dy', dy' * xhat): one partial row per block
   const int grid = reduce_grid(npix, octs);
-  float* rows = reinterpret_cast<float*>(sums + 4 * c);
+  float* rows = reinterpret_cast<float*>(work + 4 * c);
   UP_T_DISPATCH(dtype, (up::channel_reduce_kernel<kMode, 1><<<grid, 512, 512 * 16 * sizeof(float), st>>>(
                            tv(dy), tv(y), tv(z), save_mean, save_invstd, rows, npix, c, relu)));
   UP_CHECK_LAUNCH("channel_reduce_kernel<bn bwd>");
-  up::reduce_rows_kernel<<<(2 * c + 31) / 32, dim3(32, 16), 0, st>>>(rows, grid, 2 * c, sums);
-  UP_CHECK_LAUNCH("reduce_rows_kernel");
-  return 0;
-}
-
-extern "C" int up_bn_bwd_apply(const UpView* dy, const UpView* y, const UpView* z, const UpView* dz,
-                               const UpView* dres, const float* save_mean, const float* save_invstd,
-                               const float* gamma, double* sums, int64_t npix, int c_real, int c, int relu,
-                               int dtype, float* dgamma, float* dbeta, void* stream) {
-  int rc = check_view("up_bn_bwd_apply(dy)", dy, c);
-  if (rc) return rc;
-  rc = check_view("up_bn_bwd_apply(z)", z, c);
-  if (rc) return rc;
-  rc = check_view("up_bn_bwd_apply(dz)", dz, c);
-  if (rc) return rc;
-  if ((relu & 1) && (rc = check_view("up_bn_bwd_apply(y)", y, c))) return rc;
-  if (dres && (rc = check_view("up_bn_bwd_apply(dres)", dres, c))) return rc;
-  UP_CHECK_ARG(save_mean && save_invstd && gamma && sums && npix > 0 && c_real <= c, "up_bn_bwd_apply: bad argument");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // per-channel coefficients: 3*c floats right behind the 2*c reduction doubles (the work buffer holds 4*c doubles)
-  float* coef = reinterpret_cast<float*>(sums + 2 * c);
-  const int frozen = (relu & 2) ? 1 : 0;
-  relu &= 1;
-  up::bn_bwd_coef_kernel<<<(c + 127) / 128, 128, 0, st>>>(sums, static_cast<double>(npix), save_mean, save_invstd, gamma,
-                                                           coef, c_real, c, frozen);
-  UP_CHECK_LAUNCH("bn_bwd_coef_kernel");
-  const int c8 = c / 8;
-  const long long total = npix * c8;
-  if (c8 <= 256 && (c8 & (c8 - 1)) == 0) {
-    int lg = 0;
-    while ((1 << lg) < c8) ++lg;
-    constexpr int kU = 2;
-    UP_T_DISPATCH(dtype, (up::bn_bwd_apply_fast_kernel<kMode, kU>
-                          <<<static_cast<unsigned>((total + 256 * kU - 1) / (256 * kU)), 256, 0, st>>>(
-                              tv(dy), tv(y), tv(z), tvw(dz), tvw(dres), coef, total, lg, c, relu & 1, dres != nullptr)));
-  } else {
-    UP_T_DISPATCH(dtype, (up::bn_bwd_apply_kernel<kMode><<<blocks_for(total), 256, 0, st>>>(
-                             tv(dy), tv(y), tv(z), tvw(dz), tvw(dres), coef, npix, c, relu & 1, dres != nullptr)));
-  }
-  UP_CHECK_LAUNCH("bn_bwd_apply_kernel");
-  if (dgamma && dbeta) {
-    up::bn_bwd_params_kernel<<<(c_real + 127) / 128, 128, 0, st>>>(sums, dgamma, dbeta, c_real, c);
-    UP_CHECK_LAUNCH("bn_bwd_params_kernel");
-  }
+  // 2. rows -> sums -> coefficients (3*c floats right behind the 2*c doubles) + dgamma / dbeta
+  float* coef = reinterpret_cast<float*>(work + 2 * c);
+  const up::BnBwdCoefArgs a{static_cast<double>(npix), save_mean, save_invstd, gamma, coef, dgamma, dbeta, c_real, c,
+                            frozen};
+  up::bn_finish_kernel<1><<<(c + 31) / 32, dim3(32, 16), 0, st>>>(rows, grid, work, a);
+  UP_CHECK_LAUNCH("bn_finish_kernel<bn bwd>");
+  // 3. dz = k1*dy' + k2*z + k3 (and dres = dy')
+  const long long total = npix * octs;
+  int lg = 0;
+  while ((1 << lg) < octs) ++lg;
+  constexpr int kU = 2;
+  UP_T_DISPATCH(dtype, (up::bn_bwd_apply_fast_kernel<kMode, kU>
+                        <<<static_cast<unsigned>((total + 256 * kU - 1) / (256 * kU)), 256, 0, st>>>(
+                            tv(dy), tv(y), tv(z), tvw(dz), tvw(dres), coef, total, lg, c, relu, dres != nullptr)));
+  UP_CHECK_LAUNCH("bn_bwd_apply_fast_kernel");
   return 0;
 }
 

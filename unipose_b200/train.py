@@ -5,9 +5,9 @@
 optimizer.step()) runs unchanged.  One torch.autograd.Function spans the whole network; its forward / backward
 replay two static kernel plans:
 
-  forward   per conv+BN unit: tcgen05 conv (raw output z) -> up_bn_stats -> up_bn_finalize (batch statistics, running
+  forward   per conv+BN unit: tcgen05 conv (raw output z) -> up_bn_stats_finalize (batch statistics, running
             stats update) -> up_scale_shift_act (normalise + residual + ReLU + dropout mask)
-  backward  reverse tape: up_bn_bwd_* (ReLU gate + BatchNorm backward, dgamma/dbeta, residual gradient) ->
+  backward  reverse tape: up_bn_bwd (ReLU gate + BatchNorm backward, dgamma/dbeta, residual gradient) ->
             tcgen05 wgrad (MN-major operands) -> dgrad = the forward conv kernel on the flipped/transposed filter
             (gradient accumulation across branches rides on its residual input)
 
@@ -204,8 +204,9 @@ class TrainPlan:
                 self.fwd.append(lambda: ops.bn_eval_prepare(bn, scale, shift, mean, invstd, co_r, c))
             else:
                 self.bn_modules.append(bn)
-                self.fwd.append(lambda: ops.bn_stats(z, c, sums))
-                self.fwd.append(lambda: ops.bn_finalize(sums, count, bn, scale, shift, mean, invstd, co_r, c))
+                zv = ops.as_view(z)
+                assert count == zv.n * zv.h * zv.w
+                self.fwd.append(lambda: ops.bn_stats_finalize(z, sums, bn, scale, shift, mean, invstd, co_r, c))
             self.fwd.append(lambda: ops.scale_shift_act(z, y, scale, shift, relu=relu, residual=residual, mask=mask))
             rec.update(sums=sums, mean=mean, invstd=invstd, frozen=frozen)
         rec["y"] = y
