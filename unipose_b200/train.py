@@ -41,6 +41,12 @@ class TrainPlan:
         self.mode = ops.mode_of(precision)
         self.fwd: List = []
         self.bwd: List = []
+        # indices of backward ops that may run on the side stream: the weight gradients.  wgrad(L) only needs dz(L) and
+        # the saved input x(L); nothing on the critical path bn_bwd(L) -> dgrad(L) -> bn_bwd(L-1) -> ... reads its
+        # result, so it overlaps the (HBM-bound) BatchNorm backward and the heads/tails of the dgrad kernels.
+        self.bwd_side = set()
+        self.side_stream: Optional[torch.cuda.Stream] = None
+        self.overlap_wgrad = os.environ.get("UNIPOSE_B200_WGRAD_OVERLAP", "1") != "0"
         self.tape: List = []
         self.buffers: List = []
         self.weights = engine.WeightTable(self.device, self.mode, always=True)   # refilled every step
@@ -54,10 +60,12 @@ class TrainPlan:
         self.masks: List[Tuple[Act, float]] = []
         self.bn_modules: List[nn.BatchNorm2d] = []
         self.scratch_bytes = 0
+        self.scratch_main_bytes = 0
         self.live_params: List[nn.Parameter] = []
         self._live_ids = set()
         self.flat_g: Optional[torch.Tensor] = None
         self.scratch: Optional[torch.Tensor] = None
+        self.scratch_main: Optional[torch.Tensor] = None
         self.input: Optional[torch.Tensor] = None
         self.heat: Optional[torch.Tensor] = None
         self.dheat: Optional[torch.Tensor] = None
@@ -279,16 +287,20 @@ class TrainPlan:
         # ---- weight gradient ----
         d = ops.conv_desc(xv, pc, ho, wo, stride=r["stride"], dil=r["dil"], pad=r["pad"], x_groups=r["x_groups"],
                           x_group_nstride=r["x_group_nstride"], x_window=r["x_window"])
-        self.scratch_bytes = max(self.scratch_bytes, ops.wgrad_scratch_bytes(d))
+        if r["weight_fn"] is None:
+            self.scratch_bytes = max(self.scratch_bytes, ops.wgrad_scratch_bytes(d))
+        else:       # stays on the main stream (torch ops follow it): its own split scratch, the side stream owns the other
+            self.scratch_main_bytes = max(self.scratch_main_bytes, ops.wgrad_scratch_bytes(d))
         gw = self.param_grad(conv.weight)
         acc = id(conv.weight) in self.pgrad_written
         self.pgrad_written.add(id(conv.weight))
         if r["weight_fn"] is None:
+            self.bwd_side.add(len(self.bwd))
             self.bwd.append(lambda: ops.conv2d_wgrad(d, xv, dzv, gw, self.scratch, accumulate=acc))
         else:
             gtmp = self.tensor((r["co_r"], r["ci_r"], r["kh"], r["kw"]))
             inv = r["weight_fn_inv"]
-            self.bwd.append(lambda: ops.conv2d_wgrad(d, xv, dzv, gtmp, self.scratch, accumulate=False))
+            self.bwd.append(lambda: ops.conv2d_wgrad(d, xv, dzv, gtmp, self.scratch_main, accumulate=False))
             if acc:
                 self.bwd.append(lambda: gw.add_(inv(gtmp)))
             else:
@@ -389,6 +401,7 @@ class TrainPlan:
         for t in reversed(self.tape):
             t()
         self.scratch = torch.empty(max(self.scratch_bytes // 4, 1), dtype=torch.float32, device=self.device)
+        self.scratch_main = torch.empty(max(self.scratch_main_bytes // 4, 1), dtype=torch.float32, device=self.device)
 
     def run_forward(self, x: torch.Tensor, masks: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
         with torch.cuda.device(self.device):     # C-ABI launches use the current device's stream
@@ -410,8 +423,28 @@ class TrainPlan:
     def run_backward(self, dheat: torch.Tensor) -> None:
         with torch.cuda.device(self.device):
             self.dheat.copy_(dheat)
-            for op in self.bwd:
+            self.run_backward_ops(0, len(self.bwd))
+
+    def run_backward_ops(self, lo: int, hi: int) -> None:
+        """Backward ops [lo, hi) in order; the weight gradients go to the side stream (forked behind the op that
+        produced their dz, joined at the end of the range - so a range is also capturable as one CUDA graph)."""
+        if not (self.overlap_wgrad and any(i in self.bwd_side for i in range(lo, hi))):
+            for op in self.bwd[lo:hi]:
                 op()
+            return
+        if self.side_stream is None:
+            self.side_stream = torch.cuda.Stream(device=self.device)
+        main, side = torch.cuda.current_stream(self.device), self.side_stream
+        for i in range(lo, hi):
+            if i in self.bwd_side:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    self.bwd[i]()
+            else:
+                self.bwd[i]()
+        main.wait_stream(side)
 
     def _fill_masks(self, given) -> None:
         for i, (act, p) in enumerate(self.masks):
@@ -794,8 +827,7 @@ class TrainStep:
 
     def _bwd_segment(self, k: int) -> None:
         lo = self.buckets[k - 1][2] if k > 0 else 0
-        for op in self.plan.bwd[lo:self.buckets[k][2]]:
-            op()
+        self.plan.run_backward_ops(lo, self.buckets[k][2])
 
     def _run_piece(self, k: int, world: int) -> None:
         """piece 0 = forward + loss + backward segment 0; piece k = backward segment k."""
