@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(256, 1)
   __syncthreads();
   tcgen05_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // programmatic dependent launch: barrier init and TMEM allocation above overlapped the previous kernel's tail
+  pdl_enter();
   const int a_boxes = 2;                         // 128 cout = 2 x 64
   const int b_boxes = p.block_n / p.ckx;         // cin block = b_boxes x ckx
 
@@ -301,6 +303,7 @@ __global__ void __launch_bounds__(256, 1)
 // Sum the pixel splits and scatter [tap][cout][cin] -> OIHW fp32 [cout_real][cin_real][kh][kw].
 __global__ void wgrad_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int splits, int taps,
                                     int cout, int cin, int cout_real, int cin_real, int accumulate) {
+  pdl_enter();
   const long long total = static_cast<long long>(cout_real) * cin_real * taps;
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= total) return;
@@ -462,12 +465,13 @@ extern "C" int up_conv2d_wgrad(const UpConvDesc* d, const void* x, const void* d
   const int grid = static_cast<int>(total_items < g_wg_sm_count ? total_items : g_wg_sm_count);
   const size_t smem = fixed + static_cast<size_t>(stages) * (p.a_bytes + p.b_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  conv_wgrad_tcgen05_kernel<<<grid, 256, smem, st>>>(tmZ0, tmZ1, tmX0, tmX1, p);
-  UP_CHECK_LAUNCH("conv_wgrad_tcgen05_kernel launch");
+  rc = check_cuda(launch_pdl(conv_wgrad_tcgen05_kernel, grid, 256, smem, st, tmZ0, tmZ1, tmX0, tmX1, p),
+                      "conv_wgrad_tcgen05_kernel launch");
+  if (rc) return rc;
   const long long total = static_cast<long long>(cout_real) * cin_real * d->kh * d->kw;
-  wgrad_reduce_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(scratch, dw_oihw, p.splits, d->kh * d->kw,
-                                                                             d->cout, d->cin, cout_real, cin_real,
-                                                                             accumulate);
-  UP_CHECK_LAUNCH("wgrad_reduce_kernel launch");
+  rc = check_cuda(launch_pdl(wgrad_reduce_kernel, static_cast<int>((total + 255) / 256), 256, 0, st, scratch, dw_oihw,
+                             p.splits, d->kh * d->kw, d->cout, d->cin, cout_real, cin_real, accumulate),
+                  "wgrad_reduce_kernel launch");
+  if (rc) return rc;
   return 0;
 }

@@ -177,6 +177,7 @@ template <int kMode, int kWhat>
 __global__ void __launch_bounds__(512)
     channel_reduce_kernel(TView a, TView b, TView c, const float* __restrict__ mean, const float* __restrict__ invstd,
                           float* __restrict__ rows, long long npix, int ch, int relu) {
+  pdl_enter();
   const int octs = ch / 8;
   const int oct = threadIdx.x % octs;
   const int pstride = blockDim.x / octs;
@@ -261,6 +262,7 @@ __global__ void __launch_bounds__(512)
 // blockDim = (32, 16): 32 consecutive sums per block, the rows split 16 ways, combined in shared memory in a fixed
 // order (deterministic).
 __global__ void reduce_rows_kernel(const float* __restrict__ rows, int nrows, int c2, double* __restrict__ sums) {
+  pdl_enter();
   __shared__ double part[16][33];
   const int i = blockIdx.x * 32 + threadIdx.x;
   double s = 0.0;
@@ -311,6 +313,7 @@ __device__ __forceinline__ void bn_finalize_channel(int i, double sum, double su
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, const BnFinalizeArgs a) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.c) return;
   bn_finalize_channel(i, sums[i], sums[a.c + i], a);
@@ -350,6 +353,7 @@ __device__ __forceinline__ void bn_bwd_coef_channel(int i, double sum_dy, double
 // (kWhat 0) or the backward coefficients and dgamma / dbeta (kWhat 1).  blockDim = (32, 16).
 template <int kWhat, class Args>
 __global__ void bn_finish_kernel(const float* __restrict__ rows, int nrows, double* __restrict__ sums, const Args a) {
+  pdl_enter();
   __shared__ double part[2][16][33];
   const int c = a.c;
   const int i = blockIdx.x * 32 + threadIdx.x;
@@ -390,6 +394,7 @@ __global__ void __launch_bounds__(256)
     scale_shift_act_fast_kernel(TView z, TViewW y, TView res, TView mask, const float* __restrict__ scale,
                                 const float* __restrict__ shift, long long total, int lg, int relu, int has_res,
                                 int has_mask) {
+  pdl_enter();
   const int g = threadIdx.x & ((1 << lg) - 1);
   const long long base = blockIdx.x * (256LL * kU) + threadIdx.x;
   Raw8<kMode> rz[kU], rr[kU], rm[kU];
@@ -431,6 +436,7 @@ template <int kMode>
 __global__ void scale_shift_act_kernel(TView z, TViewW y, TView res, TView mask, const float* __restrict__ scale,
                                        const float* __restrict__ shift, long long npix, int ch, int relu, int has_res,
                                        int has_mask) {
+  pdl_enter();
   const int c8 = ch / 8;
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= npix * c8) return;
@@ -478,6 +484,7 @@ template <int kMode, int kU>
 __global__ void __launch_bounds__(256)
     bn_bwd_apply_fast_kernel(TView dy, TView y, TView z, TViewW dz, TViewW dres, const float* __restrict__ coef,
                              long long total, int lg, int ch, int relu, int has_dres) {
+  pdl_enter();
   const int g = threadIdx.x & ((1 << lg) - 1);
   const long long base = blockIdx.x * (256LL * kU) + threadIdx.x;
   Raw8<kMode> rd[kU], rz[kU], ry[kU];
@@ -856,10 +863,10 @@ extern "C" int up_bn_stats(const UpView* x, int64_t npix, int c, int dtype, doub
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = reduce_grid(npix, octs);
   float* rows = reinterpret_cast<float*>(sums + 4 * c);
-  UP_T_DISPATCH(dtype, (up::channel_reduce_kernel<kMode, 0><<<grid, 512, 512 * 16 * sizeof(float), st>>>(
-                           tv(x), up::TView{}, up::TView{}, nullptr, nullptr, rows, npix, c, 0)));
+  UP_T_DISPATCH(dtype, (up::launch_pdl(up::channel_reduce_kernel<kMode, 0>, grid, 512, 512 * 16 * sizeof(float), st, tv(x),
+                                          up::TView{}, up::TView{}, nullptr, nullptr, rows, npix, c, 0)));
   UP_CHECK_LAUNCH("channel_reduce_kernel<stats>");
-  up::reduce_rows_kernel<<<(2 * c + 31) / 32, dim3(32, 16), 0, st>>>(rows, grid, 2 * c, sums);
+  up::launch_pdl(up::reduce_rows_kernel, (2 * c + 31) / 32, dim3(32, 16), 0, st, rows, grid, 2 * c, sums);
   UP_CHECK_LAUNCH("reduce_rows_kernel");
   return 0;
 }
@@ -871,7 +878,7 @@ extern "C" int up_bn_finalize(const double* sums, int64_t count, const float* ga
                "up_bn_finalize: bad argument");
   const up::BnFinalizeArgs a{static_cast<double>(count), gamma, beta, running_mean, running_var, momentum, eps,
                              scale, shift, save_mean, save_invstd, c_real, c};
-  up::bn_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, a);
+  up::launch_pdl(up::bn_finalize_kernel, (c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), sums, a);
   UP_CHECK_LAUNCH("bn_finalize_kernel");
   return 0;
 }
@@ -890,12 +897,12 @@ extern "C" int up_bn_stats_finalize(const UpView* x, int64_t npix, int c, int dt
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = reduce_grid(npix, octs);
   float* rows = reinterpret_cast<float*>(work + 4 * c);
-  UP_T_DISPATCH(dtype, (up::channel_reduce_kernel<kMode, 0><<<grid, 512, 512 * 16 * sizeof(float), st>>>(
-                           tv(x), up::TView{}, up::TView{}, nullptr, nullptr, rows, npix, c, 0)));
+  UP_T_DISPATCH(dtype, (up::launch_pdl(up::channel_reduce_kernel<kMode, 0>, grid, 512, 512 * 16 * sizeof(float), st, tv(x),
+                                          up::TView{}, up::TView{}, nullptr, nullptr, rows, npix, c, 0)));
   UP_CHECK_LAUNCH("channel_reduce_kernel<stats>");
   const up::BnFinalizeArgs a{static_cast<double>(npix), gamma, beta, running_mean, running_var, momentum, eps,
                              scale, shift, save_mean, save_invstd, c_real, c};
-  up::bn_finish_kernel<0><<<(c + 31) / 32, dim3(32, 16), 0, st>>>(rows, grid, work, a);
+  up::launch_pdl(up::bn_finish_kernel<0, up::BnFinalizeArgs>, (c + 31) / 32, dim3(32, 16), 0, st, rows, grid, work, a);
   UP_CHECK_LAUNCH("bn_finish_kernel<stats>");
   return 0;
 }
@@ -950,15 +957,15 @@ extern "C" int up_scale_shift_act(const UpView* z, const UpView* y, const UpView
     while ((1 << lg) < c8) ++lg;
     UP_T_DISPATCH(dtype, ({
                     constexpr int kU = kMode == 2 ? 2 : 4;
-                    up::scale_shift_act_fast_kernel<kMode, kU>
-                        <<<static_cast<unsigned>((total + 256 * kU - 1) / (256 * kU)), 256, 0, (cudaStream_t)stream>>>(
-                            tv(z), tvw(y), tv(residual), tv(mask), scale, shift, total, lg, relu, residual != nullptr,
-                            mask != nullptr);
+                    up::launch_pdl(up::scale_shift_act_fast_kernel<kMode, kU>,
+                                   static_cast<unsigned>((total + 256 * kU - 1) / (256 * kU)), 256, 0,
+                                   (cudaStream_t)stream, tv(z), tvw(y), tv(residual), tv(mask), scale, shift, total, lg,
+                                   relu, residual != nullptr, mask != nullptr);
                   }));
   } else {
-    UP_T_DISPATCH(dtype, (up::scale_shift_act_kernel<kMode><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
-                             tv(z), tvw(y), tv(residual), tv(mask), scale, shift, npix, c, relu, residual != nullptr,
-                             mask != nullptr)));
+    UP_T_DISPATCH(dtype, up::launch_pdl(up::scale_shift_act_kernel<kMode>, blocks_for(total), 256, 0, (cudaStream_t)stream,
+                                            tv(z), tvw(y), tv(residual), tv(mask), scale, shift, npix, c, relu,
+                                            residual != nullptr, mask != nullptr));
   }
   UP_CHECK_LAUNCH("scale_shift_act_kernel");
   return 0;
@@ -986,23 +993,23 @@ extern "C" int up_bn_bwd(const UpView* dy, const UpView* y, const UpView* z, con
   // 1. per-channel sums of (dy', dy' * xhat): one partial row per block
   const int grid = reduce_grid(npix, octs);
   float* rows = reinterpret_cast<float*>(work + 4 * c);
-  UP_T_DISPATCH(dtype, (up::channel_reduce_kernel<kMode, 1><<<grid, 512, 512 * 16 * sizeof(float), st>>>(
-                           tv(dy), tv(y), tv(z), save_mean, save_invstd, rows, npix, c, relu)));
+  UP_T_DISPATCH(dtype, (up::launch_pdl(up::channel_reduce_kernel<kMode, 1>, grid, 512, 512 * 16 * sizeof(float), st, tv(dy),
+                                          tv(y), tv(z), save_mean, save_invstd, rows, npix, c, relu)));
   UP_CHECK_LAUNCH("channel_reduce_kernel<bn bwd>");
   // 2. rows -> sums -> coefficients (3*c floats right behind the 2*c doubles) + dgamma / dbeta
   float* coef = reinterpret_cast<float*>(work + 2 * c);
   const up::BnBwdCoefArgs a{static_cast<double>(npix), save_mean, save_invstd, gamma, coef, dgamma, dbeta, c_real, c,
                             frozen};
-  up::bn_finish_kernel<1><<<(c + 31) / 32, dim3(32, 16), 0, st>>>(rows, grid, work, a);
+  up::launch_pdl(up::bn_finish_kernel<1, up::BnBwdCoefArgs>, (c + 31) / 32, dim3(32, 16), 0, st, rows, grid, work, a);
   UP_CHECK_LAUNCH("bn_finish_kernel<bn bwd>");
   // 3. dz = k1*dy' + k2*z + k3 (and dres = dy')
   const long long total = npix * octs;
   int lg = 0;
   while ((1 << lg) < octs) ++lg;
   constexpr int kU = 2;
-  UP_T_DISPATCH(dtype, (up::bn_bwd_apply_fast_kernel<kMode, kU>
-                        <<<static_cast<unsigned>((total + 256 * kU - 1) / (256 * kU)), 256, 0, st>>>(
-                            tv(dy), tv(y), tv(z), tvw(dz), tvw(dres), coef, total, lg, c, relu, dres != nullptr)));
+  UP_T_DISPATCH(dtype, up::launch_pdl(up::bn_bwd_apply_fast_kernel<kMode, kU>,
+                                       static_cast<unsigned>((total + 256 * kU - 1) / (256 * kU)), 256, 0, st, tv(dy),
+                                       tv(y), tv(z), tvw(dz), tvw(dres), coef, total, lg, c, relu, dres != nullptr));
   UP_CHECK_LAUNCH("bn_bwd_apply_fast_kernel");
   return 0;
 }

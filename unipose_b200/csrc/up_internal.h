@@ -42,6 +42,40 @@ DeviceInfo* device_info();
     if (_rc != 0) return _rc;                                   \
   } while (0)
 
+// ---- programmatic dependent launch ------------------------------------------------------------
+// A kernel launched through launch_pdl may be SCHEDULED while its predecessor in the stream still runs (once every
+// CTA of the predecessor has called pdl_enter or exited), so that launch latency and prologue overlap the
+// predecessor's tail.  It must call pdl_enter() before touching anything the predecessor wrote: the wait returns when
+// the predecessor has completed and its writes are visible.  UP_PDL=0 switches the attribute off.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("UP_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- 16-bit storage <-> fp32 (device) -------------------------------------------------------
 // kFmt: 0 = fp16, 1 = bf16 (matches the tcgen05 instruction-descriptor encoding).
 template <int kFmt>
