@@ -353,10 +353,34 @@ static int wgrad_plan(const UpConvDesc* d, WgradKParams& p, int sm_count) {
   p.tiles_n = (d->n + p.bn - 1) / p.bn;
   p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int base_items = d->kh * d->kw * p.co_blocks * p.ci_blocks;
-  int splits = (sm_count + base_items - 1) / base_items;
-  if (splits > p.m_tiles) splits = p.m_tiles;
-  if (splits < 1) splits = 1;
-  p.tiles_per_split = (p.m_tiles + splits - 1) / splits;
+  // Pixel splits: minimise the makespan of the persistent grid, in units of one 64-pixel k-step (~0.27 us of MMA for a
+  // 128 x 256 tile): rounds * tiles_per_split, plus the split reduction (scratch written and read once per split at
+  // ~3 TB/s).  ceil(SMs / items) alone put 162 items on 148 SMs for the 3x3 256->256 layers of layer3: two rounds of 32
+  // k-steps where 8 splits give one round of 36.
+  const double red_per_split = static_cast<double>(d->kh) * d->kw * d->cout * d->cin * 4.0 * 2.0 / 3e12 / 0.27e-6;
+  int best = 1;
+  double best_cost = 1e30;
+  const int max_splits = p.m_tiles < 4 * sm_count ? p.m_tiles : 4 * sm_count;
+  for (int sp = 1; sp <= max_splits; ++sp) {
+    const int tps = (p.m_tiles + sp - 1) / sp;
+    const int eff = (p.m_tiles + tps - 1) / tps;
+    if (eff != sp) continue;
+    const long long items = static_cast<long long>(eff) * base_items;
+    const long long rounds = (items + sm_count - 1) / sm_count;
+    const double cost = static_cast<double>(rounds) * (tps + 4.0) + red_per_split * eff;
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = sp;
+    }
+  }
+  if (const char* e = getenv("UP_WGRAD_SPLITS_LEGACY")) {
+    if (e[0] == '1') {
+      best = (sm_count + base_items - 1) / base_items;
+      if (best > p.m_tiles) best = p.m_tiles;
+      if (best < 1) best = 1;
+    }
+  }
+  p.tiles_per_split = (p.m_tiles + best - 1) / best;
   p.splits = (p.m_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   return 0;
 }
