@@ -357,7 +357,16 @@ static int wgrad_plan(const UpConvDesc* d, WgradKParams& p, int sm_count) {
   // 128 x 256 tile): rounds * tiles_per_split, plus the split reduction (scratch written and read once per split at
   // ~3 TB/s).  ceil(SMs / items) alone put 162 items on 148 SMs for the 3x3 256->256 layers of layer3: two rounds of 32
   // k-steps where 8 splits give one round of 36.
-  const double red_per_split = static_cast<double>(d->kh) * d->kw * d->cout * d->cin * 4.0 * 2.0 / 3e12 / 0.27e-6;
+  static const double red_scale = []() {
+    const char* e = getenv("UP_WGRAD_RED_COST");
+    return e ? atof(e) : 1.0;
+  }();
+  static const double item_overhead = []() {
+    const char* e = getenv("UP_WGRAD_ITEM_COST");
+    return e ? atof(e) : 4.0;
+  }();
+  const double red_per_split =
+      red_scale * static_cast<double>(d->kh) * d->kw * d->cout * d->cin * 4.0 * 2.0 / 3e12 / 0.27e-6;
   int best = 1;
   double best_cost = 1e30;
   const int max_splits = p.m_tiles < 4 * sm_count ? p.m_tiles : 4 * sm_count;
@@ -367,7 +376,7 @@ static int wgrad_plan(const UpConvDesc* d, WgradKParams& p, int sm_count) {
     if (eff != sp) continue;
     const long long items = static_cast<long long>(eff) * base_items;
     const long long rounds = (items + sm_count - 1) / sm_count;
-    const double cost = static_cast<double>(rounds) * (tps + 4.0) + red_per_split * eff;
+    const double cost = static_cast<double>(rounds) * (tps + item_overhead) + red_per_split * eff;
     if (cost < best_cost) {
       best_cost = cost;
       best = sp;
