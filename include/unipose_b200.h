@@ -192,10 +192,16 @@ typedef struct UpBneckTailDesc {
   int32_t planes;      /* 64 or 128 */
   int32_t dil;         /* dilation (= padding) of the 3x3 conv */
   int32_t dtype;       /* UP_FP16 or UP_BF16 */
+  int32_t proj_cin;    /* 0: identity shortcut (`residual` = the block input, 4*planes channels);
+                          > 0 (multiple of 64): projection shortcut of a stage's first block (resnet.py:36-37,
+                          `downsample` = 1x1 conv + BN, stride 1): `residual` = the block input x [n,h,w,proj_cin],
+                          wd packed [1][4*planes][proj_cin] (BN scale folded in), shiftd fp32 [4*planes] -
+                          Wd x is accumulated into the output accumulator, the shortcut tensor is never written */
 } UpBneckTailDesc;
 int up_bneck_tail_supported(const UpBneckTailDesc* desc);
 int up_bneck_tail_fwd(const UpBneckTailDesc* desc, const void* t1, const void* w2, const float* shift2, const void* w3,
-                      const float* shift3, const void* residual, void* y, void* stream);
+                      const float* shift3, const void* residual, const void* wd, const float* shiftd, void* y,
+                      void* stream);
 
 /* Debug aid (UP_DEBUG_TIMING=1): per-CTA phase timestamps (ns) of the last up_wasp_chain_fwd launch, 160 CTAs x 32 slots. */
 int up_debug_chain_timing(unsigned long long* h_out);

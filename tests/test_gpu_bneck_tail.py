@@ -27,7 +27,9 @@ def _run(m, x, tail, monkeypatch):
     out = m(x.cuda())
     torch.cuda.synchronize()
     names = [n for n, f, s in m.plan_for(x.cuda()).ops if f is not None]
-    assert (names.count("bottleneck.tail") == 6) == tail, names       # layer1 x3 + layer2 blocks 1..3
+    # layer1 x3 (block 0 with its projection shortcut inside the kernel) + layer2 blocks 1..3
+    assert names.count("bottleneck.tail") == (6 if tail else 0), names
+    assert names.count("bottleneck.downsample") == (3 if tail else 4), names
     return out.cpu().numpy()
 
 
@@ -48,3 +50,25 @@ def test_bneck_tail_matches_layerwise_and_oracle(n, size, precision, monkeypatch
     bound = 5e-3 if precision == "fp16" else 3e-2
     assert e_tail < bound and e_base < bound, (e_tail, e_base)
     assert e_tail < 2.0 * e_base + 1e-3
+
+
+def test_projection_shortcut_inside_the_tail_matches_the_separate_launch(monkeypatch):
+    """layer1 block 0: downsample(x) accumulated in the tail kernel vs written by its own launch and read back."""
+    m, sd = _model("fp16", seed=5)
+    x = O.synth_input(2, 368, 368, seed=5)        # 92x92 maps: partial tiles
+    with torch.no_grad():
+        ref = O.unipose_forward(x, sd).numpy()
+    monkeypatch.setenv("UNIPOSE_B200_BNECK_TAIL_PROJ", "0")
+    m._plans.clear()
+    sep = m(x.cuda()).cpu().numpy()
+    names = [n for n, f, s in m.plan_for(x.cuda()).ops if f is not None]
+    assert names.count("bottleneck.tail") == 6 and names.count("bottleneck.downsample") == 4
+    monkeypatch.setenv("UNIPOSE_B200_BNECK_TAIL_PROJ", "1")
+    m._plans.clear()
+    fused = m(x.cuda()).cpu().numpy()
+    names = [n for n, f, s in m.plan_for(x.cuda()).ops if f is not None]
+    assert names.count("bottleneck.tail") == 6 and names.count("bottleneck.downsample") == 3
+    scale = float(np.abs(ref).max())
+    e_f, e_s = float(np.abs(fused - ref).max() / scale), float(np.abs(sep - ref).max() / scale)
+    print("projection in the tail: max-rel %.3g (separate launch %.3g)" % (e_f, e_s))
+    assert e_f < 5e-3 and e_f < 2.0 * e_s + 1e-3

@@ -13,6 +13,11 @@
 // conv2 of tile i+2.  Bytes per block: t1 (+halo) + residual + output - the t2 round trip (2 x N*H*W*P*2 B) and one
 // launch disappear.
 //
+// Projection mode (the first block of a stage, stride 1: layer1 block 0): the shortcut is downsample(x) = Wd x (1x1 conv
+// + BN, resnet.py:36-37) - instead of a separate launch that writes N*H*W*4P*2 bytes which the tail reads back, the x
+// tile [128 x Cx] and the Wd N-tile ride through the ring and Wd x is accumulated straight into acc3 (replaces the
+// identity MMAs); the epilogue adds both shifts.
+//
 // Warp roles (384 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM alloc + store thread, 3 idle, 4..11 epilogue.
 #include <cuda.h>
 #include <stdlib.h>
@@ -44,6 +49,8 @@ struct BtParams {
   uint32_t idesc_res;    // M128 x N=64
   const float* shift2;   // [P]
   const float* shift3;   // [4P]
+  int xchunks;           // projection mode: Cx / 64 input-channel chunks of the block input x (0 = identity shortcut)
+  const float* shiftd;   // projection mode: [4P] shift of the downsample BatchNorm
 };
 
 struct BtTile {
@@ -81,7 +88,8 @@ template <int kFmt>
 __global__ void __launch_bounds__(kBtThreads, 1)
     bneck_tail_kernel(const __grid_constant__ CUtensorMap tmT1, const __grid_constant__ CUtensorMap tmR,
                       const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW2,
-                      const __grid_constant__ CUtensorMap tmW3, const BtParams p) {
+                      const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmWd,
+                      const BtParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -111,6 +119,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     tma_prefetch_desc(&tmR);
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmW3);
+    tma_prefetch_desc(&tmWd);
     tma_prefetch_desc(&tmY);
     for (int s = 0; s < p.slots; ++s) {
       mbar_init(full_bar(s), 1);
@@ -201,6 +210,26 @@ __global__ void __launch_bounds__(kBtThreads, 1)
           __syncwarp();
           advance();
         }
+        if (p.xchunks > 0) {
+          // projection shortcut: per 64-channel chunk of x one slot with the x tile (A) and one with the Wd N-tile (B)
+          for (int xc = 0; xc < p.xchunks; ++xc) {
+            mbar_wait(empty_bar(slot), par, 16000000000LL);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(full_bar(slot), kBtABytes);
+              tma_load_5d(&tmR, smem_base + slot * kBtSlotBytes, full_bar(slot), xc * 64, t.w0, 0, t.h0, t.n0);
+            }
+            __syncwarp();
+            advance();
+            mbar_wait(empty_bar(slot), par, 16000000000LL);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(full_bar(slot), kBtSlotBytes);
+              tma_load_2d(&tmWd, smem_base + slot * kBtSlotBytes, full_bar(slot), xc * 64, nt * 256);
+            }
+            __syncwarp();
+            advance();
+          }
+          continue;
+        }
         // the residual tile of this N-tile: 256 channels = two slots of two 64-channel chunks
         for (int r2 = 0; r2 < 2; ++r2) {
           mbar_wait(empty_bar(slot), par, 16000000000LL);
@@ -283,6 +312,27 @@ __global__ void __launch_bounds__(kBtThreads, 1)
           __syncwarp();
           advance();
         }
+        if (p.xchunks > 0) {
+          for (int xc = 0; xc < p.xchunks; ++xc) {
+            const uint32_t slot_a = slot;
+            mbar_wait(full_bar(slot), phase);
+            advance();
+            mbar_wait(full_bar(slot), phase);
+            tcgen05_after_thread_sync();
+            if (elect_one()) {
+              const uint64_t ad = adesc0 + static_cast<uint64_t>(slot_step * slot_a);
+              const uint64_t bd = adesc0 + static_cast<uint64_t>(slot_step * slot);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16(tmem_acc3, ad + 2u * k, bd + 2u * k, p.idesc3, 1u);
+              umma_commit(empty_bar(slot_a));
+              umma_commit(empty_bar(slot));
+              if (xc == p.xchunks - 1) umma_commit(full3_bar);
+            }
+            __syncwarp();
+            advance();
+          }
+          continue;
+        }
         for (int r2 = 0; r2 < 2; ++r2) {
           mbar_wait(full_bar(slot), phase);
           tcgen05_after_thread_sync();
@@ -338,7 +388,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     uint32_t nT = 0, nO = 0, n3 = 0;
     uint32_t n2[2] = {0u, 0u};
     // `groups` x 64 accumulator columns -> ReLU(acc + shift) -> 16-bit -> staging buffers
-    auto epilogue = [&](uint32_t tmem_col0, int groups, const float* sh, bool setO) {
+    auto epilogue = [&](uint32_t tmem_col0, int groups, const float* sh, const float* sh2, bool setO) {
       uint32_t r[32];
       const uint32_t taddr = tmem_col0 + tlane + static_cast<uint32_t>(half * 32);
       const uint32_t nuse = setO ? nO : nT;
@@ -354,6 +404,17 @@ __global__ void __launch_bounds__(kBtThreads, 1)
           v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + h4.y;
           v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + h4.z;
           v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + h4.w;
+        }
+        if (sh2) {
+          const float4* d4 = reinterpret_cast<const float4*>(sh2 + g * 64 + half * 32);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 h4 = __ldg(d4 + j4);
+            v[4 * j4 + 0] += h4.x;
+            v[4 * j4 + 1] += h4.y;
+            v[4 * j4 + 2] += h4.z;
+            v[4 * j4 + 3] += h4.w;
+          }
         }
         if (g + 1 < groups) tmem_ld_32x32b_x32(taddr + (g + 1) * 64, r);
         uint32_t w[16];
@@ -381,7 +442,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       mbar_wait(full2_bar(a), n2[a] & 1u);
       ++n2[a];
       tcgen05_after_thread_sync();
-      epilogue(tmem_base + static_cast<uint32_t>(a * p.P), p.pchunks, p.shift2, false);
+      epilogue(tmem_base + static_cast<uint32_t>(a * p.P), p.pchunks, p.shift2, nullptr, false);
       tcgen05_before_thread_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(empty2_bar(a));
@@ -390,7 +451,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         mbar_wait(full3_bar, n3 & 1u);
         ++n3;
         tcgen05_after_thread_sync();
-        epilogue(tmem_acc3, 4, p.shift3 + nt * 256, true);
+        epilogue(tmem_acc3, 4, p.shift3 + nt * 256, p.xchunks > 0 ? p.shiftd + nt * 256 : nullptr, true);
         tcgen05_before_thread_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(empty3_bar);
@@ -416,16 +477,21 @@ static int bt_check(const UpBneckTailDesc* d) {
   if (d->dtype != UP_FP16 && d->dtype != UP_BF16) return fail(UP_ERR_UNSUPPORTED, "up_bneck_tail: fp16 / bf16 only");
   if (d->planes != 64 && d->planes != 128) return fail(UP_ERR_UNSUPPORTED, "up_bneck_tail: planes must be 64 or 128 (got %d)", d->planes);
   if (d->n <= 0 || d->h <= 0 || d->w <= 0 || d->dil < 1) return fail(UP_ERR_INVALID, "up_bneck_tail: bad dims");
+  if (d->proj_cin < 0 || d->proj_cin % 64 != 0 || d->proj_cin > 1024)
+    return fail(UP_ERR_UNSUPPORTED, "up_bneck_tail: proj_cin must be 0 or a multiple of 64 <= 1024 (got %d)", d->proj_cin);
   return 0;
 }
 
 extern "C" int up_bneck_tail_supported(const UpBneckTailDesc* d) { return bt_check(d); }
 
 extern "C" int up_bneck_tail_fwd(const UpBneckTailDesc* d, const void* t1, const void* w2, const float* shift2,
-                                 const void* w3, const float* shift3, const void* residual, void* y, void* stream) {
+                                 const void* w3, const float* shift3, const void* residual, const void* wd,
+                                 const float* shiftd, void* y, void* stream) {
   UP_CHECK_ARG(d && t1 && w2 && shift2 && w3 && shift3 && residual && y, "up_bneck_tail_fwd: null argument");
   int rc = bt_check(d);
   if (rc) return rc;
+  UP_CHECK_ARG((d->proj_cin > 0) == (wd != nullptr) && (wd != nullptr) == (shiftd != nullptr),
+               "up_bneck_tail_fwd: wd / shiftd go with proj_cin > 0");
   DeviceInfo* di = device_info();
   if (!di) return UP_ERR_CUDA;
   if (!di->tail_attr) {
@@ -461,11 +527,14 @@ extern "C" int up_bneck_tail_fwd(const UpBneckTailDesc* d, const void* t1, const
   p.idesc_res = make_idesc_f16(static_cast<uint32_t>(fmt), 128u, 64u);
   p.shift2 = shift2;
   p.shift3 = shift3;
-  CUtensorMap tmT1, tmR, tmY, tmW2, tmW3;
+  p.xchunks = d->proj_cin / 64;
+  p.shiftd = shiftd;
+  CUtensorMap tmT1, tmR, tmY, tmW2, tmW3, tmWd;
   const uint32_t abox[5] = {64u, static_cast<uint32_t>(p.bw), 1u, static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
   rc = encode_act_map(&tmT1, fmt, t1, d->n, d->h, d->w, d->planes, 1, abox, 128, "tail.t1");
   if (rc) return rc;
-  rc = encode_act_map(&tmR, fmt, residual, d->n, d->h, d->w, 4 * d->planes, 1, abox, 128, "tail.residual");
+  rc = encode_act_map(&tmR, fmt, residual, d->n, d->h, d->w, d->proj_cin > 0 ? d->proj_cin : 4 * d->planes, 1, abox, 128,
+                      "tail.residual");
   if (rc) return rc;
   rc = encode_act_map(&tmY, fmt, y, d->n, d->h, d->w, 4 * d->planes, 1, abox, 128, "tail.y");
   if (rc) return rc;
@@ -483,6 +552,14 @@ extern "C" int up_bneck_tail_fwd(const UpBneckTailDesc* d, const void* t1, const
     rc = encode_map(&tmW3, fmt, 2, w3, dims, st, box, 128, "tail.w3");
     if (rc) return rc;
   }
+  tmWd = tmW3;
+  if (d->proj_cin > 0) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(d->proj_cin), static_cast<uint64_t>(4) * d->planes};
+    const uint64_t st[1] = {static_cast<uint64_t>(d->proj_cin) * 2};
+    const uint32_t box[2] = {64u, 256u};
+    rc = encode_map(&tmWd, fmt, 2, wd, dims, st, box, 128, "tail.wd");
+    if (rc) return rc;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.total_tiles < di->sm_count ? p.total_tiles : di->sm_count);
   cfg.blockDim = dim3(kBtThreads);
@@ -493,8 +570,8 @@ extern "C" int up_bneck_tail_fwd(const UpBneckTailDesc* d, const void* t1, const
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  rc = check_cuda(fmt == 0 ? cudaLaunchKernelEx(&cfg, bneck_tail_kernel<0>, tmT1, tmR, tmY, tmW2, tmW3, p)
-                           : cudaLaunchKernelEx(&cfg, bneck_tail_kernel<1>, tmT1, tmR, tmY, tmW2, tmW3, p),
+  rc = check_cuda(fmt == 0 ? cudaLaunchKernelEx(&cfg, bneck_tail_kernel<0>, tmT1, tmR, tmY, tmW2, tmW3, tmWd, p)
+                           : cudaLaunchKernelEx(&cfg, bneck_tail_kernel<1>, tmT1, tmR, tmY, tmW2, tmW3, tmWd, p),
                   "bneck_tail_kernel launch");
   return rc;
 }

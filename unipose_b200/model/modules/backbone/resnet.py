@@ -83,12 +83,14 @@ class Bottleneck(PlanModule):
         ho, wo = (h - 1) // s + 1, (w - 1) // s + 1
         t1 = b.act(n, h, w, planes)
         b.conv(x, b.packed_conv(self.conv1, self.bn1), t1, "bottleneck.conv1", relu=True)
+        out = b.act(n, ho, wo, planes * 4)
+        if self.downsample is not None and s == 1 and self._emit_tail(b, t1, x, out, proj=self.downsample):
+            return out          # projection shortcut folded into the tail kernel: Wd x never goes to memory
         res = x
         if self.downsample is not None:
             res = b.act(n, ho, wo, planes * 4)
             b.conv(x, b.packed_conv(self.downsample[0], self.downsample[1]), res, "bottleneck.downsample",
                    stride=s, pad=0)
-        out = b.act(n, ho, wo, planes * 4)
         if self._emit_tail(b, t1, res, out):
             return out
         t2 = b.act(n, ho, wo, planes)
@@ -96,25 +98,36 @@ class Bottleneck(PlanModule):
         b.conv(t2, b.packed_conv(self.conv3, self.bn3), out, "bottleneck.conv3", relu=True, residual=res)
         return out
 
-    def _emit_tail(self, b, t1, res, out):
+    def _emit_tail(self, b, t1, res, out, proj=None):
         """conv2 (3x3) + conv3 (1x1 expansion) + residual + ReLU as ONE launch (csrc/bneck_tail.cu) for the
-        bandwidth-bound layers (planes 64 / 128, stride 1, fp16 / bf16): t2 never leaves shared memory."""
+        bandwidth-bound layers (planes 64 / 128, stride 1, fp16 / bf16): t2 never leaves shared memory.
+        proj = the block's `downsample` (1x1 conv + BN, stride 1): `res` is the block INPUT and the projection is
+        computed inside the kernel (UNIPOSE_B200_BNECK_TAIL_PROJ=0: separate launch as before)."""
         import ctypes
         from .... import _lib, ops
         planes = self.conv1.out_channels
         if (os.environ.get("UNIPOSE_B200_BNECK_TAIL", "1") == "0" or b.mode == ops.UP_SPLIT or self.stride != 1 or
-                planes not in (64, 128) or not isinstance(res, ops.Act) or res.c != 4 * planes or t1.c != planes):
+                planes not in (64, 128) or not isinstance(res, ops.Act) or t1.c != planes):
+            return False
+        if proj is None:
+            if res.c != 4 * planes:
+                return False
+        elif (os.environ.get("UNIPOSE_B200_BNECK_TAIL_PROJ", "1") == "0" or res.c % 64 != 0 or
+              proj[0].in_channels != res.c or proj[0].kernel_size != (1, 1) or proj[0].stride != (1, 1)):
             return False
         d = _lib.UpBneckTailDesc()
         d.n, d.h, d.w, d.planes, d.dil, d.dtype = t1.n, t1.h, t1.w, planes, self.dilation, b.mode
+        d.proj_cin = res.c if proj is not None else 0
         if _lib.load().up_bneck_tail_supported(ctypes.byref(d)) != 0:
             return False
         pc2 = b.packed_conv(self.conv2, self.bn2)
         pc3 = b.packed_conv(self.conv3, self.bn3)
+        pcd = b.packed_conv(proj[0], proj[1]) if proj is not None else None
 
-        def launch(keep=(pc2, pc3)):
+        def launch(keep=(pc2, pc3, pcd)):
             _lib.call("up_bneck_tail_fwd", ctypes.byref(d), t1.ptr(), ops._ptr(pc2.w), ops._ptr(pc2.shift), ops._ptr(pc3.w),
-                      ops._ptr(pc3.shift), res.ptr(), out.ptr(), ops._stream())
+                      ops._ptr(pc3.shift), res.ptr(), ops._ptr(pcd.w) if pcd else None,
+                      ops._ptr(pcd.shift) if pcd else None, out.ptr(), ops._stream())
         b.add(launch, "bottleneck.tail")
         return True
 
