@@ -9,8 +9,10 @@
 // the X box of a tap is the dZ pixel tile shifted by the tap's dilated offset (same coordinates as
 // the forward A-operand, incl. the stride-2 parity folding and whole-box skipping of OOB taps).
 //
-// Work item = (pixel split, tap, 128-wide cout block, <=256-wide cin block).  The fp32 accumulator
-// [128 x block_n] lives in TMEM (double buffered); each item writes its partial to
+// Work item = (pixel split, tap, group of `cpi` 128-wide cout blocks, <=256-wide cin block).  cpi = 2 wherever cout has
+// an even number of blocks: the X box of a k-step then feeds TWO accumulators (neither operand has any reuse across
+// k-steps, so the X stream is half of the L2 -> SM bytes: 64 instead of 96 bytes per clock and SM at full MMA rate).
+// The fp32 accumulators [128 x block_n] live in TMEM (double buffered when two sets fit); each item writes its partial to
 // scratch[split][tap][cout][cin] with plain vector stores and a second kernel reduces the splits and
 // scatters to the OIHW fp32 gradient (no atomics).
 //
@@ -37,6 +39,9 @@ struct WgradKParams {
   int tiles_w, tiles_h, tiles_n, m_tiles;
   int splits, tiles_per_split;
   int co_blocks, ci_blocks, block_n;
+  int cpi;         // cout blocks per work item (1 or 2): they share the X box of every k-step
+  int co_items;    // co_blocks / cpi
+  int nacc;        // accumulator SETS in TMEM (2 = double buffered)
   int cout, cin;
   int ckx;     // channels per X box (64, or 16 for the 16-channel inputs)
   int nterms;
@@ -84,8 +89,8 @@ __device__ __forceinline__ WgItem wg_decode(const WgradKParams& p, int item) {
   WgItem it;
   it.cib = item % p.ci_blocks;
   item /= p.ci_blocks;
-  it.cob = item % p.co_blocks;
-  item /= p.co_blocks;
+  it.cob = (item % p.co_items) * p.cpi;
+  item /= p.co_items;
   const int taps = p.taps_h * p.taps_w;
   it.tap = item % taps;
   it.split = item / taps;
@@ -110,7 +115,7 @@ __global__ void __launch_bounds__(256, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int taps = p.taps_h * p.taps_w;
-  const int total_items = p.splits * taps * p.co_blocks * p.ci_blocks;
+  const int total_items = p.splits * taps * p.co_items * p.ci_blocks;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmZ0);
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(256, 1)
   const uint32_t tmem_base = *tmem_slot_ptr;
   // programmatic dependent launch: barrier init and TMEM allocation above overlapped the previous kernel's tail
   pdl_enter();
-  const int a_boxes = 2;                         // 128 cout = 2 x 64
+  const int a_boxes = 2 * p.cpi;                 // 128 cout = 2 x 64 per cout block
   const int b_boxes = p.block_n / p.ckx;         // cin block = b_boxes x ckx
 
   if (warp == 0) {
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(256, 1)
       const int t1 = min(t0 + p.tiles_per_split, p.m_tiles);
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tcgen05_after_thread_sync();
-      const uint32_t tmem_d = tmem_base + acc * p.acc_stride;
+      const uint32_t tmem_d = tmem_base + acc * p.cpi * p.acc_stride;
       uint32_t accumulate = 0;
       for (int mt = t0; mt < t1; ++mt) {
         const int tw = mt % p.tiles_w;
@@ -211,8 +216,14 @@ __global__ void __launch_bounds__(256, 1)
           const uint32_t b_step = (2u * 8u * swz_b) >> 4;
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kWgPix / 16; ++k) {
-              umma_f16(tmem_d, adesc + a_step * k, bdesc + b_step * k, p.idesc, (accumulate | k) ? 1u : 0u);
+            for (int j = 0; j < p.cpi; ++j) {
+              // cout block j of the item: its two A boxes follow block j-1's, its accumulator sits block_n columns on
+              const uint64_t aj = adesc + static_cast<uint64_t>((2u * p.a_box_bytes * j) >> 4);
+              const uint32_t dj = tmem_d + static_cast<uint32_t>(j * p.acc_stride);
+#pragma unroll
+              for (int k = 0; k < kWgPix / 16; ++k) {
+                umma_f16(dj, aj + a_step * k, bdesc + b_step * k, p.idesc, (accumulate | k) ? 1u : 0u);
+              }
             }
             umma_commit(empty_bar(s));
           }
@@ -230,7 +241,7 @@ __global__ void __launch_bounds__(256, 1)
       }
       if (elect_one()) umma_commit(tfull_bar(acc));
       __syncwarp();
-      if (++acc == 2) {
+      if (++acc == p.nacc) {
         acc = 0;
         acc_phase ^= 1u;
       }
@@ -255,37 +266,35 @@ __global__ void __launch_bounds__(256, 1)
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_after_thread_sync();
-      const int co = it.cob * 128 + ew * 32 + lane;
-      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * p.acc_stride;
-      float* dst = p.scratch + ((static_cast<long long>(it.split) * taps + it.tap) * p.cout + co) * p.cin +
-                   it.cib * p.block_n;
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        uint32_t r[32];
-        if (c0 + 32 <= p.block_n) {
+      for (int j = 0; j < p.cpi; ++j) {
+        const int co = (it.cob + j) * 128 + ew * 32 + lane;
+        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + (acc * p.cpi + j) * p.acc_stride;
+        float* dst = p.scratch + ((static_cast<long long>(it.split) * taps + it.tap) * p.cout + co) * p.cin +
+                     it.cib * p.block_n;
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          uint32_t r[32];
+          // block_n == 16: only 16 valid columns; read 32 (the allocation is >= 32 columns) and store 16
           tmem_ld_32x32b_x32(taddr0 + c0, r);
-        } else {
-          // block_n == 16: only 16 valid columns; read 32 (allocation is >= 32 columns) and store 16
-          tmem_ld_32x32b_x32(taddr0 + c0, r);
-        }
-        tmem_ld_wait();
-        if (co < p.cout) {
-          const int ncol = min(32, p.block_n - c0);
+          tmem_ld_wait();
+          if (co < p.cout) {
+            const int ncol = min(32, p.block_n - c0);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (q * 4 < ncol) {
-              float4 v;
-              v.x = any ? __uint_as_float(r[4 * q + 0]) : 0.f;
-              v.y = any ? __uint_as_float(r[4 * q + 1]) : 0.f;
-              v.z = any ? __uint_as_float(r[4 * q + 2]) : 0.f;
-              v.w = any ? __uint_as_float(r[4 * q + 3]) : 0.f;
-              *reinterpret_cast<float4*>(dst + c0 + 4 * q) = v;
+            for (int q = 0; q < 8; ++q) {
+              if (q * 4 < ncol) {
+                float4 v;
+                v.x = any ? __uint_as_float(r[4 * q + 0]) : 0.f;
+                v.y = any ? __uint_as_float(r[4 * q + 1]) : 0.f;
+                v.z = any ? __uint_as_float(r[4 * q + 2]) : 0.f;
+                v.w = any ? __uint_as_float(r[4 * q + 3]) : 0.f;
+                *reinterpret_cast<float4*>(dst + c0 + 4 * q) = v;
+              }
             }
           }
         }
       }
       tcgen05_before_thread_sync();
       mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) {
+      if (++acc == p.nacc) {
         acc = 0;
         acc_phase ^= 1u;
       }
@@ -352,43 +361,44 @@ static int wgrad_plan(const UpConvDesc* d, WgradKParams& p, int sm_count) {
   p.tiles_h = (d->ho + p.bh - 1) / p.bh;
   p.tiles_n = (d->n + p.bn - 1) / p.bn;
   p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int base_items = d->kh * d->kw * p.co_blocks * p.ci_blocks;
-  // Pixel splits: minimise the makespan of the persistent grid, in units of one 64-pixel k-step (~0.27 us of MMA for a
-  // 128 x 256 tile): rounds * tiles_per_split, plus the split reduction (scratch written and read once per split at
-  // ~3 TB/s).  ceil(SMs / items) alone put 162 items on 148 SMs for the 3x3 256->256 layers of layer3: two rounds of 32
-  // k-steps where 8 splits give one round of 36.
-  static const double red_scale = []() {
-    const char* e = getenv("UP_WGRAD_RED_COST");
-    return e ? atof(e) : 1.0;
-  }();
-  static const double item_overhead = []() {
-    const char* e = getenv("UP_WGRAD_ITEM_COST");
-    return e ? atof(e) : 4.0;
-  }();
-  const double red_per_split =
-      red_scale * static_cast<double>(d->kh) * d->kw * d->cout * d->cin * 4.0 * 2.0 / 3e12 / 0.27e-6;
-  int best = 1;
+  // (cout blocks per item, pixel splits): minimise a time model of the persistent grid, in microseconds, calibrated on
+  // B200 (profiles/train_r2_profile.txt, ncu of the layer3 shapes):
+  //   k-step: the main loop runs at the L2 -> SM limit, 11.5 ps per staged byte (48 KB: 0.55 us);
+  //   item:   prologue / pipeline fill / epilogue, 5 us per cout block of the item;
+  //   splits: the scratch is written and read once per split at ~3 TB/s, + 1.5 us for the reduction launch.
+  // cpi = 2 halves the X stream but doubles the splits needed to fill the SMs: it wins for the big layers (decoder 3x3
+  // 320->256: 402 -> 238 us, 3x3 512->512: 111 -> 99 us) and loses for layer3's (3x3 256->256: 44 -> 56 us).
+  // ceil(SMs / items) alone had put 162 items on 148 SMs for the 3x3 256->256 layers: two rounds of 32 k-steps.
+  const double red_us = static_cast<double>(d->kh) * d->kw * d->cout * d->cin * 4.0 * 2.0 / 3e6;
+  const int cpi_hi = (p.co_blocks % 2 == 0 && p.ckx == 64) ? 2 : 1;
+  int cpi_lo = 1;
+  if (const char* e = getenv("UP_WGRAD_CPI")) {     // tuning: force 1 or 2
+    if (e[0] == '2' && cpi_hi == 2) cpi_lo = 2;
+  }
   double best_cost = 1e30;
+  int best = 1, best_cpi = 1;
   const int max_splits = p.m_tiles < 4 * sm_count ? p.m_tiles : 4 * sm_count;
-  for (int sp = 1; sp <= max_splits; ++sp) {
-    const int tps = (p.m_tiles + sp - 1) / sp;
-    const int eff = (p.m_tiles + tps - 1) / tps;
-    if (eff != sp) continue;
-    const long long items = static_cast<long long>(eff) * base_items;
-    const long long rounds = (items + sm_count - 1) / sm_count;
-    const double cost = static_cast<double>(rounds) * (tps + item_overhead) + red_per_split * eff;
-    if (cost < best_cost) {
-      best_cost = cost;
-      best = sp;
+  for (int cpi = cpi_lo; cpi <= cpi_hi; ++cpi) {
+    if (getenv("UP_WGRAD_CPI") && getenv("UP_WGRAD_CPI")[0] == '1' && cpi == 2) break;
+    const int base_items = d->kh * d->kw * (p.co_blocks / cpi) * p.ci_blocks;
+    const double stage_bytes = static_cast<double>(kWgPix) * 2.0 * (128.0 * cpi + p.block_n);
+    const double tk = 11.5e-6 * stage_bytes, t_item = 5.0 * cpi;
+    for (int sp = 1; sp <= max_splits; ++sp) {
+      const int tps = (p.m_tiles + sp - 1) / sp;
+      const int eff = (p.m_tiles + tps - 1) / tps;
+      if (eff != sp) continue;
+      const long long items = static_cast<long long>(eff) * base_items;
+      const long long rounds = (items + sm_count - 1) / sm_count;
+      const double cost = static_cast<double>(rounds) * (tps * tk + t_item) + 1.5 + red_us * eff;
+      if (cost < best_cost) {
+        best_cost = cost;
+        best = sp;
+        best_cpi = cpi;
+      }
     }
   }
-  if (const char* e = getenv("UP_WGRAD_SPLITS_LEGACY")) {
-    if (e[0] == '1') {
-      best = (sm_count + base_items - 1) / base_items;
-      if (best > p.m_tiles) best = p.m_tiles;
-      if (best < 1) best = 1;
-    }
-  }
+  p.cpi = best_cpi;
+  p.co_items = p.co_blocks / p.cpi;
   p.tiles_per_split = (p.m_tiles + best - 1) / best;
   p.splits = (p.m_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   return 0;
@@ -453,7 +463,7 @@ extern "C" int up_conv2d_wgrad(const UpConvDesc* d, const void* x, const void* d
   p.nterms = split ? 3 : 1;
   p.a_box_bytes = kWgPix * 64 * 2;
   p.b_box_bytes = kWgPix * p.ckx * 2;
-  p.a_bytes = 2 * p.a_box_bytes;
+  p.a_bytes = 2 * p.cpi * p.a_box_bytes;
   p.b_bytes = (p.block_n / p.ckx) * p.b_box_bytes;
   if (p.b_bytes < 1024) p.b_bytes = 1024;  // keep every stage 1024-byte aligned (16-channel X boxes are 2 KB anyway)
   const size_t fixed = 1024 + 8 * (2 * kWgMaxStages + 4) + 16;
@@ -465,7 +475,8 @@ extern "C" int up_conv2d_wgrad(const UpConvDesc* d, const void* x, const void* d
   p.idesc = make_idesc_f16(static_cast<uint32_t>(fmt), 128, static_cast<uint32_t>(p.block_n)) | (1u << 15) | (1u << 16);
   p.acc_stride = p.block_n < 32 ? 32 : p.block_n;
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(2 * p.acc_stride)) cols *= 2;
+  p.nacc = (2 * p.cpi * p.acc_stride <= 512) ? 2 : 1;
+  while (cols < static_cast<uint32_t>(p.nacc * p.cpi * p.acc_stride)) cols *= 2;
   p.tmem_cols = cols;
   p.scratch = scratch;
   const int64_t need = static_cast<int64_t>(p.splits) * d->kh * d->kw * d->cout * d->cin * 4;
@@ -494,7 +505,7 @@ extern "C" int up_conv2d_wgrad(const UpConvDesc* d, const void* x, const void* d
     tmZ1 = tmZ0;
     tmX1 = tmX0;
   }
-  const long long total_items = static_cast<long long>(p.splits) * d->kh * d->kw * p.co_blocks * p.ci_blocks;
+  const long long total_items = static_cast<long long>(p.splits) * d->kh * d->kw * p.co_items * p.ci_blocks;
   const int grid = static_cast<int>(total_items < g_wg_sm_count ? total_items : g_wg_sm_count);
   const size_t smem = fixed + static_cast<size_t>(stages) * (p.a_bytes + p.b_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
