@@ -49,6 +49,7 @@ struct BtParams {
   uint32_t idesc_res;    // M128 x N=64
   const float* shift2;   // [P]
   const float* shift3;   // [4P]
+  int obufs;             // output staging buffers of 64 channels (2: leaves room for a 4th ring slot; 4: one whole N-tile)
   int xchunks;           // projection mode: Cx / 64 input-channel chunks of the block input x (0 = identity shortcut)
   const float* shiftd;   // projection mode: [4P] shift of the downsample BatchNorm
 };
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t stgT = smem_base + p.slots * kBtSlotBytes;     // P/64 buffers: t2 tile
   const uint32_t stgO = stgT + 2 * kBtBuf;                       // 4 buffers: one 256-channel N-tile of the output
-  const uint32_t ident = stgO + 4 * kBtBuf;                      // 64 x 64 identity (K-major, 128B swizzle), 8 KB
+  const uint32_t ident = stgO + p.obufs * kBtBuf;                // 64 x 64 identity (K-major, 128B swizzle), 8 KB
   const uint32_t bars = ident + 8192u;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kBtMaxSlots + s); };
@@ -361,18 +362,23 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     }
   } else if (threadIdx.x == 64) {
     // ===================== store thread =====================
-    uint32_t nO = 0;
+    // the 64-channel output groups form one stream q = 0, 1, ...: group q lives in buffer q % obufs; a buffer goes back
+    // to the epilogue as soon as the store that read it has finished reading (one younger store may still be pending)
+    uint32_t q = 0;
+    const uint32_t nb = static_cast<uint32_t>(p.obufs);
     for (int tile = first; tile < p.total_tiles; tile += step) {
       const BtTile t = bt_tile(p, tile);
       for (int nt = 0; nt < p.ntiles; ++nt) {
-        for (int g = 0; g < 4; ++g) {
-          mbar_wait(readyO(g), nO & 1u);
-          tma_store_5d(&tmY, stgO + g * kBtBuf, nt * 256 + g * 64, t.w0, 0, t.h0, t.n0);
+        for (int g = 0; g < 4; ++g, ++q) {
+          const uint32_t b = q % nb;
+          mbar_wait(readyO(b), (q / nb) & 1u);
+          tma_store_5d(&tmY, stgO + b * kBtBuf, nt * 256 + g * 64, t.w0, 0, t.h0, t.n0);
           tma_store_commit();
+          if (q > 0) {
+            tma_store_wait_read<1>();
+            mbar_arrive(availO((q - 1) % nb));
+          }
         }
-        tma_store_wait_read<0>();
-        for (int g = 0; g < 4; ++g) mbar_arrive(availO(g));
-        ++nO;
       }
     }
     tma_store_wait_all<0>();
@@ -391,7 +397,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     auto epilogue = [&](uint32_t tmem_col0, int groups, const float* sh, const float* sh2, bool setO) {
       uint32_t r[32];
       const uint32_t taddr = tmem_col0 + tlane + static_cast<uint32_t>(half * 32);
-      const uint32_t nuse = setO ? nO : nT;
+      const uint32_t nb = static_cast<uint32_t>(p.obufs);
       tmem_ld_32x32b_x32(taddr, r);
       for (int g = 0; g < groups; ++g) {
         const float4* s4 = reinterpret_cast<const float4*>(sh + g * 64 + half * 32);
@@ -420,8 +426,10 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         uint32_t w[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) w[e] = bt_pack2_relu<kFmt>(v[2 * e], v[2 * e + 1]);
-        mbar_wait(setO ? availO(g) : availT(g), (nuse & 1u) ^ 1u);
-        const uint32_t rowaddr = (setO ? stgO : stgT) + g * kBtBuf + rowoff;
+        const uint32_t q = nO * 4u + static_cast<uint32_t>(g);     // output group stream (see the store thread)
+        const uint32_t b = setO ? q % nb : static_cast<uint32_t>(g);
+        mbar_wait(setO ? availO(b) : availT(g), ((setO ? q / nb : nT) & 1u) ^ 1u);
+        const uint32_t rowaddr = (setO ? stgO : stgT) + b * kBtBuf + rowoff;
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           const uint32_t addr = rowaddr + (((static_cast<uint32_t>(half) * 4u + c4) ^ row7) << 4);
@@ -431,7 +439,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(setO ? readyO(g) : s2readyT(g));
+        if (lane == 0) mbar_arrive(setO ? readyO(b) : s2readyT(g));
       }
       if (setO) ++nO; else ++nT;
     };
@@ -517,7 +525,12 @@ extern "C" int up_bneck_tail_fwd(const UpBneckTailDesc* d, const void* t1, const
   p.pchunks = d->planes / 64;
   p.ntiles = (4 * d->planes) / 256;
   p.dil = d->dil;
-  const size_t fixed = 1024 + 6 * kBtBuf + 8192 + 8 * (2 * kBtMaxSlots + 18) + 16;
+  static const int obufs = []() {
+    const char* e = getenv("UP_TAIL_OBUFS");      // tuning: 2 (default, 4 ring slots) or 4 (3 ring slots)
+    return (e && e[0] == '4') ? 4 : 2;
+  }();
+  p.obufs = obufs;
+  const size_t fixed = 1024 + static_cast<size_t>(2 + obufs) * kBtBuf + 8192 + 8 * (2 * kBtMaxSlots + 18) + 16;
   int slots = static_cast<int>((di->max_smem - fixed) / kBtSlotBytes);
   if (slots > kBtMaxSlots) slots = kBtMaxSlots;
   UP_CHECK_ARG(slots >= 2, "up_bneck_tail_fwd: not enough shared memory");
