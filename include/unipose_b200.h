@@ -49,6 +49,12 @@ enum {
                                 pipeline (identity MMA into the fp32 accumulator): y = act(scale*(conv + res) + shift).
                                 Callers fold a BatchNorm scale into the weights and pass scale = 1. */
   UP_FLAG_OUT_NCHW_F32 = 4,  /* write fp32 NCHW [n, cout_valid, ho, wo] instead of 16-bit NHWC */
+  UP_FLAG_PROJ = 16,         /* projection shortcut of a stage's first bottleneck (resnet.py:36-37: out += downsample(x))
+                                inside the same GEMM: `residual` points to a SECOND input x2 [n, ho*proj_stride,
+                                wo*proj_stride, r_cstride] (view r_coff .. r_coff + proj_cin) whose 1x1 projection of
+                                stride proj_stride extends K.  1x1 stride-1 main filter, 16-bit NHWC output, not with
+                                UP_FLAG_RESIDUAL / UP_SPLIT.  Packed filter: [1 + proj_cin / cin][cout][cin] - the
+                                projection's filter follows the main one as proj_cin / cin slices of cin columns. */
   UP_FLAG_STATS = 8          /* RESERVED: per-channel sum / sum-of-squares of the stored output fused into the
                                 epilogue.  Not implemented in this build - up_conv2d_fwd rejects it with an error;
                                 train-mode BatchNorm statistics come from up_bn_stats. */
@@ -108,6 +114,8 @@ typedef struct UpConvDesc {
   int64_t y_plane_stride;
   int64_t r_plane_stride;
   int64_t w_plane_stride;
+  int32_t proj_cin;            /* UP_FLAG_PROJ: channels of the second input that are projected (multiple of cin) */
+  int32_t proj_stride;         /* UP_FLAG_PROJ: 1 or 2 */
 } UpConvDesc;
 
 int up_conv2d_fwd(const UpConvDesc* desc, const void* x, const void* w_packed, const float* scale,

@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported():
 
 def test_conv_desc_struct_layout_matches_header():
     # 28 int32 + 4 int64, no padding surprises
-    assert ctypes.sizeof(_lib.UpConvDesc) == 28 * 4 + 4 * 8
+    assert ctypes.sizeof(_lib.UpConvDesc) == 28 * 4 + 4 * 8 + 2 * 4
     assert _lib.UpConvDesc.x_plane_stride.offset == 28 * 4
 
 

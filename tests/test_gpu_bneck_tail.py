@@ -27,9 +27,10 @@ def _run(m, x, tail, monkeypatch):
     out = m(x.cuda())
     torch.cuda.synchronize()
     names = [n for n, f, s in m.plan_for(x.cuda()).ops if f is not None]
-    # layer1 x3 (block 0 with its projection shortcut inside the kernel) + layer2 blocks 1..3
+    # layer1 x3 (block 0 with its projection shortcut inside the kernel) + layer2 blocks 1..3; the other projection
+    # shortcuts ride in their block's conv3 (UP_FLAG_PROJ): no downsample launch is left
     assert names.count("bottleneck.tail") == (6 if tail else 0), names
-    assert names.count("bottleneck.downsample") == (3 if tail else 4), names
+    assert names.count("bottleneck.downsample") == 0 and names.count("bottleneck.conv3+proj") == (3 if tail else 4), names
     return out.cpu().numpy()
 
 
@@ -58,6 +59,7 @@ def test_projection_shortcut_inside_the_tail_matches_the_separate_launch(monkeyp
     x = O.synth_input(2, 368, 368, seed=5)        # 92x92 maps: partial tiles
     with torch.no_grad():
         ref = O.unipose_forward(x, sd).numpy()
+    monkeypatch.setenv("UNIPOSE_B200_PROJ_FUSE", "0")     # layers 2-4 keep their downsample launches in both runs
     monkeypatch.setenv("UNIPOSE_B200_BNECK_TAIL_PROJ", "0")
     m._plans.clear()
     sep = m(x.cuda()).cpu().numpy()

@@ -11,7 +11,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 from . import build as _build
 
 UP_BF16, UP_FP16, UP_SPLIT = 0, 1, 2
-UP_FLAG_RELU, UP_FLAG_RESIDUAL, UP_FLAG_OUT_NCHW_F32, UP_FLAG_STATS = 1, 2, 4, 8
+UP_FLAG_RELU, UP_FLAG_RESIDUAL, UP_FLAG_OUT_NCHW_F32, UP_FLAG_STATS, UP_FLAG_PROJ = 1, 2, 4, 8, 16
 
 
 class UpConvDesc(ctypes.Structure):
@@ -31,6 +31,7 @@ class UpConvDesc(ctypes.Structure):
         ("x_cextent", c_int32), ("x_wpitch", c_int32),
         ("x_plane_stride", c_int64), ("y_plane_stride", c_int64),
         ("r_plane_stride", c_int64), ("w_plane_stride", c_int64),
+        ("proj_cin", c_int32), ("proj_stride", c_int32),
     ]
 
 

@@ -74,6 +74,8 @@ struct ConvKParams {
   int cluster;     // CTAs per cluster (1, 2 or 4): they share one weight tile per k-block via TMA multicast
   int res_terms;   // residual tiles (128 px x 64 ch, 16 KB) per 64-channel group (0 = none, 1, or 2 in split mode)
   int res_per_slot;  // how many of them share one ring slot (the slot is a_bytes + b_bytes wide)
+  int proj_taps;     // UP_FLAG_PROJ: extra K - a second input (tensor map A1) projected by proj_taps more "taps" of the
+  int proj_coff;     //   packed filter (cin columns each); proj_coff = first channel of that input's view
   int bsplit;        // experiment (UP_DEBUG_BSPLIT): fetch the weight tile with this many TMA instructions
   int tall;          // 3x3 stride-1 convs on single-image tiles: ONE activation box of bh + 2*dil rows per (kw, chunk)
                      // serves the three filter rows through row-offset descriptors (a_bytes = tall box, b_bytes = 3 taps)
@@ -406,6 +408,35 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
       }
+      // projection shortcut (UP_FLAG_PROJ): k-blocks over the SECOND input (tensor map A1; a stride-2 map reads parity
+      // plane 0 at offset 0 = pixel (2h, 2w)) against the filter rows that follow the main taps
+      for (int j = 0; j < p.proj_taps; ++j) {
+        const int brow = (taps + j) * p.cout + brow_nt;
+        for (int chunk = 0; chunk < p.chunks; ++chunk) {
+          const int c = p.proj_coff + (j * p.chunks + chunk) * p.ck;
+          const uint32_t dst = smem_base + s * stage_bytes;
+          const bool mine = (issued & 1) == which;
+          if (mine) mbar_wait(empty_bar(s), wait_par, 16000000000LL);
+          if (mine && elect_one()) {
+            if constexpr (kPair) {
+              if (crank == 0) mbar_arrive_expect_tx(full_bar(s), 2u * stage_bytes);
+              else mbar_arrive_remote(full_bar(s), 0u);
+              tma_load_5d_2cta(&tmA1, dst, full_bar(s), c, t.w0, 0, t.h0, t.n0);
+              tma_load_2d_2cta(&tmB, dst + p.a_bytes, full_bar(s), chunk * p.ck,
+                               brow + static_cast<int>(crank) * (p.block_n >> 1));
+            } else {
+              mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+              tma_load_5d(&tmA1, dst, full_bar(s), c, t.w0, 0, t.h0, t.n0);
+              tma_load_2d(&tmB, dst + p.a_bytes, full_bar(s), chunk * p.ck, brow);
+            }
+          }
+          ++issued;
+          if (++s == static_cast<uint32_t>(p.stages)) {
+            s = 0;
+            wait_par ^= 1u;
+          }
+        }
+      }
       // residual slots: up to res_per_slot tiles [128 px x 64 ch] side by side; their B operand is the resident identity
       for (int u0 = 0; u0 < res_units; u0 += p.res_per_slot) {
         const int u_end = min(u0 + p.res_per_slot, res_units);
@@ -455,7 +486,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       int kh_lo, kh_hi, kw_lo, kw_hi;
       tap_range(p, p.taps_h, p.pad_h, t.h0, p.bh, p.Hq, kh_lo, kh_hi);
       tap_range(p, p.taps_w, p.pad_w, t.w0, p.bw, p.Wq, kw_lo, kw_hi);
-      const int nkb_conv = (p.tall ? 1 : (kh_hi - kh_lo + 1)) * (kw_hi - kw_lo + 1) * p.chunks * p.nterms;
+      const int nkb_conv = (p.tall ? 1 : (kh_hi - kh_lo + 1)) * (kw_hi - kw_lo + 1) * p.chunks * p.nterms +
+                           p.proj_taps * p.chunks;   // projection k-blocks look like ordinary ones to the issuer
       const int res_units = (p.block_n >> 6) * p.res_terms;
       const int nkb = nkb_conv + (p.res_terms ? (res_units + p.res_per_slot - 1) / p.res_per_slot : 0);
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -736,6 +768,21 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
     UP_CHECK_ARG((reinterpret_cast<uintptr_t>(residual) & 15) == 0, "up_conv2d_fwd: residual must be 16B aligned");
     if (split) UP_CHECK_ARG(d->r_plane_stride % 8 == 0 && d->r_plane_stride > 0, "up_conv2d_fwd: bad r_plane_stride");
   }
+  const bool has_proj = (d->flags & UP_FLAG_PROJ) != 0;
+  if (has_proj) {
+    // second input x2 (passed in `residual`, viewed through r_cstride / r_coff): its 1x1 projection of stride
+    // proj_stride is accumulated into the same tile; the packed filter holds proj_cin / cin extra "taps" of cin columns
+    UP_CHECK_ARG(residual != nullptr && !has_res && !split && !nchw, "up_conv2d_fwd: UP_FLAG_PROJ needs the second input "
+                 "in `residual`, 16-bit NHWC output, no UP_FLAG_RESIDUAL, no split mode");
+    UP_CHECK_ARG(d->kh == 1 && d->kw == 1 && d->stride == 1 && groups == 1 && ck == 64 && d->x_cextent == 0,
+                 "up_conv2d_fwd: UP_FLAG_PROJ needs a 1x1 stride-1 main filter with cin %% 64 == 0");
+    UP_CHECK_ARG(d->proj_cin > 0 && d->proj_cin % d->cin == 0, "up_conv2d_fwd: proj_cin (%d) must be a multiple of cin (%d)",
+                 d->proj_cin, d->cin);
+    UP_CHECK_ARG(d->proj_stride == 1 || d->proj_stride == 2, "up_conv2d_fwd: proj_stride must be 1 or 2");
+    UP_CHECK_ARG(d->r_cstride % 8 == 0 && d->r_coff % 8 == 0 && d->r_coff + d->proj_cin <= d->r_cstride,
+                 "up_conv2d_fwd: bad projection input channel view");
+    UP_CHECK_ARG((reinterpret_cast<uintptr_t>(residual) & 15) == 0, "up_conv2d_fwd: projection input must be 16B aligned");
+  }
   // every tile must see at least one in-bounds tap: the centre of the receptive field has to hit the image
   UP_CHECK_ARG(d->pad_h <= (d->kh - 1) * d->dil && d->pad_w <= (d->kw - 1) * d->dil,
                "up_conv2d_fwd: padding larger than the filter extent");
@@ -811,10 +858,10 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
     p.pair = nchw ? 0 : 1;
     if (const char* e = getenv("UP_PAIR")) p.pair = (e[0] == '1') ? 1 : 0;
   }
-  if (!p.pair && !getenv("UP_CLUSTER")) p.cluster = 1;   // plain multicast clusters measured slower than independent CTAs
+  if (!p.pair && (has_proj || !getenv("UP_CLUSTER"))) p.cluster = 1;   // plain multicast clusters measured slower than independent CTAs
   if (const char* e = getenv("UP_DEBUG_BSPLIT")) {
     const int v = atoi(e);
-    if (p.cluster == 1 && (v == 2 || v == 4) && block_n % (8 * v) == 0) p.bsplit = v;
+    if (p.cluster == 1 && !has_proj && (v == 2 || v == 4) && block_n % (8 * v) == 0) p.bsplit = v;
   }
   if (p.pair) p.b_bytes = static_cast<uint32_t>(block_n / 2) * ck * 2;   // each CTA of the pair holds half of the weight tile
   // Filter-row reuse ("tall" activation box): 3x3, stride 1, same padding, single-image tiles with bw a multiple of 8
@@ -882,6 +929,8 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   p.out_c_total = d->out_c_total > 0 ? d->out_c_total : d->cout_valid;
   p.y_coff = d->y_coff;
   p.r_coff = d->r_coff;
+  p.proj_taps = has_proj ? d->proj_cin / d->cin : 0;
+  p.proj_coff = d->r_coff;
   p.scale = scale;
   p.shift = shift;
   p.out_f32 = nchw ? static_cast<float*>(y) : nullptr;
@@ -907,11 +956,15 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
     rc = encode_act_map(&tmA1, fmt, static_cast<const uint16_t*>(x) + d->x_plane_stride, n_total, d->h, d->w,
                         d->x_cstride, d->stride, abox, sw, "x.lo", d->x_cextent, d->x_wpitch);
     if (rc) return rc;
+  } else if (has_proj) {
+    rc = encode_act_map(&tmA1, fmt, residual, d->n, d->ho * d->proj_stride, d->wo * d->proj_stride, d->r_cstride,
+                        d->proj_stride, abox, sw, "x2 (projection input)");
+    if (rc) return rc;
   } else {
     tmA1 = tmA0;
   }
   {
-    const int taps = d->kh * d->kw;
+    const int taps = d->kh * d->kw + p.proj_taps;   // the projection's filter rows follow the main taps
     const uint64_t dims[2] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(split ? 2 : 1) * taps * d->cout};
     const uint64_t st[1] = {static_cast<uint64_t>(d->cin) * 2};
     const uint32_t box[2] = {static_cast<uint32_t>(ck), static_cast<uint32_t>(block_n / p.cluster / p.bsplit)};

@@ -87,6 +87,12 @@ class Bottleneck(PlanModule):
         if self.downsample is not None and s == 1 and self._emit_tail(b, t1, x, out, proj=self.downsample):
             return out          # projection shortcut folded into the tail kernel: Wd x never goes to memory
         res = x
+        pcp = self._packed_conv3_proj(b, x) if self.downsample is not None else None
+        if pcp is not None:
+            t2 = b.act(n, ho, wo, planes)
+            b.conv(t1, b.packed_conv(self.conv2, self.bn2), t2, "bottleneck.conv2", stride=s, dil=d, pad=d, relu=True)
+            b.conv(t2, pcp, out, "bottleneck.conv3+proj", relu=True, proj=(x, s))
+            return out
         if self.downsample is not None:
             res = b.act(n, ho, wo, planes * 4)
             b.conv(x, b.packed_conv(self.downsample[0], self.downsample[1]), res, "bottleneck.downsample",
@@ -97,6 +103,37 @@ class Bottleneck(PlanModule):
         b.conv(t1, b.packed_conv(self.conv2, self.bn2), t2, "bottleneck.conv2", stride=s, dil=d, pad=d, relu=True)
         b.conv(t2, b.packed_conv(self.conv3, self.bn3), out, "bottleneck.conv3", relu=True, residual=res)
         return out
+
+    def _packed_conv3_proj(self, b, x):
+        """conv3 and the projection shortcut (`downsample`: 1x1 conv of stride s + BN, resnet.py:36-37,75-79) as ONE
+        GEMM: out = ReLU([W3*s3 | Wd*sd] . [t2 ; x_strided] + (shift3 + shiftd)) - K grows by the block's input
+        channels, the shortcut tensor and the downsample launch disappear (UP_FLAG_PROJ).  Returns the packed filter
+        [1 + inplanes / planes][cout][planes] or None when the shape does not qualify."""
+        from .... import engine, ops
+        conv_d, bn_d = self.downsample[0], self.downsample[1]
+        planes, s = self.conv1.out_channels, self.stride
+        cout = 4 * planes
+        if (os.environ.get("UNIPOSE_B200_PROJ_FUSE", "1") == "0" or b.mode == ops.UP_SPLIT or planes % 64 or
+                not isinstance(x, ops.Act) or x.c != conv_d.in_channels or x.c % planes or s not in (1, 2) or
+                x.h % s or x.w % s or conv_d.kernel_size != (1, 1) or conv_d.stride != (s, s) or
+                conv_d.bias is not None or conv_d.out_channels != cout):
+            return None
+        pt = x.c // planes
+        dev, f32 = b.device, torch.float32
+        wbuf = torch.empty((1, 1 + pt, cout, planes), dtype=torch.float16 if b.mode == ops.UP_FP16 else torch.bfloat16,
+                           device=dev)
+        pc3 = b.packed_conv(self.conv3, self.bn3, wbuf=wbuf[:, 0:1])
+        fold_d = torch.empty(bn_d.num_features, dtype=f32, device=dev)
+        scale_d, shift_d, shift_sum = (torch.empty(cout, dtype=f32, device=dev) for _ in range(3))
+        wt = b.plan.weights
+        wt.add_epilogue(scale_d, shift_d, cout, bn=bn_d, fold_scale=fold_d)
+        for j in range(pt):          # slice j of the projection's input channels = filter "tap" 1 + j
+            wt.add_pack(lambda: conv_d.weight, wbuf[0, 1 + j], cout, planes, ci_off=j * planes, cin_slice=planes,
+                        row_scale=fold_d, scale_period=bn_d.num_features)
+        bns = [t for bn in (self.bn3, bn_d) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var)]
+        b.plan.pack_jobs.append(engine._PackJob(bns, lambda: torch.add(pc3.shift, shift_d, out=shift_sum)))
+        b.plan.buffers.append((wbuf, scale_d, shift_d, fold_d))
+        return ops.PackedConv(wbuf, pc3.scale, shift_sum, 1, 1, cout, planes, cout, planes, b.mode)
 
     def _emit_tail(self, b, t1, res, out, proj=None):
         """conv2 (3x3) + conv3 (1x1 expansion) + residual + ReLU as ONE launch (csrc/bneck_tail.cu) for the

@@ -12,7 +12,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (UP_BF16, UP_FLAG_OUT_NCHW_F32, UP_FLAG_RELU, UP_FLAG_RESIDUAL, UP_FP16, UP_SPLIT, UpConvDesc)
+from ._lib import (UP_BF16, UP_FLAG_OUT_NCHW_F32, UP_FLAG_PROJ, UP_FLAG_RELU, UP_FLAG_RESIDUAL, UP_FP16, UP_SPLIT,
+                   UpConvDesc)
 
 PRECISIONS = {"bf16": UP_BF16, "fp16": UP_FP16, "fp32": UP_SPLIT}
 
@@ -167,8 +168,10 @@ def make_packed_conv(w_oihw, mode, scale=None, shift=None, bias=None, cout=None,
 def conv2d(x, pc: PackedConv, y, *, stride: int = 1, dil: int = 1, pad=None, relu: bool = False,
            residual=None, ho: Optional[int] = None, wo: Optional[int] = None, x_groups: int = 1,
            x_group_nstride: int = 0, cout_valid: Optional[int] = None, out_c_total: Optional[int] = None,
-           x_window=None) -> None:
-    """y = epilogue(conv(x, w)).  `y` is an Act/View (NHWC 16-bit) or an fp32 NCHW tensor [n, cout_valid, ho, wo]."""
+           x_window=None, proj=None) -> None:
+    """y = epilogue(conv(x, w)).  `y` is an Act/View (NHWC 16-bit) or an fp32 NCHW tensor [n, cout_valid, ho, wo].
+    proj = (x2, stride): UP_FLAG_PROJ - the 1x1 / `stride` projection of the second input x2 (all of its view's
+    channels) extends K; `pc.w` then holds 1 + x2.c / pc.cin filter slices (see include/unipose_b200.h)."""
     xv = as_view(x)
     if pad is None:
         pad = (dil * (pc.kh - 1) // 2, dil * (pc.kw - 1) // 2)
@@ -199,6 +202,14 @@ def conv2d(x, pc: PackedConv, y, *, stride: int = 1, dil: int = 1, pad=None, rel
         flags |= UP_FLAG_RESIDUAL
         d.r_cstride, d.r_coff, d.r_plane_stride = rv.act.c, rv.coff, rv.act.plane_stride
         rptr = rv.ptr()
+    if proj is not None:
+        assert residual is None, "UP_FLAG_PROJ excludes UP_FLAG_RESIDUAL"
+        pv, pstride = as_view(proj[0]), int(proj[1])
+        assert (pv.n, pv.h, pv.w) == (xv.n, ho * pstride, wo * pstride), ((pv.n, pv.h, pv.w), (xv.n, ho, wo, pstride))
+        assert pc.w.numel() == (1 + pv.c // pc.cin) * pc.cout * pc.cin and pv.c % pc.cin == 0
+        flags |= UP_FLAG_PROJ
+        d.r_cstride, d.r_coff, d.proj_cin, d.proj_stride = pv.act.c, pv.coff, pv.c, pstride
+        rptr = pv.ptr()
     if isinstance(y, torch.Tensor):
         flags |= UP_FLAG_OUT_NCHW_F32
         d.cout_valid = cout_valid if cout_valid is not None else pc.cout_real
