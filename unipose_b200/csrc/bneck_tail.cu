@@ -32,7 +32,8 @@ constexpr int kBtEpiWarp0 = 4;
 constexpr int kBtEpiThreads = 256;
 constexpr int kBtMaxSlots = 4;
 constexpr uint32_t kBtABytes = 16384;
-constexpr uint32_t kBtSlotBytes = 32768;
+constexpr uint32_t kBtSlotBytes = 32768;   // a filter N-tile (256 rows x 64 ch) or two 64-channel activation chunks;
+                                           // also the ring slot size unless the tall conv2 boxes need more
 constexpr uint32_t kBtBuf = 16384;
 
 struct BtParams {
@@ -52,6 +53,14 @@ struct BtParams {
   int obufs;             // output staging buffers of 64 channels (2: leaves room for a 4th ring slot; 4: one whole N-tile)
   int xchunks;           // projection mode: Cx / 64 input-channel chunks of the block input x (0 = identity shortcut)
   const float* shiftd;   // projection mode: [4P] shift of the downsample BatchNorm
+  // Filter-row reuse for conv2 (the conv kernel's "tall" boxes): single-image tiles with bw % 8 == 0 fetch ONE
+  // activation box of bh + 2*dil rows per (kw, chunk); filter row r reads it r*dil*bw pixel rows further down (a
+  // multiple of the 1024-byte swizzle atom) against its own filter tile - 3 slots of (tall box + 3 filter tiles)
+  // instead of 9 of (16 KB + 1 filter tile): the nine halo taps no longer re-read the tile from L2
+  int tall;
+  uint32_t slot_bytes;     // ring slot stride
+  uint32_t tall_a_bytes;   // (bh + 2*dil) * bw * 128
+  uint32_t tall_a_step;    // dil * bw * 128 >> 4: descriptor step between filter rows
 };
 
 struct BtTile {
@@ -90,11 +99,11 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     bneck_tail_kernel(const __grid_constant__ CUtensorMap tmT1, const __grid_constant__ CUtensorMap tmR,
                       const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW2,
                       const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmWd,
-                      const BtParams p) {
+                      const __grid_constant__ CUtensorMap tmT1t, const BtParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t stgT = smem_base + p.slots * kBtSlotBytes;     // P/64 buffers: t2 tile
+  const uint32_t stgT = smem_base + p.slots * p.slot_bytes;     // P/64 buffers: t2 tile
   const uint32_t stgO = stgT + 2 * kBtBuf;                       // 4 buffers: one 256-channel N-tile of the output
   const uint32_t ident = stgO + p.obufs * kBtBuf;                // 64 x 64 identity (K-major, 128B swizzle), 8 KB
   const uint32_t bars = ident + 8192u;
@@ -117,6 +126,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmT1);
+    tma_prefetch_desc(&tmT1t);
     tma_prefetch_desc(&tmR);
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmW3);
@@ -183,12 +193,28 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       bt_taps(p.dil, t.h0, p.bh, p.H, kh_lo, kh_hi);
       bt_taps(p.dil, t.w0, p.bw, p.W, kw_lo, kw_hi);
       const uint32_t bbytes = static_cast<uint32_t>(p.P) * 128u;
+      if (p.tall) {
+        for (int kw = kw_lo; kw <= kw_hi; ++kw)
+          for (int c = 0; c < p.pchunks; ++c) {
+            mbar_wait(empty_bar(slot), par, 16000000000LL);
+            if (elect_one()) {
+              const uint32_t dst = smem_base + slot * p.slot_bytes;
+              mbar_arrive_expect_tx(full_bar(slot), p.tall_a_bytes + 3u * bbytes);
+              tma_load_5d(&tmT1t, dst, full_bar(slot), c * 64, t.w0 + (kw - 1) * p.dil, 0, t.h0 - p.dil, t.n0);
+              for (int r = 0; r < 3; ++r)
+                tma_load_2d(&tmW2, dst + p.tall_a_bytes + r * bbytes, full_bar(slot), c * 64, (r * 3 + kw) * p.P);
+            }
+            __syncwarp();
+            advance();
+          }
+        return;
+      }
       for (int kh = kh_lo; kh <= kh_hi; ++kh)
         for (int kw = kw_lo; kw <= kw_hi; ++kw)
           for (int c = 0; c < p.pchunks; ++c) {
             mbar_wait(empty_bar(slot), par, 16000000000LL);
             if (elect_one()) {
-              const uint32_t dst = smem_base + slot * kBtSlotBytes;
+              const uint32_t dst = smem_base + slot * p.slot_bytes;
               mbar_arrive_expect_tx(full_bar(slot), kBtABytes + bbytes);
               tma_load_5d(&tmT1, dst, full_bar(slot), c * 64, t.w0 + (kw - 1) * p.dil, 0, t.h0 + (kh - 1) * p.dil, t.n0);
               tma_load_2d(&tmW2, dst + kBtABytes, full_bar(slot), c * 64, (kh * 3 + kw) * p.P);
@@ -204,7 +230,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         for (int c = 0; c < p.pchunks; ++c) {
           mbar_wait(empty_bar(slot), par, 16000000000LL);
           if (elect_one()) {
-            const uint32_t dst = smem_base + slot * kBtSlotBytes;
+            const uint32_t dst = smem_base + slot * p.slot_bytes;
             mbar_arrive_expect_tx(full_bar(slot), kBtSlotBytes);
             tma_load_2d(&tmW3, dst, full_bar(slot), c * 64, nt * 256);
           }
@@ -217,14 +243,14 @@ __global__ void __launch_bounds__(kBtThreads, 1)
             mbar_wait(empty_bar(slot), par, 16000000000LL);
             if (elect_one()) {
               mbar_arrive_expect_tx(full_bar(slot), kBtABytes);
-              tma_load_5d(&tmR, smem_base + slot * kBtSlotBytes, full_bar(slot), xc * 64, t.w0, 0, t.h0, t.n0);
+              tma_load_5d(&tmR, smem_base + slot * p.slot_bytes, full_bar(slot), xc * 64, t.w0, 0, t.h0, t.n0);
             }
             __syncwarp();
             advance();
             mbar_wait(empty_bar(slot), par, 16000000000LL);
             if (elect_one()) {
               mbar_arrive_expect_tx(full_bar(slot), kBtSlotBytes);
-              tma_load_2d(&tmWd, smem_base + slot * kBtSlotBytes, full_bar(slot), xc * 64, nt * 256);
+              tma_load_2d(&tmWd, smem_base + slot * p.slot_bytes, full_bar(slot), xc * 64, nt * 256);
             }
             __syncwarp();
             advance();
@@ -235,7 +261,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         for (int r2 = 0; r2 < 2; ++r2) {
           mbar_wait(empty_bar(slot), par, 16000000000LL);
           if (elect_one()) {
-            const uint32_t dst = smem_base + slot * kBtSlotBytes;
+            const uint32_t dst = smem_base + slot * p.slot_bytes;
             mbar_arrive_expect_tx(full_bar(slot), kBtSlotBytes);
             for (int cc = 0; cc < 2; ++cc)
               tma_load_5d(&tmR, dst + cc * kBtABytes, full_bar(slot), nt * 256 + (2 * r2 + cc) * 64, t.w0, 0, t.h0, t.n0);
@@ -262,7 +288,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     const uint64_t adesc0 = make_smem_desc_kmajor(smem_base, 128);
     const uint64_t tdesc0 = make_smem_desc_kmajor(stgT, 128);
     const uint64_t identdesc = make_smem_desc_kmajor(ident, 128);
-    const uint32_t slot_step = kBtSlotBytes >> 4;
+    const uint32_t slot_step = p.slot_bytes >> 4;
     uint32_t n2[2] = {0u, 0u};      // uses of the conv2 accumulators
     uint32_t n3 = 0;                // uses of the output accumulator
     uint32_t nT = 0;                // t2 tiles consumed (s2readyT parity)
@@ -271,7 +297,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       int kh_lo, kh_hi, kw_lo, kw_hi;
       bt_taps(p.dil, t.h0, p.bh, p.H, kh_lo, kh_hi);
       bt_taps(p.dil, t.w0, p.bw, p.W, kw_lo, kw_hi);
-      const int nkb = (kh_hi - kh_lo + 1) * (kw_hi - kw_lo + 1) * p.pchunks;
+      const int nkb = (p.tall ? 1 : (kh_hi - kh_lo + 1)) * (kw_hi - kw_lo + 1) * p.pchunks;
       const int a = it & 1;
       mbar_wait(empty2_bar(a), (n2[a] & 1u) ^ 1u);
       ++n2[a];
@@ -282,9 +308,20 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         tcgen05_after_thread_sync();
         if (elect_one()) {
           const uint64_t ad = adesc0 + static_cast<uint64_t>(slot_step * slot);
-          const uint64_t bd = ad + static_cast<uint64_t>(kBtABytes >> 4);
+          if (p.tall) {
+            // three filter rows from ONE activation box (all three always: out-of-image rows are zero-filled)
+            const uint64_t bd0 = ad + static_cast<uint64_t>(p.tall_a_bytes >> 4);
+            for (int r = 0; r < 3; ++r) {
+              const uint64_t ar = ad + static_cast<uint64_t>(p.tall_a_step * r);
+              const uint64_t br = bd0 + static_cast<uint64_t>((static_cast<uint32_t>(p.P) * 128u >> 4) * r);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tacc, ad + 2u * k, bd + 2u * k, p.idesc2, (kb | k) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) umma_f16(tacc, ar + 2u * k, br + 2u * k, p.idesc2, (kb | r | k) ? 1u : 0u);
+            }
+          } else {
+            const uint64_t bd = ad + static_cast<uint64_t>(kBtABytes >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tacc, ad + 2u * k, bd + 2u * k, p.idesc2, (kb | k) ? 1u : 0u);
+          }
           umma_commit(empty_bar(slot));
           if (kb == nkb - 1) umma_commit(full2_bar(a));
         }
@@ -531,7 +568,24 @@ extern "C" int up_bneck_tail_fwd(const UpBneckTailDesc* d, const void* t1, const
   }();
   p.obufs = obufs;
   const size_t fixed = 1024 + static_cast<size_t>(2 + obufs) * kBtBuf + 8192 + 8 * (2 * kBtMaxSlots + 18) + 16;
-  int slots = static_cast<int>((di->max_smem - fixed) / kBtSlotBytes);
+  p.tall = 0;
+  p.slot_bytes = kBtSlotBytes;
+  p.tall_a_bytes = static_cast<uint32_t>(p.bh + 2 * d->dil) * p.bw * 128u;
+  p.tall_a_step = (static_cast<uint32_t>(d->dil) * p.bw * 128u) >> 4;
+  {
+    static const bool want = []() {
+      const char* e = getenv("UP_TAIL_TALL");
+      return !(e && e[0] == '0');
+    }();
+    // one tall box must be smaller than the two extra 16 KB boxes it replaces, and three slots must still fit
+    const uint32_t slot = p.tall_a_bytes + 3u * static_cast<uint32_t>(d->planes) * 128u;
+    if (want && p.bn == 1 && p.bw % 8 == 0 && p.bh + 2 * d->dil <= 256 && p.tall_a_bytes <= 2u * kBtABytes &&
+        slot >= kBtSlotBytes && fixed + 3u * static_cast<size_t>(slot) <= di->max_smem) {
+      p.tall = 1;
+      p.slot_bytes = slot;
+    }
+  }
+  int slots = static_cast<int>((di->max_smem - fixed) / p.slot_bytes);
   if (slots > kBtMaxSlots) slots = kBtMaxSlots;
   UP_CHECK_ARG(slots >= 2, "up_bneck_tail_fwd: not enough shared memory");
   p.slots = slots;
@@ -542,10 +596,16 @@ extern "C" int up_bneck_tail_fwd(const UpBneckTailDesc* d, const void* t1, const
   p.shift3 = shift3;
   p.xchunks = d->proj_cin / 64;
   p.shiftd = shiftd;
-  CUtensorMap tmT1, tmR, tmY, tmW2, tmW3, tmWd;
+  CUtensorMap tmT1, tmR, tmY, tmW2, tmW3, tmWd, tmT1t;
   const uint32_t abox[5] = {64u, static_cast<uint32_t>(p.bw), 1u, static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
   rc = encode_act_map(&tmT1, fmt, t1, d->n, d->h, d->w, d->planes, 1, abox, 128, "tail.t1");
   if (rc) return rc;
+  tmT1t = tmT1;
+  if (p.tall) {
+    const uint32_t tbox[5] = {64u, static_cast<uint32_t>(p.bw), 1u, static_cast<uint32_t>(p.bh + 2 * d->dil), 1u};
+    rc = encode_act_map(&tmT1t, fmt, t1, d->n, d->h, d->w, d->planes, 1, tbox, 128, "tail.t1 (tall box)");
+    if (rc) return rc;
+  }
   rc = encode_act_map(&tmR, fmt, residual, d->n, d->h, d->w, d->proj_cin > 0 ? d->proj_cin : 4 * d->planes, 1, abox, 128,
                       "tail.residual");
   if (rc) return rc;
@@ -576,15 +636,15 @@ extern "C" int up_bneck_tail_fwd(const UpBneckTailDesc* d, const void* t1, const
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.total_tiles < di->sm_count ? p.total_tiles : di->sm_count);
   cfg.blockDim = dim3(kBtThreads);
-  cfg.dynamicSmemBytes = fixed + static_cast<size_t>(slots) * kBtSlotBytes;
+  cfg.dynamicSmemBytes = fixed + static_cast<size_t>(slots) * p.slot_bytes;
   cfg.stream = static_cast<cudaStream_t>(stream);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  rc = check_cuda(fmt == 0 ? cudaLaunchKernelEx(&cfg, bneck_tail_kernel<0>, tmT1, tmR, tmY, tmW2, tmW3, tmWd, p)
-                           : cudaLaunchKernelEx(&cfg, bneck_tail_kernel<1>, tmT1, tmR, tmY, tmW2, tmW3, tmWd, p),
+  rc = check_cuda(fmt == 0 ? cudaLaunchKernelEx(&cfg, bneck_tail_kernel<0>, tmT1, tmR, tmY, tmW2, tmW3, tmWd, tmT1t, p)
+                           : cudaLaunchKernelEx(&cfg, bneck_tail_kernel<1>, tmT1, tmR, tmY, tmW2, tmW3, tmWd, tmT1t, p),
                   "bneck_tail_kernel launch");
   return rc;
 }
