@@ -205,11 +205,15 @@ typedef struct UpBneckTailDesc {
                           `downsample` = 1x1 conv + BN, stride 1): `residual` = the block input x [n,h,w,proj_cin],
                           wd packed [1][4*planes][proj_cin] (BN scale folded in), shiftd fp32 [4*planes] -
                           Wd x is accumulated into the output accumulator, the shortcut tensor is never written */
+  int32_t next_planes; /* 0, or (planes 64 only) 64 / 128: ALSO compute the following bottleneck's conv1 + bn1 + ReLU
+                          (resnet.py:25-27: 1x1, 4*planes -> next_planes, stride 1) from the output tile while it is on
+                          chip: t1n [n,h,w,next_planes] = ReLU(w1n . y + shift1n), w1n packed [1][next_planes][4*planes]
+                          (BN scale folded in).  The following block then starts at its 3x3 conv. */
 } UpBneckTailDesc;
 int up_bneck_tail_supported(const UpBneckTailDesc* desc);
 int up_bneck_tail_fwd(const UpBneckTailDesc* desc, const void* t1, const void* w2, const float* shift2, const void* w3,
                       const float* shift3, const void* residual, const void* wd, const float* shiftd, void* y,
-                      void* stream);
+                      const void* w1n, const float* shift1n, void* t1n, void* stream);
 
 /* Debug aid (UP_DEBUG_TIMING=1): per-CTA phase timestamps (ns) of the last up_wasp_chain_fwd launch, 160 CTAs x 32 slots. */
 int up_debug_chain_timing(unsigned long long* h_out);

@@ -21,6 +21,10 @@ def _model(precision, seed=0):
     return m.cuda().eval(), sd
 
 
+def _tails(names):
+    return names.count("bottleneck.tail") + names.count("bottleneck.tail+conv1")
+
+
 def _run(m, x, tail, monkeypatch):
     monkeypatch.setenv("UNIPOSE_B200_BNECK_TAIL", "1" if tail else "0")
     m._plans.clear()
@@ -29,7 +33,7 @@ def _run(m, x, tail, monkeypatch):
     names = [n for n, f, s in m.plan_for(x.cuda()).ops if f is not None]
     # layer1 x3 (block 0 with its projection shortcut inside the kernel) + layer2 blocks 1..3; the other projection
     # shortcuts ride in their block's conv3 (UP_FLAG_PROJ): no downsample launch is left
-    assert names.count("bottleneck.tail") == (6 if tail else 0), names
+    assert _tails(names) == (6 if tail else 0), names
     assert names.count("bottleneck.downsample") == 0 and names.count("bottleneck.conv3+proj") == (3 if tail else 4), names
     return out.cpu().numpy()
 
@@ -64,13 +68,41 @@ def test_projection_shortcut_inside_the_tail_matches_the_separate_launch(monkeyp
     m._plans.clear()
     sep = m(x.cuda()).cpu().numpy()
     names = [n for n, f, s in m.plan_for(x.cuda()).ops if f is not None]
-    assert names.count("bottleneck.tail") == 6 and names.count("bottleneck.downsample") == 4
+    assert _tails(names) == 6 and names.count("bottleneck.downsample") == 4
     monkeypatch.setenv("UNIPOSE_B200_BNECK_TAIL_PROJ", "1")
     m._plans.clear()
     fused = m(x.cuda()).cpu().numpy()
     names = [n for n, f, s in m.plan_for(x.cuda()).ops if f is not None]
-    assert names.count("bottleneck.tail") == 6 and names.count("bottleneck.downsample") == 3
+    assert _tails(names) == 6 and names.count("bottleneck.downsample") == 3
     scale = float(np.abs(ref).max())
     e_f, e_s = float(np.abs(fused - ref).max() / scale), float(np.abs(sep - ref).max() / scale)
     print("projection in the tail: max-rel %.3g (separate launch %.3g)" % (e_f, e_s))
     assert e_f < 5e-3 and e_f < 2.0 * e_s + 1e-3
+
+
+@pytest.mark.parametrize("n,size,precision", [(4, 384, "fp16"), (3, 368, "fp16"), (1, 96, "bf16"), (2, 256, "fp16"),
+                                              (5, 160, "fp16")])
+def test_next_conv1_inside_the_tail_matches_its_own_launch(n, size, precision, monkeypatch):
+    """layer1: the following block's conv1 + bn1 + ReLU computed by the tail kernel from the on-chip output tile
+    (64 -> 64 twice, 64 -> 128 into layer2 block 0) vs the separate conv1 launches."""
+    m, sd = _model(precision, seed=17)
+    x = O.synth_input(n, size, size, seed=17)
+    with torch.no_grad():
+        ref = O.unipose_forward(x, sd).numpy()
+    outs, conv1s = {}, {}
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("UNIPOSE_B200_TAIL_CONV1", fuse)
+        m._plans.clear()
+        outs[fuse] = m(x.cuda()).cpu().numpy()
+        if fuse == "1":
+            assert np.array_equal(outs[fuse], m(x.cuda()).cpu().numpy())      # graph replay: same bits
+        names = [nm for nm, f, s in m.plan_for(x.cuda()).ops if f is not None]
+        assert names.count("bottleneck.tail+conv1") == (3 if fuse == "1" else 0), names
+        conv1s[fuse] = names.count("bottleneck.conv1")
+    assert conv1s["1"] == conv1s["0"] - 3, conv1s
+    scale = float(np.abs(ref).max())
+    e_f = float(np.abs(outs["1"] - ref).max() / scale)
+    e_s = float(np.abs(outs["0"] - ref).max() / scale)
+    print("next conv1 in the tail %dx%d^2 %s: max-rel %.3g (own launch %.3g)" % (n, size, precision, e_f, e_s))
+    bound = 5e-3 if precision == "fp16" else 3e-2
+    assert e_f < bound and e_f < 2.0 * e_s + 1e-3, (e_f, e_s)

@@ -62,7 +62,8 @@ def main():
     starts, nblk = [], 0
     bounds = {0: None, 3: None, 7: None, 30: None}
     for i, n in enumerate(names):
-        if n == "bottleneck.conv1" or n.startswith("bottleneck.chain"):
+        # a block whose conv1 ran inside the previous block's tail kernel starts at its next own launch
+        if n == "bottleneck.conv1" or n.startswith("bottleneck.chain") or (i > 0 and names[i - 1] == "bottleneck.tail+conv1"):
             if nblk in bounds and bounds[nblk] is None:
                 bounds[nblk] = i
             nblk += int(re.search(r"\[(\d+)\]", n).group(1)) if n.startswith("bottleneck.chain") else 1

@@ -62,7 +62,7 @@ class UpBneckChainDesc(ctypes.Structure):
 
 class UpBneckTailDesc(ctypes.Structure):
     _fields_ = [("n", c_int32), ("h", c_int32), ("w", c_int32), ("planes", c_int32), ("dil", c_int32), ("dtype", c_int32),
-                ("proj_cin", c_int32)]
+                ("proj_cin", c_int32), ("next_planes", c_int32)]
 
 
 class UpBneckChainWeights(ctypes.Structure):
@@ -126,7 +126,7 @@ _SIGNATURES = {
     "up_wasp_chain_supported": [POINTER(UpWaspChainDesc)],
     "up_bneck_chain_supported": [POINTER(UpBneckChainDesc)],
     "up_bneck_tail_supported": [POINTER(UpBneckTailDesc)],
-    "up_bneck_tail_fwd": [POINTER(UpBneckTailDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "up_bneck_tail_fwd": [POINTER(UpBneckTailDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "up_bneck_chain_fwd": [POINTER(UpBneckChainDesc), POINTER(UpBneckChainWeights), _P, _P, _P, _P, _L, _P],
     "up_debug_bneck_timing": [_P],
     "up_wasp_chain_fwd": [POINTER(UpWaspChainDesc), POINTER(UpWaspChainWeights), _P, _P, _P, _P, _L, _P],

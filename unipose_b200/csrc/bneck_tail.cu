@@ -18,6 +18,13 @@
 // tile [128 x Cx] and the Wd N-tile ride through the ring and Wd x is accumulated straight into acc3 (replaces the
 // identity MMAs); the epilogue adds both shifts.
 //
+// Next-conv1 mode (planes 64, `next_planes` = 64 / 128): the FOLLOWING bottleneck's conv1 (1x1, 4P -> N1, + BN + ReLU,
+// resnet.py:25-27) is a per-pixel GEMM over exactly the tile this kernel has just produced, so it runs here: every
+// 64-channel output group, while it sits in its staging buffer for the TMA store, is also the A operand of
+// D1[128 x N1] += O_g x W1n[:, g]  (TMEM columns [128, 128 + N1), filter chunks through the ring); after the fourth group
+// epilogue C turns D1 into the next block's t1 tile and stores it.  That block then starts at its 3x3: its conv1 launch
+// and the re-read of this block's output (151 MB per layer1 block at 384^2 x 32) disappear.
+//
 // Warp roles (384 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM alloc + store thread, 3 idle, 4..11 epilogue.
 #include <cuda.h>
 #include <stdlib.h>
@@ -57,6 +64,10 @@ struct BtParams {
   // activation box of bh + 2*dil rows per (kw, chunk); filter row r reads it r*dil*bw pixel rows further down (a
   // multiple of the 1024-byte swizzle atom) against its own filter tile - 3 slots of (tall box + 3 filter tiles)
   // instead of 9 of (16 KB + 1 filter tile): the nine halo taps no longer re-read the tile from L2
+  int n1;                  // next-conv1 mode: output channels of the following block's conv1 (0 = off, 64, 128)
+  int n1_cps;              //   its 64-channel K-chunks [n1 x 64] per ring slot (32 KB): 4 or 2
+  uint32_t idesc1;         //   M128 x N=n1
+  const float* shift1n;    //   [n1] shift of the following block's bn1
   int tall;
   uint32_t slot_bytes;     // ring slot stride
   uint32_t tall_a_bytes;   // (bh + 2*dil) * bw * 128
@@ -99,7 +110,8 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     bneck_tail_kernel(const __grid_constant__ CUtensorMap tmT1, const __grid_constant__ CUtensorMap tmR,
                       const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW2,
                       const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmWd,
-                      const __grid_constant__ CUtensorMap tmT1t, const BtParams p) {
+                      const __grid_constant__ CUtensorMap tmT1t, const __grid_constant__ CUtensorMap tmW1n,
+                      const __grid_constant__ CUtensorMap tmT1n, const BtParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -117,7 +129,8 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   auto s2readyT = [&](int g) { return b0 + 8u * (8 + g); };       // [2] epilogue -> MMA
   auto availO = [&](int g) { return b0 + 8u * (10 + g); };        // [4] store drained
   auto readyO = [&](int g) { return b0 + 8u * (14 + g); };        // [4] epilogue -> store thread
-  const uint32_t tmem_slot = b0 + 8u * 18;
+  const uint32_t full1_bar = b0 + 8u * 18, empty1_bar = b0 + 8u * 19;   // next-conv1 accumulator D1
+  const uint32_t tmem_slot = b0 + 8u * 20;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5;
@@ -127,6 +140,10 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmT1);
     tma_prefetch_desc(&tmT1t);
+    if (p.n1) {
+      tma_prefetch_desc(&tmW1n);
+      tma_prefetch_desc(&tmT1n);
+    }
     tma_prefetch_desc(&tmR);
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmW3);
@@ -145,9 +162,12 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     mbar_init(full3_bar, 1);
     mbar_init(empty3_bar, kBtEpiThreads / 32);
     for (int g = 0; g < 4; ++g) {
-      mbar_init(availO(g), 1);
+      // next-conv1 mode: a buffer is free again once the TMA store AND the D1 MMAs have read it (two arrivals)
+      mbar_init(availO(g), p.n1 ? 2 : 1);
       mbar_init(readyO(g), kBtEpiThreads / 32);
     }
+    mbar_init(full1_bar, 1);
+    mbar_init(empty1_bar, kBtEpiThreads / 32);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -174,10 +194,14 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   const uint32_t tmem_base = *tmem_slot_ptr;
   // TMEM columns: conv2 accumulators at [0, P) and [P, 2P); the 256-column output accumulator at [256, 512)
   const uint32_t tmem_acc3 = tmem_base + 256u;
+  const uint32_t tmem_d1 = tmem_base + 128u;     // next-conv1 accumulator (planes 64 only: conv2 uses [0, 128))
+  const int c1 = p.n1 >> 6;                      // 64-channel groups of the next block's t1 tile
+  const int gpt = 4 * p.ntiles + c1;             // staging-buffer groups per tile in the output stream
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  // Work order shared by producer and MMA issuer: conv2(tile 0); then for i >= 0: conv2(tile i+1) [if any], conv3(tile i)
+  // Work order shared by producer and MMA issuer: conv2(tile 0), conv2(tile 1); then for i >= 0: conv3(tile i),
+  // conv2(tile i+2) [if any], next-conv1(tile i) [n1 mode]
   if (warp == 0) {
     // ===================== TMA producer =====================
     uint32_t slot = 0, par = 1;
@@ -271,10 +295,26 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         }
       }
     };
+    auto conv1n_loads = [&]() {
+      // the following block's conv1 filter, 64-channel K-chunks [n1 rows x 64] side by side, 32 KB per slot
+      const uint32_t cbytes = static_cast<uint32_t>(p.n1) * 128u;
+      for (int g0 = 0; g0 < 4; g0 += p.n1_cps) {
+        mbar_wait(empty_bar(slot), par, 16000000000LL);
+        if (elect_one()) {
+          const uint32_t dst = smem_base + slot * p.slot_bytes;
+          mbar_arrive_expect_tx(full_bar(slot), kBtSlotBytes);
+          for (int j = 0; j < p.n1_cps; ++j) tma_load_2d(&tmW1n, dst + j * cbytes, full_bar(slot), (g0 + j) * 64, 0);
+        }
+        __syncwarp();
+        advance();
+      }
+    };
     if (first < p.total_tiles) conv2_loads(first);
+    if (first + step < p.total_tiles) conv2_loads(first + step);
     for (int tile = first; tile < p.total_tiles; tile += step) {
-      if (tile + step < p.total_tiles) conv2_loads(tile + step);
       conv3_loads(tile);
+      if (tile + 2 * step < p.total_tiles) conv2_loads(tile + 2 * step);
+      if (p.n1) conv1n_loads();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -391,17 +431,53 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       }
       ++nT;
     };
+    const uint64_t odesc0 = make_smem_desc_kmajor(stgO, 128);
+    uint32_t n1u = 0;               // uses of the next-conv1 accumulator
+    auto conv1n_mma = [&](int it) {
+      // D1 += O_g x W1n[:, g]: the A operand is the output group in its staging buffer (the store thread reads the
+      // same bytes); the buffer returns to the epilogue when both readers are done (availO counts 2)
+      const uint32_t nb = static_cast<uint32_t>(p.obufs);
+      const uint32_t q0 = static_cast<uint32_t>(it) * static_cast<uint32_t>(gpt);
+      const uint32_t cstep = (static_cast<uint32_t>(p.n1) * 128u) >> 4;
+      mbar_wait(empty1_bar, (n1u & 1u) ^ 1u);
+      ++n1u;
+      tcgen05_after_thread_sync();
+      for (int g = 0; g < 4; ++g) {
+        const int j = g % p.n1_cps;
+        if (j == 0) mbar_wait(full_bar(slot), phase);
+        const uint32_t q = q0 + static_cast<uint32_t>(g);
+        const uint32_t b = q % nb;
+        mbar_wait(readyO(b), (q / nb) & 1u);
+        tcgen05_after_thread_sync();
+        if (elect_one()) {
+          const uint64_t ad = odesc0 + static_cast<uint64_t>((kBtBuf >> 4) * b);
+          const uint64_t bd = adesc0 + static_cast<uint64_t>(slot_step * slot) + static_cast<uint64_t>(cstep * j);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_d1, ad + 2u * k, bd + 2u * k, p.idesc1, (g | k) ? 1u : 0u);
+          umma_commit(availO(b));
+          if (j == p.n1_cps - 1) umma_commit(empty_bar(slot));
+          if (g == 3) umma_commit(full1_bar);
+        }
+        __syncwarp();
+        if (j == p.n1_cps - 1) advance();
+      }
+    };
+    // conv2 runs two tiles ahead of the output epilogue; the D1 MMAs of tile i (which wait for the epilogue's output
+    // groups) come after conv2 of tile i+2, so the ring already holds conv3(i+1)'s operands while the issuer waits
     int it = 0;
     if (first < p.total_tiles) conv2_mma(first, 0);
+    if (first + step < p.total_tiles) conv2_mma(first + step, 1);
     for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
-      if (tile + step < p.total_tiles) conv2_mma(tile + step, it + 1);
       conv3_mma();
+      if (tile + 2 * step < p.total_tiles) conv2_mma(tile + 2 * step, it + 2);
+      if (p.n1) conv1n_mma(it);
     }
   } else if (threadIdx.x == 64) {
     // ===================== store thread =====================
     // the 64-channel output groups form one stream q = 0, 1, ...: group q lives in buffer q % obufs; a buffer goes back
     // to the epilogue as soon as the store that read it has finished reading (one younger store may still be pending)
     uint32_t q = 0;
+    bool prev_c = false;            // the previous group of the stream was a t1 group (next-conv1 mode)
     const uint32_t nb = static_cast<uint32_t>(p.obufs);
     for (int tile = first; tile < p.total_tiles; tile += step) {
       const BtTile t = bt_tile(p, tile);
@@ -414,8 +490,21 @@ __global__ void __launch_bounds__(kBtThreads, 1)
           if (q > 0) {
             tma_store_wait_read<1>();
             mbar_arrive(availO((q - 1) % nb));
+            if (prev_c) mbar_arrive(availO((q - 1) % nb));   // a t1 group has no MMA reader: second arrival
           }
+          prev_c = false;
         }
+      }
+      // next-conv1 mode: the groups of the following block's t1 tile ride in the same buffer stream
+      for (int g = 0; g < c1; ++g, ++q) {
+        const uint32_t b = q % nb;
+        mbar_wait(readyO(b), (q / nb) & 1u);
+        tma_store_5d(&tmT1n, stgO + b * kBtBuf, g * 64, t.w0, 0, t.h0, t.n0);
+        tma_store_commit();
+        tma_store_wait_read<1>();                              // q > 0 here
+        mbar_arrive(availO((q - 1) % nb));
+        if (prev_c) mbar_arrive(availO((q - 1) % nb));
+        prev_c = true;
       }
     }
     tma_store_wait_all<0>();
@@ -428,7 +517,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
     const uint32_t row7 = static_cast<uint32_t>(row) & 7u;
     const uint32_t tlane = static_cast<uint32_t>(quarter * 32) << 16;
-    uint32_t nT = 0, nO = 0, n3 = 0;
+    uint32_t nT = 0, qO = 0, n3 = 0, n1e = 0;   // qO: next group of the output stream (see the store thread)
     uint32_t n2[2] = {0u, 0u};
     // `groups` x 64 accumulator columns -> ReLU(acc + shift) -> 16-bit -> staging buffers
     auto epilogue = [&](uint32_t tmem_col0, int groups, const float* sh, const float* sh2, bool setO) {
@@ -463,7 +552,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         uint32_t w[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) w[e] = bt_pack2_relu<kFmt>(v[2 * e], v[2 * e + 1]);
-        const uint32_t q = nO * 4u + static_cast<uint32_t>(g);     // output group stream (see the store thread)
+        const uint32_t q = qO + static_cast<uint32_t>(g);
         const uint32_t b = setO ? q % nb : static_cast<uint32_t>(g);
         mbar_wait(setO ? availO(b) : availT(g), ((setO ? q / nb : nT) & 1u) ^ 1u);
         const uint32_t rowaddr = (setO ? stgO : stgT) + b * kBtBuf + rowoff;
@@ -478,12 +567,10 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(setO ? readyO(b) : s2readyT(g));
       }
-      if (setO) ++nO; else ++nT;
+      if (setO) qO += static_cast<uint32_t>(groups); else ++nT;
     };
-    int it = 0;
-    for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
+    auto epilogue_a = [&](int it) {      // t2 of the tile with sequence number `it`
       const int a = it & 1;
-      // ---- epilogue A: t2 ----
       mbar_wait(full2_bar(a), n2[a] & 1u);
       ++n2[a];
       tcgen05_after_thread_sync();
@@ -491,6 +578,10 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       tcgen05_before_thread_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(empty2_bar(a));
+    };
+    int it = 0;
+    if (first < p.total_tiles) epilogue_a(0);      // ---- epilogue A: t2, always one tile ahead of epilogue B ----
+    for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
       // ---- epilogue B: the block's output, 256 channels per N-tile ----
       for (int nt = 0; nt < p.ntiles; ++nt) {
         mbar_wait(full3_bar, n3 & 1u);
@@ -500,6 +591,18 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         tcgen05_before_thread_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(empty3_bar);
+      }
+      // t2 of the next tile (its conv2 finished long ago): the issuer can go on to that tile's conv3
+      if (tile + step < p.total_tiles) epilogue_a(it + 1);
+      if (p.n1) {
+        // ---- epilogue C: the following block's t1 tile = ReLU(D1 + shift1n) ----
+        mbar_wait(full1_bar, n1e & 1u);
+        ++n1e;
+        tcgen05_after_thread_sync();
+        epilogue(tmem_d1, c1, p.shift1n, nullptr, true);
+        tcgen05_before_thread_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty1_bar);
       }
     }
   }
@@ -524,6 +627,8 @@ static int bt_check(const UpBneckTailDesc* d) {
   if (d->n <= 0 || d->h <= 0 || d->w <= 0 || d->dil < 1) return fail(UP_ERR_INVALID, "up_bneck_tail: bad dims");
   if (d->proj_cin < 0 || d->proj_cin % 64 != 0 || d->proj_cin > 1024)
     return fail(UP_ERR_UNSUPPORTED, "up_bneck_tail: proj_cin must be 0 or a multiple of 64 <= 1024 (got %d)", d->proj_cin);
+  if (d->next_planes != 0 && (d->planes != 64 || (d->next_planes != 64 && d->next_planes != 128)))
+    return fail(UP_ERR_UNSUPPORTED, "up_bneck_tail: next_planes (%d) needs planes 64 and must be 64 or 128", d->next_planes);
   return 0;
 }
 
@@ -531,12 +636,16 @@ extern "C" int up_bneck_tail_supported(const UpBneckTailDesc* d) { return bt_che
 
 extern "C" int up_bneck_tail_fwd(const UpBneckTailDesc* d, const void* t1, const void* w2, const float* shift2,
                                  const void* w3, const float* shift3, const void* residual, const void* wd,
-                                 const float* shiftd, void* y, void* stream) {
+                                 const float* shiftd, void* y, const void* w1n, const float* shift1n, void* t1n,
+                                 void* stream) {
   UP_CHECK_ARG(d && t1 && w2 && shift2 && w3 && shift3 && residual && y, "up_bneck_tail_fwd: null argument");
   int rc = bt_check(d);
   if (rc) return rc;
   UP_CHECK_ARG((d->proj_cin > 0) == (wd != nullptr) && (wd != nullptr) == (shiftd != nullptr),
                "up_bneck_tail_fwd: wd / shiftd go with proj_cin > 0");
+  UP_CHECK_ARG((d->next_planes > 0) == (w1n != nullptr) && (w1n != nullptr) == (shift1n != nullptr) &&
+                   (w1n != nullptr) == (t1n != nullptr),
+               "up_bneck_tail_fwd: w1n / shift1n / t1n go with next_planes > 0");
   DeviceInfo* di = device_info();
   if (!di) return UP_ERR_CUDA;
   if (!di->tail_attr) {
@@ -567,7 +676,7 @@ extern "C" int up_bneck_tail_fwd(const UpBneckTailDesc* d, const void* t1, const
     return (e && e[0] == '4') ? 4 : 2;
   }();
   p.obufs = obufs;
-  const size_t fixed = 1024 + static_cast<size_t>(2 + obufs) * kBtBuf + 8192 + 8 * (2 * kBtMaxSlots + 18) + 16;
+  const size_t fixed = 1024 + static_cast<size_t>(2 + obufs) * kBtBuf + 8192 + 8 * (2 * kBtMaxSlots + 20) + 16;
   p.tall = 0;
   p.slot_bytes = kBtSlotBytes;
   p.tall_a_bytes = static_cast<uint32_t>(p.bh + 2 * d->dil) * p.bw * 128u;
@@ -596,7 +705,11 @@ extern "C" int up_bneck_tail_fwd(const UpBneckTailDesc* d, const void* t1, const
   p.shift3 = shift3;
   p.xchunks = d->proj_cin / 64;
   p.shiftd = shiftd;
-  CUtensorMap tmT1, tmR, tmY, tmW2, tmW3, tmWd, tmT1t;
+  p.n1 = d->next_planes;
+  p.n1_cps = p.n1 ? static_cast<int>(kBtSlotBytes / (static_cast<uint32_t>(p.n1) * 128u)) : 1;
+  p.idesc1 = make_idesc_f16(static_cast<uint32_t>(fmt), 128u, static_cast<uint32_t>(p.n1 ? p.n1 : 64));
+  p.shift1n = shift1n;
+  CUtensorMap tmT1, tmR, tmY, tmW2, tmW3, tmWd, tmT1t, tmW1n, tmT1n;
   const uint32_t abox[5] = {64u, static_cast<uint32_t>(p.bw), 1u, static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
   rc = encode_act_map(&tmT1, fmt, t1, d->n, d->h, d->w, d->planes, 1, abox, 128, "tail.t1");
   if (rc) return rc;
@@ -633,6 +746,17 @@ extern "C" int up_bneck_tail_fwd(const UpBneckTailDesc* d, const void* t1, const
     rc = encode_map(&tmWd, fmt, 2, wd, dims, st, box, 128, "tail.wd");
     if (rc) return rc;
   }
+  tmW1n = tmW3;
+  tmT1n = tmY;
+  if (p.n1) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(4) * d->planes, static_cast<uint64_t>(p.n1)};
+    const uint64_t st[1] = {static_cast<uint64_t>(4) * d->planes * 2};
+    const uint32_t box[2] = {64u, static_cast<uint32_t>(p.n1)};
+    rc = encode_map(&tmW1n, fmt, 2, w1n, dims, st, box, 128, "tail.w1n");
+    if (rc) return rc;
+    rc = encode_act_map(&tmT1n, fmt, t1n, d->n, d->h, d->w, p.n1, 1, abox, 128, "tail.t1n");
+    if (rc) return rc;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.total_tiles < di->sm_count ? p.total_tiles : di->sm_count);
   cfg.blockDim = dim3(kBtThreads);
@@ -643,8 +767,8 @@ extern "C" int up_bneck_tail_fwd(const UpBneckTailDesc* d, const void* t1, const
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  rc = check_cuda(fmt == 0 ? cudaLaunchKernelEx(&cfg, bneck_tail_kernel<0>, tmT1, tmR, tmY, tmW2, tmW3, tmWd, tmT1t, p)
-                           : cudaLaunchKernelEx(&cfg, bneck_tail_kernel<1>, tmT1, tmR, tmY, tmW2, tmW3, tmWd, tmT1t, p),
+  rc = check_cuda(fmt == 0 ? cudaLaunchKernelEx(&cfg, bneck_tail_kernel<0>, tmT1, tmR, tmY, tmW2, tmW3, tmWd, tmT1t, tmW1n, tmT1n, p)
+                           : cudaLaunchKernelEx(&cfg, bneck_tail_kernel<1>, tmT1, tmR, tmY, tmW2, tmW3, tmWd, tmT1t, tmW1n, tmT1n, p),
                   "bneck_tail_kernel launch");
   return rc;
 }

@@ -76,15 +76,20 @@ class Bottleneck(PlanModule):
         self.stride, self.dilation = stride, dilation
         self._out_channels = (planes * 4,)
 
-    def _emit(self, b, x):
+    def _emit(self, b, x, t1=None, nxt=None):
+        """t1: this block's conv1 output when the PREVIOUS block's tail kernel already produced it; nxt: the following
+        bottleneck - when this block ends in the tail kernel and qualifies, that kernel also runs nxt.conv1 and the
+        result is left in self._next_t1 for the caller to hand on."""
         n, h, w = x.n, x.h, x.w
         planes = self.conv1.out_channels
         s, d = self.stride, self.dilation
         ho, wo = (h - 1) // s + 1, (w - 1) // s + 1
-        t1 = b.act(n, h, w, planes)
-        b.conv(x, b.packed_conv(self.conv1, self.bn1), t1, "bottleneck.conv1", relu=True)
+        self._next_t1 = None
+        if t1 is None:
+            t1 = b.act(n, h, w, planes)
+            b.conv(x, b.packed_conv(self.conv1, self.bn1), t1, "bottleneck.conv1", relu=True)
         out = b.act(n, ho, wo, planes * 4)
-        if self.downsample is not None and s == 1 and self._emit_tail(b, t1, x, out, proj=self.downsample):
+        if self.downsample is not None and s == 1 and self._emit_tail(b, t1, x, out, proj=self.downsample, nxt=nxt):
             return out          # projection shortcut folded into the tail kernel: Wd x never goes to memory
         res = x
         pcp = self._packed_conv3_proj(b, x) if self.downsample is not None else None
@@ -97,7 +102,7 @@ class Bottleneck(PlanModule):
             res = b.act(n, ho, wo, planes * 4)
             b.conv(x, b.packed_conv(self.downsample[0], self.downsample[1]), res, "bottleneck.downsample",
                    stride=s, pad=0)
-        if self._emit_tail(b, t1, res, out):
+        if self._emit_tail(b, t1, res, out, nxt=nxt):
             return out
         t2 = b.act(n, ho, wo, planes)
         b.conv(t1, b.packed_conv(self.conv2, self.bn2), t2, "bottleneck.conv2", stride=s, dil=d, pad=d, relu=True)
@@ -135,11 +140,13 @@ class Bottleneck(PlanModule):
         b.plan.buffers.append((wbuf, scale_d, shift_d, fold_d))
         return ops.PackedConv(wbuf, pc3.scale, shift_sum, 1, 1, cout, planes, cout, planes, b.mode)
 
-    def _emit_tail(self, b, t1, res, out, proj=None):
+    def _emit_tail(self, b, t1, res, out, proj=None, nxt=None):
         """conv2 (3x3) + conv3 (1x1 expansion) + residual + ReLU as ONE launch (csrc/bneck_tail.cu) for the
         bandwidth-bound layers (planes 64 / 128, stride 1, fp16 / bf16): t2 never leaves shared memory.
         proj = the block's `downsample` (1x1 conv + BN, stride 1): `res` is the block INPUT and the projection is
-        computed inside the kernel (UNIPOSE_B200_BNECK_TAIL_PROJ=0: separate launch as before)."""
+        computed inside the kernel (UNIPOSE_B200_BNECK_TAIL_PROJ=0: separate launch as before).
+        nxt = the following bottleneck: at planes 64 its conv1 + bn1 + ReLU (1x1, stride 1, 64 or 128 outputs) runs in
+        the same kernel on the output tile while it is on chip (UNIPOSE_B200_TAIL_CONV1=0: its own launch)."""
         import ctypes
         from .... import _lib, ops
         planes = self.conv1.out_channels
@@ -155,17 +162,28 @@ class Bottleneck(PlanModule):
         d = _lib.UpBneckTailDesc()
         d.n, d.h, d.w, d.planes, d.dil, d.dtype = t1.n, t1.h, t1.w, planes, self.dilation, b.mode
         d.proj_cin = res.c if proj is not None else 0
+        c1n = nxt.conv1 if nxt is not None else None
+        if (c1n is not None and os.environ.get("UNIPOSE_B200_TAIL_CONV1", "1") != "0" and planes == 64 and
+                c1n.kernel_size == (1, 1) and c1n.stride == (1, 1) and c1n.in_channels == 4 * planes and
+                c1n.out_channels in (64, 128) and c1n.bias is None):
+            d.next_planes = c1n.out_channels
         if _lib.load().up_bneck_tail_supported(ctypes.byref(d)) != 0:
             return False
         pc2 = b.packed_conv(self.conv2, self.bn2)
         pc3 = b.packed_conv(self.conv3, self.bn3)
         pcd = b.packed_conv(proj[0], proj[1]) if proj is not None else None
+        pc1n = t1n = None
+        if d.next_planes:
+            pc1n = b.packed_conv(nxt.conv1, nxt.bn1)
+            t1n = b.act(t1.n, t1.h, t1.w, d.next_planes)
+            self._next_t1 = t1n
 
-        def launch(keep=(pc2, pc3, pcd)):
+        def launch(keep=(pc2, pc3, pcd, pc1n)):
             _lib.call("up_bneck_tail_fwd", ctypes.byref(d), t1.ptr(), ops._ptr(pc2.w), ops._ptr(pc2.shift), ops._ptr(pc3.w),
                       ops._ptr(pc3.shift), res.ptr(), ops._ptr(pcd.w) if pcd else None,
-                      ops._ptr(pcd.shift) if pcd else None, out.ptr(), ops._stream())
-        b.add(launch, "bottleneck.tail")
+                      ops._ptr(pcd.shift) if pcd else None, out.ptr(), ops._ptr(pc1n.w) if pc1n else None,
+                      ops._ptr(pc1n.shift) if pc1n else None, t1n.ptr() if t1n is not None else None, ops._stream())
+        b.add(launch, "bottleneck.tail+conv1" if pc1n else "bottleneck.tail")
         return True
 
 
@@ -253,17 +271,23 @@ class ResNet(PlanModule):
         x = b.act(n, h // 4, w // 4, 64)
         b.add(lambda stem=stem, x=x: ops.maxpool3x3s2(stem, x), "maxpool")
         low = None
-        for name in ('layer1', 'layer2', 'layer3', 'layer4'):
+        names = ('layer1', 'layer2', 'layer3', 'layer4')
+        t1 = None          # conv1 output of the block about to be emitted, when the previous tail kernel produced it
+        for li, name in enumerate(names):
             blocks = list(getattr(self, name))
             i = 0
             while i < len(blocks):
                 run = self._chain_run(blocks, i)
-                fused = self._emit_chain(b, x, blocks[i:i + run]) if run >= 2 else None
+                fused = self._emit_chain(b, x, blocks[i:i + run]) if (run >= 2 and t1 is None) else None
                 if fused is not None:
                     x = fused
                     i += run
                 else:
-                    x = blocks[i]._emit(b, x)
+                    nxt = blocks[i + 1] if i + 1 < len(blocks) else (
+                        getattr(self, names[li + 1])[0] if li + 1 < len(names) else None)
+                    blk = blocks[i]
+                    x = blk._emit(b, x, t1=t1, nxt=nxt)
+                    t1 = blk._next_t1
                     i += 1
             if name == 'layer1':
                 low = x
