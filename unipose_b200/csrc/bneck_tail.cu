@@ -68,6 +68,7 @@ struct BtParams {
   int n1_cps;              //   its 64-channel K-chunks [n1 x 64] per ring slot (32 KB): 4 or 2
   uint32_t idesc1;         //   M128 x N=n1
   const float* shift1n;    //   [n1] shift of the following block's bn1
+  int l2pf;                // bulk L2 prefetch of the NEXT tile's shortcut operand (UP_TAIL_L2PF)
   int tall;
   uint32_t slot_bytes;     // ring slot stride
   uint32_t tall_a_bytes;   // (bh + 2*dil) * bw * 128
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t stgT = smem_base + p.slots * p.slot_bytes;     // P/64 buffers: t2 tile
-  const uint32_t stgO = stgT + 2 * kBtBuf;                       // 4 buffers: one 256-channel N-tile of the output
+  const uint32_t stgO = stgT + p.pchunks * kBtBuf;               // obufs buffers: the stream of 64-channel output groups
   const uint32_t ident = stgO + p.obufs * kBtBuf;                // 64 x 64 identity (K-major, 128B swizzle), 8 KB
   const uint32_t bars = ident + 8192u;
   auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -309,9 +310,24 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         advance();
       }
     };
+    // The shortcut operand (residual tile / projection input) is the kernel's big DRAM stream and enters the ring only
+    // right before its MMAs: a bulk L2 prefetch one tile ahead turns its DRAM latency into L2 latency
+    auto prefetch_shortcut = [&](int tile) {
+      const BtTile t = bt_tile(p, tile);
+      if (elect_one()) {
+        const int nch = p.xchunks > 0 ? p.xchunks : 4 * p.ntiles;
+        for (int c = 0; c < nch; ++c)
+          asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tmR)),
+                       "r"(c * 64), "r"(t.w0), "r"(0), "r"(t.h0), "r"(t.n0)
+                       : "memory");
+      }
+      __syncwarp();
+    };
     if (first < p.total_tiles) conv2_loads(first);
     if (first + step < p.total_tiles) conv2_loads(first + step);
     for (int tile = first; tile < p.total_tiles; tile += step) {
+      if (p.l2pf && tile + step < p.total_tiles) prefetch_shortcut(tile + step);
       conv3_loads(tile);
       if (tile + 2 * step < p.total_tiles) conv2_loads(tile + 2 * step);
       if (p.n1) conv1n_loads();
@@ -671,12 +687,16 @@ extern "C" int up_bneck_tail_fwd(const UpBneckTailDesc* d, const void* t1, const
   p.pchunks = d->planes / 64;
   p.ntiles = (4 * d->planes) / 256;
   p.dil = d->dil;
-  static const int obufs = []() {
-    const char* e = getenv("UP_TAIL_OBUFS");      // tuning: 2 (default, 4 ring slots) or 4 (3 ring slots)
-    return (e && e[0] == '4') ? 4 : 2;
+  static const int obufs_env = []() {
+    const char* e = getenv("UP_TAIL_OBUFS");      // tuning: 2 .. 4 output staging buffers (0 = default)
+    return (e && e[0] >= '2' && e[0] <= '4') ? e[0] - '0' : 0;
   }();
+  // planes 64: the t2 set is one buffer, the 16 KB it leaves buy a third output buffer (ncu: the epilogue warps spent
+  // 21 % of their samples waiting for a free buffer with two, see profiles/ncu_r2_tail_conv1_*.txt); planes 128 keeps
+  // two buffers and a fourth ring slot
+  const int obufs = obufs_env ? obufs_env : (d->planes == 64 ? 3 : 2);
   p.obufs = obufs;
-  const size_t fixed = 1024 + static_cast<size_t>(2 + obufs) * kBtBuf + 8192 + 8 * (2 * kBtMaxSlots + 20) + 16;
+  const size_t fixed = 1024 + static_cast<size_t>(d->planes / 64 + obufs) * kBtBuf + 8192 + 8 * (2 * kBtMaxSlots + 20) + 16;
   p.tall = 0;
   p.slot_bytes = kBtSlotBytes;
   p.tall_a_bytes = static_cast<uint32_t>(p.bh + 2 * d->dil) * p.bw * 128u;
@@ -705,6 +725,11 @@ extern "C" int up_bneck_tail_fwd(const UpBneckTailDesc* d, const void* t1, const
   p.shift3 = shift3;
   p.xchunks = d->proj_cin / 64;
   p.shiftd = shiftd;
+  static const int l2pf = []() {
+    const char* e = getenv("UP_TAIL_L2PF");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  p.l2pf = l2pf;
   p.n1 = d->next_planes;
   p.n1_cps = p.n1 ? static_cast<int>(kBtSlotBytes / (static_cast<uint32_t>(p.n1) * 128u)) : 1;
   p.idesc1 = make_idesc_f16(static_cast<uint32_t>(fmt), 128u, static_cast<uint32_t>(p.n1 ? p.n1 : 64));
