@@ -119,3 +119,15 @@ def test_kernel_table_tool_reads_the_committed_ncu_capture():
                           os.path.join(root, "profiles", "wasp_block_ncu_metrics_r1.csv")],
                          capture_output=True, text=True, check=True).stdout
     assert "conv_tcgen05_kernel<1>" in out and "global_avgpool_kernel<0>" in out and "total" in out
+
+
+def test_stem_weight_regroupings_as_gathers_match_their_slice_copy_definitions():
+    """The stem's filter regroupings run as one gather through a cached index map; the map must reproduce the
+    slice-copy definitions exactly (including the structural zeros)."""
+    from unipose_b200.model.modules.backbone import resnet as R
+    w = torch.randn(64, 3, 7, 7)
+    assert torch.equal(R.stem_s2d_weight(w), R._stem_s2d_loops(w))
+    assert torch.equal(R.stem_superpixel_weight(w), R._stem_superpixel_loops(w))
+    w2 = torch.randn(8, 3, 7, 7)              # another co: its own index map
+    assert torch.equal(R.stem_superpixel_weight(w2), R._stem_superpixel_loops(w2))
+    assert R.stem_window_weight(w).shape == (64, 64, 4, 1)

@@ -31,7 +31,8 @@ for lid, d in per.items():
     a["n"] += 1
     a["ns"] += ns
     a["bytes"] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
-    a["tc_ns"] += ns * d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0.0) / 100.0
+    a["tc_ns"] += ns * d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+                             d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0)) / 100.0
 tot = sum(a["ns"] for a in agg.values())
 print("%-44s %6s %10s %7s %10s %9s" % ("kernel", "n", "time us", "share", "DRAM GB/s", "tensor %"))
 for name, a in sorted(agg.items(), key=lambda x: -x[1]["ns"]):

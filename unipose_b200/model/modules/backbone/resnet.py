@@ -17,9 +17,29 @@ from ....plan_module import PlanModule
 _IMAGENET_FILE = 'resnet101-5d3b4d8f.pth'   # what resnet.py:142 downloads
 
 
+def _gather_like(loops_fn, name, w):
+    """Apply a pure regrouping of filter elements (defined by slice copies in `loops_fn`) as ONE gather: the index map
+    (0 = structural zero) is derived once per (co, device) by pushing element numbers through the definition, so a call
+    costs three kernels instead of ~100 - it runs at every weight refresh, i.e. every step of a training plan."""
+    key = (name, w.shape[0], str(w.device))
+    idx = _GATHER_INDEX.get(key)
+    if idx is None:
+        numbered = torch.arange(1, w.numel() + 1, dtype=torch.float64).reshape(w.shape)
+        idx = loops_fn(numbered).long().to(w.device)
+        _GATHER_INDEX[key] = idx
+    return torch.cat([w.new_zeros(1), w.reshape(-1)])[idx]
+
+
+_GATHER_INDEX = {}
+
+
 def stem_s2d_weight(w):
     """[co,3,7,7] stride-2 stem filter -> [co,16,4,4] stride-1 filter over the 2x2 space-to-depth image
     (channel order (ph,pw,c), taps at offsets -2..1; up_pack_input_s2d produces the matching activations)."""
+    return _gather_like(_stem_s2d_loops, "s2d", w)
+
+
+def _stem_s2d_loops(w):
     w2 = w.new_zeros((w.shape[0], 16, 4, 4))
     for a in range(4):
         for ph in range(2):
@@ -41,14 +61,9 @@ def stem_window_weight(w):
     return w2.permute(0, 3, 1, 2).reshape(w.shape[0], 64, 4, 1).contiguous()   # cin index = kw' * 16 + ch
 
 
-def stem_superpixel_weight(w):
-    """[co,3,7,7] stride-2 stem filter -> [4*co, 64, 4, 2]: an ORDINARY 4x2 stride-1 convolution that produces four
-    horizontally adjacent output pixels (x = 4s .. 4s+3) at once from the space-to-depth image regrouped into
-    "super pixels" of 4 s2d pixels x 16 channels = 64 contiguous elements (128 aligned bytes).
-
-    Output channel j*co + o is output pixel 4s+j, channel o; input element p*16 + ch of tap (a, kw) is s2d pixel
-    4(s+kw) + p - 2 (the rows carry 2 zero pixels of left padding), i.e. horizontal s2d tap b = 4*kw + p - j."""
-    w2 = stem_s2d_weight(w)                                    # [co, 16, a, b]
+def _stem_superpixel_loops(w):
+    """Definition of the super-pixel regrouping (see stem_superpixel_weight) as explicit slice copies."""
+    w2 = _stem_s2d_loops(w)                                    # [co, 16, a, b]
     co = w.shape[0]
     out = w.new_zeros((4 * co, 64, 4, 2))
     for j in range(4):
@@ -58,6 +73,16 @@ def stem_superpixel_weight(w):
                 if 0 <= b < 4:
                     out[j * co:(j + 1) * co, pp * 16:(pp + 1) * 16, :, kw] = w2[:, :, :, b]
     return out
+
+
+def stem_superpixel_weight(w):
+    """[co,3,7,7] stride-2 stem filter -> [4*co, 64, 4, 2]: an ORDINARY 4x2 stride-1 convolution that produces four
+    horizontally adjacent output pixels (x = 4s .. 4s+3) at once from the space-to-depth image regrouped into
+    "super pixels" of 4 s2d pixels x 16 channels = 64 contiguous elements (128 aligned bytes).
+
+    Output channel j*co + o is output pixel 4s+j, channel o; input element p*16 + ch of tap (a, kw) is s2d pixel
+    4(s+kw) + p - 2 (the rows carry 2 zero pixels of left padding), i.e. horizontal s2d tap b = 4*kw + p - j."""
+    return _gather_like(_stem_superpixel_loops, "superpixel", w)
 
 
 class Bottleneck(PlanModule):
