@@ -36,6 +36,12 @@ CASES = [
     dict(name="groups_concat", n=2, h=24, w=24, cin=512, cout=256, k=1, prec="bf16", groups=2),
     dict(name="k11_video", n=1, h=46, w=46, cin=16, cout=128, k=11, prec="bf16", relu=True, bias=True),
     dict(name="big_layer3_3x3", n=32, h=24, w=24, cin=256, cout=256, k=3, prec="bf16", relu=True),
+    # N = 512 tiles (one 512-column accumulator, two UMMAs per k-step): layer4 conv1 shapes at batch 32
+    dict(name="wide_n512_k2048", n=32, h=24, w=24, cin=2048, cout=512, k=1, prec="fp16", relu=True),
+    dict(name="wide_n512_k1024_bf16", n=32, h=24, w=24, cin=1024, cout=512, k=1, prec="bf16", relu=True),
+    dict(name="wide_n1024_two_ntiles", n=16, h=24, w=24, cin=1024, cout=1024, k=1, prec="fp16"),
+    dict(name="wide_n512_3x3_d2_layer4", n=32, h=24, w=24, cin=512, cout=512, k=3, dil=2, prec="fp16", relu=True),
+    dict(name="wide_n512_3x3_d4_odd_map", n=32, h=23, w=23, cin=512, cout=512, k=3, dil=4, prec="bf16", relu=True),
 ]
 
 

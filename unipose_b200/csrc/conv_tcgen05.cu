@@ -74,6 +74,8 @@ struct ConvKParams {
   int cluster;     // CTAs per cluster (1, 2 or 4): they share one weight tile per k-block via TMA multicast
   int res_terms;   // residual tiles (128 px x 64 ch, 16 KB) per 64-channel group (0 = none, 1, or 2 in split mode)
   int res_per_slot;  // how many of them share one ring slot (the slot is a_bytes + b_bytes wide)
+  int wide;          // N = 512 tile (CTA pairs only): ONE accumulator of 512 TMEM columns, two N = 256 UMMAs per k-step
+                     // over the same activation slot - the activation tile is fetched once per 512 output channels
   int proj_taps;     // UP_FLAG_PROJ: extra K - a second input (tensor map A1) projected by proj_taps more "taps" of the
   int proj_coff;     //   packed filter (cin columns each); proj_coff = first channel of that input's view
   int bsplit;        // experiment (UP_DEBUG_BSPLIT): fetch the weight tile with this many TMA instructions
@@ -259,6 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int total_tiles = (p.tiles_n / p.cluster) * p.tiles_h * p.tiles_w * p.n_tiles;
   const bool nchw = (p.flags & UP_FLAG_OUT_NCHW_F32) != 0;
   const bool has_res = (p.flags & UP_FLAG_RESIDUAL) != 0;
+  const int nacc = p.wide ? 1 : 2;      // accumulator buffers in TMEM (the 512-column tile has no second one)
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA0);
@@ -368,6 +371,12 @@ __global__ void __launch_bounds__(kThreads, 1)
                     for (int r = 0; r < 3; ++r)
                       tma_load_2d_2cta(&tmB, dst + p.a_bytes + r * p.tall_b_bytes, full_bar(s), chunk * p.ck,
                                        brow + r * p.taps_w * p.cout + static_cast<int>(crank) * (p.block_n >> 1));
+                  } else if (p.wide) {
+                    // each N = 256 UMMA takes 128 filter rows from either CTA: this CTA holds rows
+                    // [j*256 + rank*128, +128) of the 512-row tile, j = 0, 1
+                    for (int j = 0; j < 2; ++j)
+                      tma_load_2d_2cta(&tmB, dst + p.a_bytes + j * (p.b_bytes >> 1), full_bar(s), chunk * p.ck,
+                                       brow + j * 256 + static_cast<int>(crank) * 128);
                   } else {
                     tma_load_2d_2cta(&tmB, dst + p.a_bytes, full_bar(s), chunk * p.ck,
                                      brow + static_cast<int>(crank) * (p.block_n >> 1));
@@ -529,8 +538,14 @@ __global__ void __launch_bounds__(kThreads, 1)
             const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage_step * s);
             for (int k = 0; k < kk; ++k) {
               // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in 16-byte units
-              if constexpr (kPair) umma_f16_2cta(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, (kb | k) ? 1u : 0u);
-              else umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, (kb | k) ? 1u : 0u);
+              if constexpr (kPair) {
+                umma_f16_2cta(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, (kb | k) ? 1u : 0u);
+                if (p.wide)   // second half of the 512 output channels: same activation slot, next 128 filter rows
+                  umma_f16_2cta(tmem_d + 256u, adesc + 2u * k, bdesc + static_cast<uint64_t>(p.b_bytes >> 5) + 2u * k,
+                                p.idesc, (kb | k) ? 1u : 0u);
+              } else {
+                umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, p.idesc, (kb | k) ? 1u : 0u);
+              }
             }
           }
           // frees the smem slot once these MMAs have read it - in every CTA of the cluster (peers multicast into it)
@@ -550,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           phase ^= 1u;
         }
       }
-      if (++acc == 2) {
+      if (++acc == nacc) {
         acc = 0;
         acc_phase ^= 1u;
       }
@@ -665,7 +680,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (kPair && crank != 0) mbar_arrive_remote(tempty_bar(acc), 0u);
         else mbar_arrive(tempty_bar(acc));
       }
-      if (++acc == 2) {
+      if (++acc == nacc) {
         acc = 0;
         acc_phase ^= 1u;
       }
@@ -864,6 +879,30 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
     if (p.cluster == 1 && !has_proj && (v == 2 || v == 4) && block_n % (8 * v) == 0) p.bsplit = v;
   }
   if (p.pair) p.b_bytes = static_cast<uint32_t>(block_n / 2) * ck * 2;   // each CTA of the pair holds half of the weight tile
+  // N = 512 tiles (CTA pairs, cout % 512 == 0): the activation tile - the unique bytes that bound these kernels at
+  // ~57 KB/us per SM - is fetched once per 512 output channels instead of once per 256.  The single 512-column
+  // accumulator cannot overlap a tile's epilogue with the next tile's MMAs, so only when the whole launch is ONE round
+  // of work items and the k-loop is long enough to carry it.  UP_WIDE_N: 0 off, 1 = 1x1 filters only, 2 = all (default).
+  // Measured at batch 32 (profiles/segments_r2_wide.txt): layer4 conv1 2048 -> 512 45.1 -> 41.0 us, conv2 3x3 512 -> 512
+  // 75.8 -> 65.5 us.
+  p.wide = 0;
+  {
+    static const int want = []() {
+      const char* e = getenv("UP_WIDE_N");
+      return e ? atoi(e) : 2;
+    }();
+    const long long items = static_cast<long long>(m_tiles / 2) * (d->cout / 512 > 0 ? d->cout / 512 : 1);
+    const int kblocks = d->kh * d->kw * (d->cin / ck);
+    if (want > 0 && p.pair && block_n == 256 && d->cout % 512 == 0 && !split && !has_res && !has_proj && groups == 1 &&
+        ck == 64 && p.bsplit == 1 && (want >= 2 || (d->kh == 1 && d->kw == 1)) && kblocks >= 16 &&
+        items <= g_sm_count / 2) {
+      p.wide = 1;
+      block_n = 512;
+      p.block_n = 512;
+      p.n_tiles = d->cout / 512;
+      p.b_bytes = 256u * ck * 2;     // this CTA's two 128-row halves
+    }
+  }
   // Filter-row reuse ("tall" activation box): 3x3, stride 1, same padding, single-image tiles with bw a multiple of 8
   // (row offsets stay aligned to the 1024-byte swizzle atom), and a slot (tall box + three weight tiles) small
   // enough for >= 3 pipeline stages.  Cuts the activation bytes of the k-loop by 3*bh / (bh + 2*dil).
@@ -871,7 +910,7 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   p.tall_a_step = 0;
   p.tall_b_bytes = 0;
   {
-    const bool shape_ok = d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad_h == d->dil && ck == 64 && p.bn == 1 &&
+    const bool shape_ok = !p.wide && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad_h == d->dil && ck == 64 && p.bn == 1 &&
                           p.bw % 8 == 0 && p.cluster * p.bsplit == (p.pair ? 2 : 1) && d->x_cextent == 0 && !has_res;
     const uint32_t tall_a = static_cast<uint32_t>(p.bh + 2 * d->dil) * p.bw * 128u;
     const uint32_t slot = tall_a + 3u * p.b_bytes;
@@ -887,7 +926,7 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
       p.b_bytes = 3u * p.b_bytes;
     }
   }
-  p.idesc = make_idesc_f16(static_cast<uint32_t>(fmt), p.pair ? 256u : kTileM, static_cast<uint32_t>(block_n));
+  p.idesc = make_idesc_f16(static_cast<uint32_t>(fmt), p.pair ? 256u : kTileM, static_cast<uint32_t>(p.wide ? 256 : block_n));
   p.idesc_res = make_idesc_f16(static_cast<uint32_t>(fmt), p.pair ? 256u : kTileM, 64u);
   if (has_res) UP_CHECK_ARG(ck == 64, "up_conv2d_fwd: residual needs cin to be a multiple of 64");
   if (const char* e = getenv("UP_DEBUG_NBUF")) {
@@ -920,7 +959,7 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
   }
   // NOTE: filled again below once the cluster / pair decision is known
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(2 * block_n)) cols *= 2;
+  while (cols < static_cast<uint32_t>(p.wide ? block_n : 2 * block_n)) cols *= 2;
   p.tmem_cols = cols;
   p.flags = d->flags;
   p.fmt = fmt;
@@ -967,7 +1006,7 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
     const int taps = d->kh * d->kw + p.proj_taps;   // the projection's filter rows follow the main taps
     const uint64_t dims[2] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(split ? 2 : 1) * taps * d->cout};
     const uint64_t st[1] = {static_cast<uint64_t>(d->cin) * 2};
-    const uint32_t box[2] = {static_cast<uint32_t>(ck), static_cast<uint32_t>(block_n / p.cluster / p.bsplit)};
+    const uint32_t box[2] = {static_cast<uint32_t>(ck), static_cast<uint32_t>(p.wide ? 128 : block_n / p.cluster / p.bsplit)};
     if (split) {
       UP_CHECK_ARG(d->w_plane_stride == static_cast<int64_t>(taps) * d->cout * d->cin,
                    "up_conv2d_fwd: split weights must have contiguous planes (w_plane_stride = taps*cout*cin)");
