@@ -476,6 +476,19 @@ def run_b200(args) -> int:
     barrier()
     e2e_u8_ms = e0.elapsed_time(e1)
 
+    # the host->device copy of one fp32 batch alone (same pinned buffer, same copy stream): when it takes as long as a
+    # step, `e2e` is bound by the host link, not by the kernels (`e2e_uint8` moves a quarter of the bytes)
+    barrier()
+    h0 = torch.cuda.Event(enable_timing=True)
+    h1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(copy_stream):
+        h0.record(copy_stream)
+        for i in range(8):
+            x_bufs[i % 2].copy_(x_host, non_blocking=True)
+        h1.record(copy_stream)
+    barrier()
+    h2d_ms = h0.elapsed_time(h1) / 8.0
+
     t = torch.tensor([dev_ms, e2e_ms, e2e_u8_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -550,7 +563,10 @@ def run_b200(args) -> int:
             "cuda_graph": True, "e2e_call": "model(input) - unipose.forward of the nn.Module mirror"},
         "clocks": clocks,
         "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
-                "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms / args.steps},
+                "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms / args.steps,
+                "h2d_alone_ms": h2d_ms, "h2d_gbs": x_host.numel() * 4 / (h2d_ms * 1e-3) / 1e9,
+                "bound": "host link (the fp32 batch takes as long to arrive as a step takes to compute)"
+                if h2d_ms > 0.9 * dev_ms / args.steps else "kernels"},
         "e2e_uint8": {"value": frames / (e2e_u8_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": u8_host.numel(),
                       "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_u8_ms / args.steps,
                       "call": "model.forward_uint8(images_u8_nhwc) - normalisation fused into the stem's input packing",

@@ -895,7 +895,8 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
     const int kblocks = d->kh * d->kw * (d->cin / ck);
     if (want > 0 && p.pair && block_n == 256 && d->cout % 512 == 0 && !split && !has_res && !has_proj && groups == 1 &&
         ck == 64 && p.bsplit == 1 && (want >= 2 || (d->kh == 1 && d->kw == 1)) && kblocks >= 16 &&
-        items <= g_sm_count / 2) {
+        items <= g_sm_count / 2 && 2 * items > g_sm_count / 2) {   // one round instead of two; small launches keep the
+                                                                    // N = 256 tiles that spread over twice the SMs
       p.wide = 1;
       block_n = 512;
       p.block_n = 512;
