@@ -42,6 +42,7 @@ CASES = [
     dict(name="wide_n1024_two_ntiles", n=16, h=24, w=24, cin=1024, cout=1024, k=1, prec="fp16"),
     dict(name="wide_n512_3x3_d2_layer4", n=32, h=24, w=24, cin=512, cout=512, k=3, dil=2, prec="fp16", relu=True),
     dict(name="wide_n512_3x3_d4_odd_map", n=32, h=23, w=23, cin=512, cout=512, k=3, dil=4, prec="bf16", relu=True),
+    dict(name="layer4_conv3_res_bs32", n=32, h=24, w=24, cin=512, cout=2048, k=1, prec="fp16", residual=True, relu=True),
 ]
 
 

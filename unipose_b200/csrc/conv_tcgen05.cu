@@ -893,10 +893,14 @@ extern "C" int up_conv2d_fwd(const UpConvDesc* d, const void* x, const void* w_p
     }();
     const long long items = static_cast<long long>(m_tiles / 2) * (d->cout / 512 > 0 ? d->cout / 512 : 1);
     const int kblocks = d->kh * d->kw * (d->cin / ck);
-    if (want > 0 && p.pair && block_n == 256 && d->cout % 512 == 0 && !split && !has_res && !has_proj && groups == 1 &&
-        ck == 64 && p.bsplit == 1 && (want >= 2 || (d->kh == 1 && d->kw == 1)) && kblocks >= 16 &&
-        items <= g_sm_count / 2 && 2 * items > g_sm_count / 2) {   // one round instead of two; small launches keep the
-                                                                    // N = 256 tiles that spread over twice the SMs
+    // want == 3 (experiment): also the short-K 1x1 expansions with a residual that need several rounds anyway
+    // (layer4 conv3 512 -> 2048: a quarter fewer bytes through the ring per output channel, no epilogue overlap)
+    const bool single_round = items <= g_sm_count / 2 && 2 * items > g_sm_count / 2 && !has_res && kblocks >= 16;
+    const bool multi_round = want >= 3 && has_res && d->kh == 1 && d->kw == 1 && items > g_sm_count / 2 && kblocks >= 8;
+    if (want > 0 && p.pair && block_n == 256 && d->cout % 512 == 0 && !split && !has_proj && groups == 1 &&
+        ck == 64 && p.bsplit == 1 && (want >= 2 || (d->kh == 1 && d->kw == 1)) &&
+        (single_round || multi_round)) {   // one round instead of two; small launches keep the
+                                           // N = 256 tiles that spread over twice the SMs
       p.wide = 1;
       block_n = 512;
       p.block_n = 512;
