@@ -1,0 +1,99 @@
+"""Host logic of the inference plans, without a GPU: a plan can be EMITTED on CPU tensors (buffers, launch list, weight
+tables; nothing is launched), so the fusion decisions of the backbone are checked here - which launches a
+configuration produces, and that the switches documented in INTEGRATION.md select the layer-wise forms."""
+import warnings
+
+import pytest
+import torch
+
+from unipose_b200 import _lib, engine
+from unipose_b200.model.unipose import unipose
+
+
+def _names(monkeypatch, precision="fp16", shape=(2, 3, 128, 128), env=(), **kw):
+    for k, v in env:
+        monkeypatch.setenv(k, v)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = unipose(dataset="MPII", num_classes=16, precision=precision, **kw).eval()
+    plan = m._build_plan(shape, torch.device("cpu"))
+    return [n for n, f, s in plan.ops if f is not None], plan, m
+
+
+def _needs_lib():
+    try:
+        _lib.load()
+    except Exception as e:      # pragma: no cover - the driver builds the library before the CPU suite
+        pytest.skip("libunipose_b200.so not built: %s" % e)
+
+
+def test_default_fp16_plan_fuses_tails_projections_and_next_conv1(monkeypatch):
+    _needs_lib()
+    names, plan, m = _names(monkeypatch)
+    # layer1: conv1 of block 0, then three tail kernels that also produce the next block's conv1 (layer1.1, layer1.2,
+    # layer2.0); layer2 blocks 1..3: conv1 + tail; the first block of layers 2-4: conv2 + (conv3 + projection)
+    assert names[:3] == ["pack_input_s2d", "stem", "maxpool"]
+    assert names[3:9] == ["bottleneck.conv1", "bottleneck.tail+conv1", "bottleneck.tail+conv1", "bottleneck.tail+conv1",
+                          "bottleneck.conv2", "bottleneck.conv3+proj"]
+    assert names.count("bottleneck.tail") == 3 and names.count("bottleneck.conv3+proj") == 3
+    assert names.count("bottleneck.downsample") == 0
+    # 33 bottlenecks, three of which get their conv1 from the previous tail kernel
+    assert names.count("bottleneck.conv1") == 30
+    assert names[-6:] == ["decoder.low_conv", "decoder.maxpool", "decoder.upsample", "decoder.conv_a", "decoder.conv_b",
+                          "decoder.head"]
+
+
+@pytest.mark.parametrize("env,tails,tail_c1,proj,down", [
+    ((("UNIPOSE_B200_TAIL_CONV1", "0"),), 6, 0, 3, 0),
+    ((("UNIPOSE_B200_PROJ_FUSE", "0"),), 3, 3, 0, 3),                       # layer1.0's projection stays in its tail
+    ((("UNIPOSE_B200_PROJ_FUSE", "0"), ("UNIPOSE_B200_BNECK_TAIL_PROJ", "0")), 3, 3, 0, 4),
+    ((("UNIPOSE_B200_BNECK_TAIL", "0"),), 0, 0, 4, 0),                      # layer1.0 then takes the conv3 + projection GEMM
+    ((("UNIPOSE_B200_BNECK_TAIL", "0"), ("UNIPOSE_B200_PROJ_FUSE", "0")), 0, 0, 0, 4),
+])
+def test_switches_select_the_layerwise_forms(monkeypatch, env, tails, tail_c1, proj, down):
+    _needs_lib()
+    names, _, _ = _names(monkeypatch, env=env)
+    assert names.count("bottleneck.tail") == tails, names
+    assert names.count("bottleneck.tail+conv1") == tail_c1, names
+    assert names.count("bottleneck.conv3+proj") == proj, names
+    assert names.count("bottleneck.downsample") == down, names
+    blocks_with_own_conv1 = 33 - tail_c1
+    assert names.count("bottleneck.conv1") == blocks_with_own_conv1
+
+
+def test_parity_mode_plan_is_layerwise(monkeypatch):
+    """fp32-grade (bf16 x 3 split) mode: no fused kernels - every bottleneck is conv1, conv2, conv3 (+ downsample)."""
+    _needs_lib()
+    names, _, _ = _names(monkeypatch, precision="fp32")
+    assert not any(n.startswith("bottleneck.tail") or n.endswith("+proj") or n.startswith("bottleneck.chain") for n in names)
+    assert names.count("bottleneck.conv1") == names.count("bottleneck.conv2") == names.count("bottleneck.conv3") == 33
+    assert names.count("bottleneck.downsample") == 4
+
+
+def test_output_stride8_still_fuses_three_projections(monkeypatch):
+    _needs_lib()
+    names, _, _ = _names(monkeypatch, output_stride=8)
+    assert names.count("bottleneck.conv3+proj") == 3 and names.count("bottleneck.downsample") == 0
+
+
+def test_fused_projection_filter_is_packed_into_disjoint_slices(monkeypatch):
+    """conv3 + projection: ONE filter buffer [1 + inplanes / planes][cout][planes]; conv3 fills slice 0, the downsample
+    filter the others (one pack job per input-channel slice), and the epilogue shift is the sum of both BatchNorm shifts
+    (a torch-side pack job keyed on the BatchNorm tensors)."""
+    _needs_lib()
+    names, plan, m = _names(monkeypatch)
+    blk = m.backbone.layer2[0]
+    wd = blk.downsample[0].weight
+    jobs = [e for e in plan.weights.entries if e["src"]() is wd]
+    planes, cout = blk.conv1.out_channels, 4 * blk.conv1.out_channels
+    assert len(jobs) == wd.shape[1] // planes == 2
+    assert [e["ci_off"] for e in jobs] == [0, planes] and all(e["cin_slice"] == planes for e in jobs)
+    assert all((e["rows"], e["cols"]) == (cout, planes) for e in jobs)
+    base = jobs[0]["out"].data_ptr() - cout * planes * jobs[0]["out"].element_size()      # slice 0 = conv3's filter
+    c3 = [e for e in plan.weights.entries if e["src"]() is blk.conv3.weight]
+    assert len(c3) == 1 and c3[0]["out"].data_ptr() == base
+    ptrs = sorted(e["out"].data_ptr() for e in c3 + jobs)
+    assert [p - base for p in ptrs] == [i * cout * planes * 2 for i in range(3)]
+    assert len(plan.pack_jobs) == 3             # one shift-sum job per fused projection
+    watched = set(id(t) for j in plan.pack_jobs for t in j.sources)
+    assert id(blk.bn3.bias) in watched and id(blk.downsample[1].running_var) in watched
