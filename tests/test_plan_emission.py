@@ -97,3 +97,29 @@ def test_fused_projection_filter_is_packed_into_disjoint_slices(monkeypatch):
     assert len(plan.pack_jobs) == 3             # one shift-sum job per fused projection
     watched = set(id(t) for j in plan.pack_jobs for t in j.sources)
     assert id(blk.bn3.bias) in watched and id(blk.downsample[1].running_var) in watched
+
+
+@pytest.mark.parametrize("freeze", [False, True])
+def test_train_plan_has_a_gradient_slot_for_every_live_parameter(freeze):
+    """The training plan (forward list + reverse tape) also emits on CPU tensors.  Every parameter the reference's
+    backward reaches gets a slot in the flat gradient; the only parameters without one are the reference's own dead
+    ones (`Decoder.conv2` / `bn2`, defined at model/modules/decoder.py:20-21 but commented out of forward(), :43-45 -
+    autograd leaves their .grad None and Adam skips them).  Frozen BatchNorm layers keep their affine gradients
+    (eval-mode BatchNorm still trains gamma / beta) but drop out of the statistics update list."""
+    _needs_lib()
+    from unipose_b200 import train
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = unipose(dataset="MPII", num_classes=16, precision="bf16", freeze_bn=freeze).train()
+        if freeze:
+            m.freeze_bn()
+    tp = train.build_image_train_plan(m, (2, 3, 96, 96), torch.device("cpu"), "bf16", flat=True)
+    have = set(id(p) for p in tp.params)
+    missing = sorted(n for n, p in m.named_parameters() if p.requires_grad and id(p) not in have)
+    assert missing == ["decoder.bn2.bias", "decoder.bn2.weight", "decoder.conv2.weight"]
+    live = sum(p.numel() for n, p in m.named_parameters() if p.requires_grad and not n.startswith(("decoder.conv2", "decoder.bn2")))
+    assert tp.flat_g.numel() == live == 47_022_513           # 188 MB of fp32 gradient per step (DESIGN.md section 6)
+    assert len(set(id(p) for p in tp.params)) == len(tp.params)
+    n_bn = sum(1 for mod in m.modules() if isinstance(mod, torch.nn.BatchNorm2d)) - 1        # decoder.bn2 never runs
+    assert len(tp.bn_modules) == (0 if freeze else n_bn)
+    assert len(tp.fwd) > 300 and len(tp.bwd) > len(tp.fwd)
