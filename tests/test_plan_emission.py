@@ -123,3 +123,23 @@ def test_train_plan_has_a_gradient_slot_for_every_live_parameter(freeze):
     n_bn = sum(1 for mod in m.modules() if isinstance(mod, torch.nn.BatchNorm2d)) - 1        # decoder.bn2 never runs
     assert len(tp.bn_modules) == (0 if freeze else n_bn)
     assert len(tp.fwd) > 300 and len(tp.bwd) > len(tp.fwd)
+
+
+def test_video_plans_share_the_trunk_emission_and_split_at_the_recurrence(monkeypatch):
+    """UniPose-LSTM: the per-frame plan = trunk (same fused backbone as the image model, waspVideo, decoder writing
+    the first K+1 channels of the 15-channel ConvLSTM input) + centre-map pooling + cell + middle CNN; temporal
+    batching splits it into a trunk plan over all T*B frames and a per-frame step plan (uniposeLSTM.py:106-147)."""
+    _needs_lib()
+    from unipose_b200.model import uniposeLSTM
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = uniposeLSTM.unipose(num_classes=13, precision="fp16").eval()
+    dev = torch.device("cpu")
+    frame = [n for n, f, s in m._build_plan(2, 128, 128, True, dev).ops if f is not None]
+    trunk = [n for n, f, s in m._build_trunk_plan(6, 128, 128, dev).ops if f is not None]
+    step0 = [n for n, f, s in m._build_step_plan(2, 16, 16, True, dev).ops if f is not None]
+    step = [n for n, f, s in m._build_step_plan(2, 16, 16, False, dev).ops if f is not None]
+    assert trunk[-1] == "pool_center" and trunk.count("bottleneck.tail+conv1") == 3 and trunk.count("bottleneck.conv3+proj") == 3
+    assert step0 == ["lstm_0", "hide_to_nhwc", "middle.conv1", "middle.conv2", "middle.conv3", "middle.conv4", "middle.conv5"]
+    assert step == ["lstm"] + step0[1:]
+    assert frame == trunk + step0                      # same launches, one plan instead of two
