@@ -79,7 +79,7 @@ def test_output_stride8_still_fuses_three_projections(monkeypatch):
 def test_fused_projection_filter_is_packed_into_disjoint_slices(monkeypatch):
     """conv3 + projection: ONE filter buffer [1 + inplanes / planes][cout][planes]; conv3 fills slice 0, the downsample
     filter the others (one pack job per input-channel slice), and the epilogue shift is the sum of both BatchNorm shifts
-    (a torch-side pack job keyed on the BatchNorm tensors)."""
+    (a torch-side pack job that re-runs with every refresh of the weight table)."""
     _needs_lib()
     names, plan, m = _names(monkeypatch)
     blk = m.backbone.layer2[0]
@@ -94,8 +94,8 @@ def test_fused_projection_filter_is_packed_into_disjoint_slices(monkeypatch):
     assert len(c3) == 1 and c3[0]["out"].data_ptr() == base
     ptrs = sorted(e["out"].data_ptr() for e in c3 + jobs)
     assert [p - base for p in ptrs] == [i * cout * planes * 2 for i in range(3)]
-    assert len(plan.pack_jobs) == 3             # one shift-sum job per fused projection
-    watched = set(id(t) for j in plan.pack_jobs for t in j.sources)
+    assert len(plan.pack_jobs) == 3 and all(j.with_table for j in plan.pack_jobs)    # one shift-sum job per fused projection,
+    watched = set(id(t) for t in plan.weights._watched())                            # re-run with every table refresh
     assert id(blk.bn3.bias) in watched and id(blk.downsample[1].running_var) in watched
 
 
@@ -143,3 +143,29 @@ def test_video_plans_share_the_trunk_emission_and_split_at_the_recurrence(monkey
     assert step0 == ["lstm_0", "hide_to_nhwc", "middle.conv1", "middle.conv2", "middle.conv3", "middle.conv4", "middle.conv5"]
     assert step == ["lstm"] + step0[1:]
     assert frame == trunk + step0                      # same launches, one plan instead of two
+
+
+def test_pack_job_refresh_rules():
+    """_PackJob: own sources are compared by (storage, version); with_table jobs also re-run whenever the weight table
+    has refreshed, and run once on the first call either way."""
+    runs = []
+    src = torch.zeros(4)
+    j = engine._PackJob([src], lambda: runs.append("a"))
+    assert j.refresh() and not j.refresh() and not j.refresh(table_changed=True)
+    src.add_(1)                                    # in-place update bumps the version counter
+    assert j.refresh() and runs == ["a", "a"]
+    engine.note_raw_parameter_update()             # raw-pointer kernels (Adam, BN statistics) bump the global epoch
+    assert j.refresh() and not j.refresh()
+    t = engine._PackJob((), lambda: runs.append("t"), with_table=True)
+    assert t.refresh(False) and not t.refresh(False) and t.refresh(True) and t.refresh(True) and not t.refresh(False)
+    assert runs.count("t") == 3
+
+
+def test_param_lookup_follows_replaced_parameters():
+    conv = torch.nn.Conv2d(4, 4, 1, bias=False)
+    bn = torch.nn.BatchNorm2d(4)
+    assert engine._param(conv, "weight") is conv.weight and engine._param(bn, "running_var") is bn.running_var
+    conv.weight = torch.nn.Parameter(torch.ones(4, 4, 1, 1))         # e.g. load_state_dict(assign=True)
+    assert engine._param(conv, "weight") is conv.weight
+    bn.running_mean = torch.ones(4)
+    assert engine._param(bn, "running_mean") is bn.running_mean

@@ -42,20 +42,33 @@ def _versions(tensors: Sequence[torch.Tensor]) -> Tuple[int, ...]:
 
 
 class _PackJob:
-    """Keeps one derived buffer in sync with its source tensors (torch-side jobs: e.g. stacked ConvLSTM gates)."""
+    """Keeps one derived buffer in sync with its source tensors (torch-side jobs: e.g. stacked ConvLSTM gates).
+    with_table=True: the job derives from buffers the plan's WeightTable fills (e.g. the sum of two epilogue shifts) - it
+    re-runs whenever the table has refreshed, which also covers parameters that were REPLACED (the table looks its
+    tensors up through the modules at every call; `sources` are then only what the table does not watch)."""
 
-    def __init__(self, sources: Sequence[torch.Tensor], fn: Callable[[], None]):
+    def __init__(self, sources: Sequence[torch.Tensor], fn: Callable[[], None], with_table: bool = False):
         self.sources = list(sources)
         self.fn = fn
+        self.with_table = with_table
         self.seen = None
 
-    def refresh(self) -> bool:
-        v = _versions(self.sources)
-        if v != self.seen:
+    def refresh(self, table_changed: bool = False) -> bool:
+        v = _versions(self.sources) if self.sources else ()
+        if v != self.seen or (self.with_table and table_changed):
             self.fn()
             self.seen = v
             return True
         return False
+
+
+def _param(mod: nn.Module, name: str):
+    """mod.<name> for a registered parameter / buffer without nn.Module.__getattr__'s slow path (the version scan below
+    touches ~600 tensors on every forward call)."""
+    t = mod._parameters.get(name)
+    if t is None:
+        t = mod._buffers.get(name)
+    return t if t is not None else getattr(mod, name)
 
 
 class WeightTable:
@@ -104,7 +117,7 @@ class WeightTable:
         for j in self.epi:
             if j["bn"] is not None:
                 bn = j["bn"]
-                ts.extend([bn.weight, bn.bias, bn.running_mean, bn.running_var])
+                ts.extend([_param(bn, "weight"), _param(bn, "bias"), _param(bn, "running_mean"), _param(bn, "running_var")])
             if j["bias"] is not None:
                 ts.append(j["bias"]())
         return ts
@@ -267,7 +280,7 @@ class Builder:
         pc = PackedConv(wbuf, scale, shift, kh, kw, cout, cin, co_r, ci_r, self.mode, fold)
         bias = (lambda: conv.bias) if (bn is None and conv.bias is not None) else None
         wt.add_epilogue(scale, shift, co_r, bn=bn, bias=bias, fold_scale=fold)
-        wt.add_pack(lambda: conv.weight, wbuf, cout, cin, row_scale=fold,
+        wt.add_pack(lambda: _param(conv, "weight"), wbuf, cout, cin, row_scale=fold,
                     scale_period=bn.num_features if bn is not None else 1, weight_fn=weight_fn,
                     watch=list(extra_sources))
         return pc
@@ -293,7 +306,7 @@ class Builder:
             fold = torch.empty(bn.num_features, dtype=torch.float32, device=self.device)
             period = bn.num_features
         wt.add_epilogue(scale, shift, co_r, bn=bn, fold_scale=fold if bn is not None else None)
-        wt.add_pack(lambda: conv.weight, wbuf, rows, cols, transpose=True, ci_off=ci_off, cin_slice=ci_r, row_scale=fold,
+        wt.add_pack(lambda: _param(conv, "weight"), wbuf, rows, cols, transpose=True, ci_off=ci_off, cin_slice=ci_r, row_scale=fold,
                     scale_period=period, weight_fn=weight_fn, watch=list(extra_sources))
         return wbuf, shift
 
@@ -329,9 +342,9 @@ class Plan:
         self.outputs = list(outputs)
 
     def refresh_weights(self) -> bool:
-        changed = self.weights.refresh()
+        changed = table_changed = self.weights.refresh()
         for j in self.pack_jobs:
-            changed |= j.refresh()
+            changed |= j.refresh(table_changed)
         return changed
 
     def _launch_all(self) -> None:

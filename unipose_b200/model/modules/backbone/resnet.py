@@ -158,10 +158,10 @@ class Bottleneck(PlanModule):
         wt = b.plan.weights
         wt.add_epilogue(scale_d, shift_d, cout, bn=bn_d, fold_scale=fold_d)
         for j in range(pt):          # slice j of the projection's input channels = filter "tap" 1 + j
-            wt.add_pack(lambda: conv_d.weight, wbuf[0, 1 + j], cout, planes, ci_off=j * planes, cin_slice=planes,
+            wt.add_pack(lambda: engine._param(conv_d, "weight"), wbuf[0, 1 + j], cout, planes, ci_off=j * planes, cin_slice=planes,
                         row_scale=fold_d, scale_period=bn_d.num_features)
-        bns = [t for bn in (self.bn3, bn_d) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var)]
-        b.plan.pack_jobs.append(engine._PackJob(bns, lambda: torch.add(pc3.shift, shift_d, out=shift_sum)))
+        # both shifts are table outputs: the sum follows every table refresh (changed or replaced BatchNorm tensors)
+        b.plan.pack_jobs.append(engine._PackJob((), lambda: torch.add(pc3.shift, shift_d, out=shift_sum), with_table=True))
         b.plan.buffers.append((wbuf, scale_d, shift_d, fold_d))
         return ops.PackedConv(wbuf, pc3.scale, shift_sum, 1, 1, cout, planes, cout, planes, b.mode)
 
